@@ -1,0 +1,91 @@
+// Shared helpers for the ddpm3d CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+
+#include "../../include/ddpm3d.h"
+
+namespace ddpm3d {
+
+void set_error(const std::string& msg);
+
+#define DD_CUDA(expr)                                                                           \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      ::ddpm3d::set_error(std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" __FILE__ + \
+                          ":" + std::to_string(__LINE__) + ")");                                \
+      return DDPM3D_ERR_CUDA;                                                                   \
+    }                                                                                           \
+  } while (0)
+
+#define DD_CHECK(cond, code, msg)         \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::ddpm3d::set_error(msg);           \
+      return (code);                      \
+    }                                     \
+  } while (0)
+
+#define DD_TRY(expr)            \
+  do {                          \
+    int r__ = (expr);           \
+    if (r__ != DDPM3D_OK) return r__; \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- scalar conversions ------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- 16-byte vectors of activations ---------------------------------------------------------
+// A "vec" is 16 bytes: 4 floats or 8 bf16.  All channel counts on the path are multiples of 8
+// except the 2-channel network input / output, which have their own kernels.
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  float4 raw;
+  __device__ __forceinline__ void load(const float* p) { raw = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = raw; }
+  __device__ __forceinline__ void unpack(float* f) const { f[0] = raw.x; f[1] = raw.y; f[2] = raw.z; f[3] = raw.w; }
+  __device__ __forceinline__ void pack(const float* f) { raw = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <> struct Vec<bf16> {
+  static constexpr int N = 8;
+  uint4 raw;
+  __device__ __forceinline__ void load(const bf16* p) { raw = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(bf16* p) const { *reinterpret_cast<uint4*>(p) = raw; }
+  __device__ __forceinline__ void unpack(float* f) const {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ __forceinline__ void pack(const float* f) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    raw = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// accurate expf: the GN/SiLU kernels are HBM-bound, the extra ALU is hidden
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+
+}  // namespace ddpm3d

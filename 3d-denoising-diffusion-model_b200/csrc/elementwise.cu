@@ -1,0 +1,622 @@
+// HBM-bound kernels of the path: input packing, GroupNorm32(+FiLM)(+SiLU)(+pool/upsample),
+// timestep embedding MLPs and the p_sample posterior update.  sm_100a; fp32 math everywhere.
+#include "kernels.h"
+
+namespace ddpm3d {
+
+// =================================================================================================
+// pack_input: cat([x, low_res], dim=1) + cast (unet.py:1690-1693, :1035)
+// =================================================================================================
+template <typename T>
+__global__ void pack_input_kernel(const float* __restrict__ x, const float* __restrict__ low, T* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    out[2 * i] = from_f32<T>(x[i]);
+    out[2 * i + 1] = from_f32<T>(low[i]);
+  }
+}
+
+int pack_input(int dt, const float* x, const float* low, void* out, int64_t n, cudaStream_t s) {
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>(ceil_div(n, threads), 148 * 16);
+  if (dt == DDPM3D_BF16)
+    pack_input_kernel<bf16><<<blocks, threads, 0, s>>>(x, low, (bf16*)out, n);
+  else
+    pack_input_kernel<float><<<blocks, threads, 0, s>>>(x, low, (float*)out, n);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
+// =================================================================================================
+// GroupNorm32 (nn.py:17-19,93-100): statistics in fp32 over (C/32, Z, H, W) per batch element.
+// Pass 1 (stats): per-chunk partial [sum, sumsq] per group, fixed summation order (deterministic).
+// Pass 2 (finalize): fp64 reduction over chunks -> per-(b,c) affine  y = x*A + B  with gamma/beta,
+//                    FiLM (unet.py:248-252) and the additive-embedding variant folded in.
+// Pass 3 (apply):    y -> SiLU -> optional AvgPool(1,2,2) / nearest x2 -> store.
+// Algorithmic HBM bytes: 2 reads + 1 write of the tensor.
+// =================================================================================================
+int gn_chunks(int64_t rows) {
+  int64_t c = rows / 256;
+  if (c < 1) c = 1;
+  if (c > 1024) c = 1024;
+  return (int)c;
+}
+
+template <typename T>
+__global__ void gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int C1, int64_t rows,
+                                int n_chunks, const float* __restrict__ pre_add, int64_t pre_stride,
+                                float* __restrict__ partials) {
+  constexpr int N = Vec<T>::N;
+  extern __shared__ float sm[];  // [rpi][Ctot][2]
+  const int Ctot = C0 + C1;
+  const int nvec0 = C0 / N, nvec = Ctot / N;
+  const int rpi = blockDim.x / nvec;
+  const int v = threadIdx.x % nvec, r = threadIdx.x / nvec;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int64_t per = ceil_div(rows, (int64_t)n_chunks);
+  const int64_t r0 = chunk * per, r1 = min(rows, r0 + per);
+
+  const T* base;
+  int Csrc, coff;
+  if (v < nvec0) { base = s0; Csrc = C0; coff = v * N; }
+  else { base = s1; Csrc = C1; coff = (v - nvec0) * N; }
+  base += (int64_t)b * rows * Csrc + coff;
+
+  float add[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) add[i] = 0.f;
+  if (pre_add) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) add[i] = pre_add[(int64_t)b * pre_stride + v * N + i];
+  }
+
+  float s[N], q[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  int64_t row = r0 + r;
+  // 4 independent 16-byte loads in flight per thread
+  for (; row + 3 * rpi < r1; row += 4 * rpi) {
+    Vec<T> a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u].load(base + (row + (int64_t)u * rpi) * Csrc);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[N];
+      a[u].unpack(f);
+#pragma unroll
+      for (int i = 0; i < N; ++i) { const float x = f[i] + add[i]; s[i] += x; q[i] += x * x; }
+    }
+  }
+  for (; row < r1; row += rpi) {
+    Vec<T> a;
+    a.load(base + row * Csrc);
+    float f[N];
+    a.unpack(f);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { const float x = f[i] + add[i]; s[i] += x; q[i] += x * x; }
+  }
+  float* mine = sm + ((int64_t)r * Ctot + v * N) * 2;
+#pragma unroll
+  for (int i = 0; i < N; ++i) { mine[2 * i] = s[i]; mine[2 * i + 1] = q[i]; }
+  __syncthreads();
+  // group g sums its channels over the rpi row-lanes in a fixed order
+  const int gpc = Ctot / 32;
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    float acc = 0.f;
+    for (int rr = 0; rr < rpi; ++rr)
+      for (int c = g * gpc; c < (g + 1) * gpc; ++c) acc += sm[((int64_t)rr * Ctot + c) * 2 + which];
+    partials[(((int64_t)b * n_chunks + chunk) * 32 + g) * 2 + which] = acc;
+  }
+}
+
+__global__ void gn_finalize_kernel(const float* __restrict__ partials, int n_chunks, int Ctot, double inv_count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ film, int64_t film_stride,
+                                   const float* __restrict__ pre_add, int64_t pre_stride, float* __restrict__ ab) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int b = blockIdx.x;
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 1024 threads: one warp per group
+  double s = 0.0, q = 0.0;
+  for (int c = lane; c < n_chunks; c += 32) {
+    const float* p = partials + (((int64_t)b * n_chunks + c) * 32 + g) * 2;
+    s += (double)p[0];
+    q += (double)p[1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const double mean = s * inv_count;
+    double var = q * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = (float)mean;
+    s_rstd[g] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  const int gpc = Ctot / 32;
+  float* A = ab + (int64_t)b * 2 * Ctot;
+  float* Bv = A + Ctot;
+  for (int c = threadIdx.x; c < Ctot; c += blockDim.x) {
+    const int gg = c / gpc;
+    float a = s_rstd[gg] * gamma[c];
+    float o = beta[c] - s_mean[gg] * a;
+    if (film) {  // h = norm(h) * (1 + scale) + shift
+      const float sc = 1.0f + film[(int64_t)b * film_stride + c];
+      const float sh = film[(int64_t)b * film_stride + Ctot + c];
+      a *= sc;
+      o = o * sc + sh;
+    }
+    if (pre_add) o += pre_add[(int64_t)b * pre_stride + c] * a;  // norm(h + e) = h*a + (e*a + o)
+    A[c] = a;
+    Bv[c] = o;
+  }
+}
+
+template <typename T, typename TO, int MODE, bool SILU>
+__global__ void gn_apply_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int C1, int B, int Z, int H,
+                                int W, const float* __restrict__ ab, TO* __restrict__ out) {
+  constexpr int N = Vec<T>::N;
+  const int Ctot = C0 + C1;
+  const int nvec0 = C0 / N, nvec = Ctot / N;
+  const int Ho = MODE == RS_POOL ? H / 2 : H, Wo = MODE == RS_POOL ? W / 2 : W;
+  // iteration space: output rows for NONE/POOL, input rows for UP
+  const int64_t rows_it = (int64_t)B * Z * Ho * Wo;
+  const int64_t total = rows_it * nvec;
+  const int64_t rows_b_it = (int64_t)Z * Ho * Wo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const int64_t row = i / nvec;
+    const int b = (int)(row / rows_b_it);
+    const T* base;
+    int Csrc, coff;
+    if (v < nvec0) { base = s0; Csrc = C0; coff = v * N; }
+    else { base = s1; Csrc = C1; coff = (v - nvec0) * N; }
+    float A[N], Bv[N];
+    {
+      const float* pa = ab + (int64_t)b * 2 * Ctot + v * N;
+#pragma unroll
+      for (int k = 0; k < N; k += 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(pa + k);
+        const float4 b4 = *reinterpret_cast<const float4*>(pa + Ctot + k);
+        A[k] = a4.x; A[k + 1] = a4.y; A[k + 2] = a4.z; A[k + 3] = a4.w;
+        Bv[k] = b4.x; Bv[k + 1] = b4.y; Bv[k + 2] = b4.z; Bv[k + 3] = b4.w;
+      }
+    }
+    float y[N];
+    if (MODE == RS_POOL) {
+      const int wo = (int)(row % Wo);
+      const int64_t t1 = row / Wo;
+      const int ho = (int)(t1 % Ho);
+      const int64_t bz = t1 / Ho;  // b*Z + z
+      const int64_t in_row = (bz * H + 2 * ho) * W + 2 * wo;
+      Vec<T> a[4];
+      a[0].load(base + in_row * Csrc + coff);
+      a[1].load(base + (in_row + 1) * Csrc + coff);
+      a[2].load(base + (in_row + W) * Csrc + coff);
+      a[3].load(base + (in_row + W + 1) * Csrc + coff);
+#pragma unroll
+      for (int k = 0; k < N; ++k) y[k] = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[N];
+        a[u].unpack(f);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          float t = f[k] * A[k] + Bv[k];
+          if (SILU) t = silu_f(t);
+          y[k] += t;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < N; ++k) y[k] *= 0.25f;
+    } else {
+      Vec<T> a;
+      a.load(base + row * Csrc + coff);
+      float f[N];
+      a.unpack(f);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        float t = f[k] * A[k] + Bv[k];
+        if (SILU) t = silu_f(t);
+        y[k] = t;
+      }
+    }
+    // store (fp32 output uses two 16-byte stores when N == 8)
+    auto put = [&](int64_t orow) {
+      TO* dst = out + orow * Ctot + v * N;
+      if constexpr (sizeof(TO) == sizeof(T)) {
+        Vec<TO> o;
+        o.pack(y);
+        o.store(dst);
+      } else {  // T = bf16, TO = float
+#pragma unroll
+        for (int k = 0; k < N; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(y[k], y[k + 1], y[k + 2], y[k + 3]);
+      }
+    };
+    if (MODE == RS_UP) {
+      const int w = (int)(row % W);
+      const int64_t t1 = row / W;
+      const int h = (int)(t1 % H);
+      const int64_t bz = t1 / H;
+      const int64_t o0 = (bz * (2 * H) + 2 * h) * (2 * W) + 2 * w;
+      put(o0); put(o0 + 1); put(o0 + 2 * W); put(o0 + 2 * W + 1);
+    } else {
+      put(row);
+    }
+  }
+}
+
+template <typename T, typename TO>
+static int gn_apply_launch(const GnArgs& a, cudaStream_t s) {
+  constexpr int N = Vec<T>::N;
+  const int Ctot = a.C[0] + a.C[1];
+  const int Ho = a.resample == RS_POOL ? a.H / 2 : a.H, Wo = a.resample == RS_POOL ? a.W / 2 : a.W;
+  const int64_t total = (int64_t)a.B * a.Z * Ho * Wo * (Ctot / N);
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>(ceil_div(total, threads), 148 * 32);
+  const T* s0 = (const T*)a.src[0];
+  const T* s1 = (const T*)a.src[1];
+#define GN_LAUNCH(MODE, SILU) \
+  gn_apply_kernel<T, TO, MODE, SILU><<<blocks, threads, 0, s>>>(s0, s1, a.C[0], a.C[1], a.B, a.Z, a.H, a.W, a.ab, (TO*)a.out)
+  if (a.silu) {
+    if (a.resample == RS_NONE) GN_LAUNCH(RS_NONE, true);
+    else if (a.resample == RS_POOL) GN_LAUNCH(RS_POOL, true);
+    else GN_LAUNCH(RS_UP, true);
+  } else {
+    if (a.resample == RS_NONE) GN_LAUNCH(RS_NONE, false);
+    else if (a.resample == RS_POOL) GN_LAUNCH(RS_POOL, false);
+    else GN_LAUNCH(RS_UP, false);
+  }
+#undef GN_LAUNCH
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
+template <typename T>
+static int gn_stats_launch(const GnArgs& a, cudaStream_t s) {
+  constexpr int N = Vec<T>::N;
+  const int Ctot = a.C[0] + a.C[1];
+  const int nvec = Ctot / N;
+  int rpi = 256 / nvec;
+  if (rpi < 1) rpi = 1;
+  const int threads = nvec * rpi;
+  DD_CHECK(threads <= 1024 && threads >= 64, DDPM3D_ERR_ARG, "groupnorm: unsupported channel count");
+  const int64_t rows = (int64_t)a.Z * a.H * a.W;
+  const size_t smem = (size_t)rpi * Ctot * 2 * sizeof(float);
+  dim3 grid(a.n_chunks, a.B);
+  gn_stats_kernel<T><<<grid, threads, smem, s>>>((const T*)a.src[0], (const T*)a.src[1], a.C[0], a.C[1], rows, a.n_chunks,
+                                                 a.pre_add, a.pre_stride, a.partials);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
+int gn_forward(const GnArgs& a, cudaStream_t s, int* launches) {
+  const int Ctot = a.C[0] + a.C[1];
+  const int N = a.dt == DDPM3D_BF16 ? 8 : 4;
+  DD_CHECK(Ctot % 32 == 0, DDPM3D_ERR_ARG, "groupnorm: channels must be a multiple of 32");
+  DD_CHECK(a.C[0] % N == 0 && a.C[1] % N == 0, DDPM3D_ERR_ARG, "groupnorm: per-source channels must fill 16-byte vectors");
+  DD_CHECK(a.resample != RS_POOL || (a.H % 2 == 0 && a.W % 2 == 0), DDPM3D_ERR_ARG, "groupnorm: pool needs even H, W");
+  DD_CHECK(!(a.out_f32 && a.dt == DDPM3D_FP32 && false), DDPM3D_ERR_ARG, "");
+  if (a.dt == DDPM3D_BF16) DD_TRY(gn_stats_launch<bf16>(a, s));
+  else DD_TRY(gn_stats_launch<float>(a, s));
+  const double inv_count = 1.0 / ((double)a.Z * a.H * a.W * (Ctot / 32));
+  gn_finalize_kernel<<<a.B, 1024, 0, s>>>(a.partials, a.n_chunks, Ctot, inv_count, a.gamma, a.beta, a.film, a.film_stride,
+                                          a.pre_add, a.pre_stride, a.ab);
+  DD_CUDA(cudaGetLastError());
+  if (a.dt == DDPM3D_BF16) {
+    if (a.out_f32) DD_TRY((gn_apply_launch<bf16, float>(a, s)));
+    else DD_TRY((gn_apply_launch<bf16, bf16>(a, s)));
+  } else {
+    DD_TRY((gn_apply_launch<float, float>(a, s)));
+  }
+  if (launches) *launches += 3;
+  return DDPM3D_OK;
+}
+
+// =================================================================================================
+// plain nearest x2 / avg-pool on (H, W)  (Upsample/Downsample without conv, unet.py:81-140)
+// =================================================================================================
+template <typename T, int MODE>
+__global__ void resample_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int Z, int H, int W, int C) {
+  constexpr int N = Vec<T>::N;
+  const int nvec = C / N;
+  const int Ho = MODE == RS_POOL ? H / 2 : H, Wo = MODE == RS_POOL ? W / 2 : W;
+  const int64_t total = (int64_t)B * Z * Ho * Wo * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const int64_t row = i / nvec;
+    if (MODE == RS_POOL) {
+      const int wo = (int)(row % Wo);
+      const int64_t t1 = row / Wo;
+      const int ho = (int)(t1 % Ho);
+      const int64_t bz = t1 / Ho;
+      const int64_t r = (bz * H + 2 * ho) * W + 2 * wo;
+      float acc[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) acc[k] = 0.f;
+      const int64_t rr[4] = {r, r + 1, r + W, r + W + 1};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        Vec<T> a;
+        a.load(in + rr[u] * C + v * N);
+        float f[N];
+        a.unpack(f);
+#pragma unroll
+        for (int k = 0; k < N; ++k) acc[k] += f[k];
+      }
+#pragma unroll
+      for (int k = 0; k < N; ++k) acc[k] *= 0.25f;
+      Vec<T> o;
+      o.pack(acc);
+      o.store(out + row * C + v * N);
+    } else {
+      Vec<T> a;
+      a.load(in + row * C + v * N);
+      const int w = (int)(row % W);
+      const int64_t t1 = row / W;
+      const int h = (int)(t1 % H);
+      const int64_t bz = t1 / H;
+      const int64_t o0 = (bz * (2 * H) + 2 * h) * (2 * W) + 2 * w;
+      a.store(out + o0 * C + v * N);
+      a.store(out + (o0 + 1) * C + v * N);
+      a.store(out + (o0 + 2 * W) * C + v * N);
+      a.store(out + (o0 + 2 * W + 1) * C + v * N);
+    }
+  }
+}
+
+int resample_hw(int dt, const void* in, void* out, int B, int Z, int H, int W, int C, int mode, cudaStream_t s) {
+  const int N = dt == DDPM3D_BF16 ? 8 : 4;
+  DD_CHECK(C % N == 0, DDPM3D_ERR_ARG, "resample: channels must fill 16-byte vectors");
+  DD_CHECK(mode == RS_POOL || mode == RS_UP, DDPM3D_ERR_ARG, "resample: bad mode");
+  const int Ho = mode == RS_POOL ? H / 2 : H, Wo = mode == RS_POOL ? W / 2 : W;
+  const int64_t total = (int64_t)B * Z * Ho * Wo * (C / N);
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>(ceil_div(total, threads), 148 * 32);
+  if (dt == DDPM3D_BF16) {
+    if (mode == RS_POOL) resample_kernel<bf16, RS_POOL><<<blocks, threads, 0, s>>>((const bf16*)in, (bf16*)out, B, Z, H, W, C);
+    else resample_kernel<bf16, RS_UP><<<blocks, threads, 0, s>>>((const bf16*)in, (bf16*)out, B, Z, H, W, C);
+  } else {
+    if (mode == RS_POOL) resample_kernel<float, RS_POOL><<<blocks, threads, 0, s>>>((const float*)in, (float*)out, B, Z, H, W, C);
+    else resample_kernel<float, RS_UP><<<blocks, threads, 0, s>>>((const float*)in, (float*)out, B, Z, H, W, C);
+  }
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
+// =================================================================================================
+// timestep embedding (nn.py:103-121) and the embedding MLPs (unet.py:798-803,199-205)
+// =================================================================================================
+__device__ __forceinline__ float temb_value(float t, int j, int dim) {
+  const int half = dim / 2;
+  if (j >= 2 * half) return 0.f;  // odd dim: zero pad
+  const int i = j < half ? j : j - half;
+  // th.exp(-math.log(max_period) * arange(half, fp32) / half): fp32 mul, fp32 div, exp
+  const float freq = expf(__fdiv_rn(__fmul_rn(-9.210340371976184f, (float)i), (float)half));
+  const float ang = __fmul_rn(t, freq);
+  return j < half ? cosf(ang) : sinf(ang);
+}
+
+__global__ void temb_kernel(const float* __restrict__ t, float* __restrict__ out, int dim) {
+  const int b = blockIdx.x;
+  for (int j = threadIdx.x; j < dim; j += blockDim.x) out[(int64_t)b * dim + j] = temb_value(t[b], j, dim);
+}
+
+int timestep_embedding_k(const float* t, float* out, int B, int dim, cudaStream_t s) {
+  temb_kernel<<<B, 128, 0, s>>>(t, out, dim);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one CTA per batch element: sinusoid -> Linear -> SiLU -> Linear (+label_emb) -> SiLU
+__global__ void time_embed_kernel(EmbArgs a) {
+  extern __shared__ float sm[];  // e0[mc] | h1[ted]
+  float* e0 = sm;
+  float* h1 = sm + a.model_channels;
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const float t = a.t[b];
+  for (int j = threadIdx.x; j < a.model_channels; j += blockDim.x) e0[j] = temb_value(t, j, a.model_channels);
+  __syncthreads();
+  for (int r = warp; r < a.ted; r += nwarp) {
+    const float* w = a.w0 + (int64_t)r * a.model_channels;
+    float acc = 0.f;
+    for (int k = lane; k < a.model_channels; k += 32) acc += w[k] * e0[k];
+    acc = warp_sum(acc);
+    if (lane == 0) h1[r] = silu_f(acc + a.b0[r]);
+  }
+  __syncthreads();
+  for (int r = warp; r < a.ted; r += nwarp) {
+    const float* w = a.w2 + (int64_t)r * a.ted;
+    float acc = 0.f;
+    for (int k = lane; k < a.ted; k += 32) acc += w[k] * h1[k];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float e = acc + a.b2[r];
+      if (a.label_emb) e += a.label_emb[a.y[b] * (int64_t)a.ted + r];  // unet.py:1031-1033
+      a.emb_silu[(int64_t)b * a.ted + r] = silu_f(e);
+    }
+  }
+}
+
+// every ResBlock's emb_layers Linear at once: one warp per output row (weights read once for all b)
+__global__ void emb_layers_kernel(EmbArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= a.rows_total) return;
+  const float* w = a.w_all + (int64_t)warp * a.ted;
+  for (int b = 0; b < a.B; ++b) {
+    const float* e = a.emb_silu + (int64_t)b * a.ted;
+    float acc = 0.f;
+    for (int k = lane; k < a.ted; k += 32) acc += w[k] * e[k];
+    acc = warp_sum(acc);
+    if (lane == 0) a.emb_out[(int64_t)b * a.rows_total + warp] = acc + a.b_all[warp];
+  }
+}
+
+int embedding_forward(const EmbArgs& a, cudaStream_t s, int* launches) {
+  const size_t smem = (size_t)(a.model_channels + a.ted) * sizeof(float);
+  time_embed_kernel<<<a.B, 512, smem, s>>>(a);
+  DD_CUDA(cudaGetLastError());
+  if (a.rows_total > 0) {
+    const int threads = 256;
+    const int blocks = (int)ceil_div((int64_t)a.rows_total * 32, threads);
+    emb_layers_kernel<<<blocks, threads, 0, s>>>(a);
+    DD_CUDA(cudaGetLastError());
+  }
+  if (launches) *launches += 2;
+  return DDPM3D_OK;
+}
+
+// =================================================================================================
+// p_sample posterior update (gaussian_diffusion.py:262-326, 430-438): one elementwise kernel.
+// Every mul/add is an explicit round-to-nearest intrinsic so nothing is contracted into an FMA:
+// the result matches the reference's separate torch ops bit for bit except for exp().
+// Algorithmic HBM bytes per voxel: read x, eps, v, noise (16 B) + write x_{t-1} (4 B) = 20 B.
+// =================================================================================================
+struct Philox {
+  // Philox4x32-10, counter = (idx_lo, idx_hi, step, 0), key = seed
+  __device__ static uint4 rand4(uint64_t seed, uint64_t idx, uint32_t step) {
+    uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = step, c3 = 0;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+      const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+      const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+      c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+  __device__ static void normal4(uint64_t seed, uint64_t idx, uint32_t step, float* z) {
+    const uint4 r = rand4(seed, idx, step);
+    const float u0 = ((float)r.x + 0.5f) * 2.3283064365386963e-10f, u1 = ((float)r.y + 0.5f) * 2.3283064365386963e-10f;
+    const float u2 = ((float)r.z + 0.5f) * 2.3283064365386963e-10f, u3 = ((float)r.w + 0.5f) * 2.3283064365386963e-10f;
+    const float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+    float s0, c0, s1, c1;
+    sincospif(2.0f * u1, &s0, &c0);
+    sincospif(2.0f * u3, &s1, &c1);
+    z[0] = ra * c0; z[1] = ra * s0; z[2] = rb * c1; z[3] = rb * s1;
+  }
+};
+
+template <int MEAN, int VAR, bool CLIP>
+__global__ void p_sample_update_kernel(UpdateArgs a) {
+  const int64_t per_b = (int64_t)a.C * a.n;  // multiple of 4 (checked by the launcher)
+  const int64_t total4 = (int64_t)a.B * per_b / 4;
+  int exec = 0, cur = -1;
+  if (a.step_counter) { cur = a.step_counter[0]; exec = a.step_counter[1]; }
+  const float* noise = a.noise ? a.noise + (int64_t)exec * a.noise_step_stride : nullptr;
+  constexpr bool LEARNED = (VAR == DDPM3D_VAR_LEARNED || VAR == DDPM3D_VAR_LEARNED_RANGE);
+  for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i4 * 4;
+    const int b = (int)(i / per_b);
+    const int64_t off = i - (int64_t)b * per_b;  // c*n + j
+    const int ti = a.t_index ? a.t_index[b] : cur;
+    const ddpm3d_step_scalars sc = a.table[ti];
+    const int64_t mo_base = (int64_t)b * (LEARNED ? 2 : 1) * per_b + off;
+    const float4 x4 = *reinterpret_cast<const float4*>(a.x + i);
+    const float4 m4 = *reinterpret_cast<const float4*>(a.model_out + mo_base);
+    float4 v4 = make_float4(0, 0, 0, 0);
+    if (LEARNED) v4 = *reinterpret_cast<const float4*>(a.model_out + mo_base + per_b);
+    float z[4];
+    if (noise) {
+      const float4 n4 = *reinterpret_cast<const float4*>(noise + i);
+      z[0] = n4.x; z[1] = n4.y; z[2] = n4.z; z[3] = n4.w;
+    } else {
+      Philox::normal4(a.seed, (uint64_t)i4, (uint32_t)exec, z);
+    }
+    const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ms[4] = {m4.x, m4.y, m4.z, m4.w}, vs[4] = {v4.x, v4.y, v4.z, v4.w};
+    float smp[4], x0s[4], mus[4], lvs[4];
+    const float mask = ti != 0 ? 1.0f : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float logvar;
+      if (VAR == DDPM3D_VAR_LEARNED) {
+        logvar = vs[k];
+      } else if (VAR == DDPM3D_VAR_LEARNED_RANGE) {
+        const float frac = __fdiv_rn(__fadd_rn(vs[k], 1.0f), 2.0f);
+        logvar = __fadd_rn(__fmul_rn(frac, sc.max_log), __fmul_rn(__fsub_rn(1.0f, frac), sc.min_log));
+      } else {
+        logvar = sc.fixed_log_variance;
+      }
+      float x0, mu;
+      if (MEAN == DDPM3D_MEAN_PREVIOUS_X) {
+        x0 = __fsub_rn(__fmul_rn(sc.recip_coef1, ms[k]), __fmul_rn(sc.coef2_over_coef1, xs[k]));
+        if (CLIP) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+        mu = ms[k];
+      } else {
+        if (MEAN == DDPM3D_MEAN_START_X) x0 = ms[k];
+        else x0 = __fsub_rn(__fmul_rn(sc.sqrt_recip_alphas_cumprod, xs[k]), __fmul_rn(sc.sqrt_recipm1_alphas_cumprod, ms[k]));
+        if (CLIP) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+        mu = __fadd_rn(__fmul_rn(sc.posterior_mean_coef1, x0), __fmul_rn(sc.posterior_mean_coef2, xs[k]));
+      }
+      const float sd = expf(__fmul_rn(0.5f, logvar));
+      smp[k] = __fadd_rn(mu, __fmul_rn(__fmul_rn(mask, sd), z[k]));
+      x0s[k] = x0; mus[k] = mu; lvs[k] = logvar;
+    }
+    *reinterpret_cast<float4*>(a.sample + i) = make_float4(smp[0], smp[1], smp[2], smp[3]);
+    if (a.pred_xstart) *reinterpret_cast<float4*>(a.pred_xstart + i) = make_float4(x0s[0], x0s[1], x0s[2], x0s[3]);
+    if (a.mean) *reinterpret_cast<float4*>(a.mean + i) = make_float4(mus[0], mus[1], mus[2], mus[3]);
+    if (a.log_variance) *reinterpret_cast<float4*>(a.log_variance + i) = make_float4(lvs[0], lvs[1], lvs[2], lvs[3]);
+  }
+}
+
+template <int MEAN, int VAR>
+static void update_launch(const UpdateArgs& a, int blocks, int threads, cudaStream_t s) {
+  if (a.clip) p_sample_update_kernel<MEAN, VAR, true><<<blocks, threads, 0, s>>>(a);
+  else p_sample_update_kernel<MEAN, VAR, false><<<blocks, threads, 0, s>>>(a);
+}
+template <int MEAN>
+static int update_dispatch_var(const UpdateArgs& a, int blocks, int threads, cudaStream_t s) {
+  switch (a.var_type) {
+    case DDPM3D_VAR_LEARNED: update_launch<MEAN, DDPM3D_VAR_LEARNED>(a, blocks, threads, s); break;
+    case DDPM3D_VAR_LEARNED_RANGE: update_launch<MEAN, DDPM3D_VAR_LEARNED_RANGE>(a, blocks, threads, s); break;
+    case DDPM3D_VAR_FIXED_SMALL:
+    case DDPM3D_VAR_FIXED_LARGE: update_launch<MEAN, DDPM3D_VAR_FIXED_SMALL>(a, blocks, threads, s); break;
+    default: set_error("p_sample_update: bad var_type"); return DDPM3D_ERR_ARG;
+  }
+  return DDPM3D_OK;
+}
+
+int p_sample_update_k(const UpdateArgs& a, cudaStream_t s) {
+  DD_CHECK(((int64_t)a.C * a.n) % 4 == 0, DDPM3D_ERR_ARG, "p_sample_update: C*n_spatial must be a multiple of 4");
+  DD_CHECK(a.table != nullptr, DDPM3D_ERR_STATE, "p_sample_update: schedule not set");
+  const int64_t total4 = (int64_t)a.B * a.C * a.n / 4;
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>(ceil_div(total4, threads), 148 * 16);
+  switch (a.mean_type) {
+    case DDPM3D_MEAN_PREVIOUS_X: DD_TRY(update_dispatch_var<DDPM3D_MEAN_PREVIOUS_X>(a, blocks, threads, s)); break;
+    case DDPM3D_MEAN_START_X: DD_TRY(update_dispatch_var<DDPM3D_MEAN_START_X>(a, blocks, threads, s)); break;
+    case DDPM3D_MEAN_EPSILON: DD_TRY(update_dispatch_var<DDPM3D_MEAN_EPSILON>(a, blocks, threads, s)); break;
+    default: set_error("p_sample_update: bad mean_type"); return DDPM3D_ERR_ARG;
+  }
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
+// step bookkeeping for the device-resident loop: counter = {current index i, executed steps k}
+__global__ void step_advance_kernel(int32_t* counter, float* t_model, const ddpm3d_step_scalars* table, int B) {
+  const int next = counter[0] - 1;
+  if (threadIdx.x == 0) { counter[0] = next; counter[1] = counter[1] + 1; }
+  if (next >= 0)
+    for (int b = threadIdx.x; b < B; b += blockDim.x) t_model[b] = table[next].model_t;
+}
+
+int step_advance_k(int32_t* counter, float* t_model, const ddpm3d_step_scalars* table, int B, cudaStream_t s) {
+  step_advance_kernel<<<1, 32, 0, s>>>(counter, t_model, table, B);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
+}  // namespace ddpm3d

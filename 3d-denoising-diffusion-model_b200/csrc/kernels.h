@@ -1,0 +1,107 @@
+// Launchers of every device kernel on the path.  All tensors are channels-last (NDHWC) unless
+// stated.  `dt` is DDPM3D_FP32 or DDPM3D_BF16 and selects the activation / conv-weight element.
+#pragma once
+
+#include "common.cuh"
+
+namespace ddpm3d {
+
+// Residual handling in the conv epilogue (ResBlock skip path, unet.py:238-256).
+enum ResMode { RES_NONE = 0, RES_SAME = 1, RES_POOL = 2 /* avg 2x2 of a (2Ho,2Wo) tensor */, RES_UP = 3 /* nearest from (Ho/2,Wo/2) */ };
+// Resampling of a GroupNorm/SiLU result before it is written (h_upd, unet.py:240-242).
+enum Resample { RS_NONE = 0, RS_POOL = 1, RS_UP = 2 };
+
+struct ConvSrc {
+  const void* ptr = nullptr;  // [B][Z][Hin][Win][C]
+  int C = 0;
+};
+
+struct ConvArgs {
+  int dt = DDPM3D_FP32;       // element type of main/extra sources and of w
+  ConvSrc main;               // 3x3x3 (taps=27) or 1x1x1 (taps=1) source
+  int taps = 27;
+  int stride_hw = 1;          // Downsample(use_conv=True): (1,2,2)  (unet.py:129-133)
+  ConvSrc extra[2];           // 1x1x1 sources appended along K (skip_connection folded in; K11 concat elision)
+  int n_extra = 0;
+  const void* w = nullptr;    // [Cout][Ktot], Ktot = taps*main.C + sum(extra.C); k = tap*C + ci
+  const float* bias = nullptr;  // [Cout] (already includes the folded skip bias)
+  const void* residual = nullptr;  // element type dt
+  int res_mode = RES_NONE;
+  void* out = nullptr;        // dt, channels-last; or fp32 planar NCDHW when out_planar_f32
+  int out_planar_f32 = 0;
+  int B = 0, Z = 0, Ho = 0, Wo = 0, Cout = 0;  // output geometry; input H/W = Ho*stride
+};
+
+int conv_simt(const ConvArgs& a, cudaStream_t s);
+// tcgen05 path; returns DDPM3D_ERR_ARG (without launching) when the shape is not eligible.
+bool conv_tc_eligible(const ConvArgs& a);
+int conv_tc(const ConvArgs& a, cudaStream_t s);
+
+// ---- GroupNorm32 + FiLM + SiLU (K4/K5/K6) ------------------------------------------------------
+struct GnArgs {
+  int dt = DDPM3D_FP32;
+  const void* src[2] = {nullptr, nullptr};  // virtual channel concat of up to two tensors (K11)
+  int C[2] = {0, 0};
+  int B = 0, Z = 0, H = 0, W = 0;           // input geometry
+  const float* gamma = nullptr;             // [Ctot]
+  const float* beta = nullptr;
+  const float* film = nullptr;              // [B][film_stride] : scale at +0, shift at +Ctot (unet.py:248-252); or NULL
+  int64_t film_stride = 0;
+  const float* pre_add = nullptr;           // [B][pre_stride]: h + emb_out before the norm (use_scale_shift_norm=False, unet.py:253-255)
+  int64_t pre_stride = 0;
+  int silu = 1;
+  int resample = RS_NONE;
+  void* out = nullptr;                      // dt (or fp32 when out_f32)
+  int out_f32 = 0;
+  // scratch (owned by the caller / workspace)
+  float* partials = nullptr;                // [B][n_chunks][32][2]
+  float* ab = nullptr;                      // [B][2][Ctot]
+  int n_chunks = 0;
+};
+int gn_chunks(int64_t rows_per_batch);      // number of stats chunks per batch element
+int gn_forward(const GnArgs& a, cudaStream_t s, int* launches);
+
+// plain resample (Upsample(use_conv=True) front half, unet.py:100-105)
+int resample_hw(int dt, const void* in, void* out, int B, int Z, int H, int W, int C, int mode, cudaStream_t s);
+
+// ---- network input / embedding -----------------------------------------------------------------
+// cat([x, low_res], 1) + cast (unet.py:1690-1693,1035): two fp32 (B,1,Z,H,W) -> [B][Z][H][W][2]
+int pack_input(int dt, const float* x, const float* low, void* out, int64_t n_vox_total, cudaStream_t s);
+
+struct EmbArgs {
+  const float* t = nullptr;          // [B]
+  const int64_t* y = nullptr;        // [B] or NULL
+  int B = 0, model_channels = 0, ted = 0;
+  const float *w0, *b0, *w2, *b2;    // time_embed.{0,2}
+  const float* label_emb = nullptr;  // [num_classes][ted]
+  float* emb_silu = nullptr;         // [B][ted]  = SiLU(emb)   (every consumer applies SiLU first, unet.py:199-205)
+  const float* w_all = nullptr;      // all emb_layers.1.weight stacked: [rows_total][ted]
+  const float* b_all = nullptr;      // [rows_total]
+  int rows_total = 0;
+  float* emb_out = nullptr;          // [B][rows_total]
+};
+int timestep_embedding_k(const float* t, float* out, int B, int dim, cudaStream_t s);
+int embedding_forward(const EmbArgs& a, cudaStream_t s, int* launches);
+
+// ---- sampler update (K9) ---------------------------------------------------------------------
+struct UpdateArgs {
+  const float* x = nullptr;
+  const float* model_out = nullptr;
+  const float* noise = nullptr;          // or NULL with use_philox
+  const int32_t* t_index = nullptr;      // device [B]  (or NULL: use *step_counter for every b)
+  const int32_t* step_counter = nullptr; // device scalar
+  const ddpm3d_step_scalars* table = nullptr;  // device [T]
+  int mean_type = DDPM3D_MEAN_EPSILON, var_type = DDPM3D_VAR_LEARNED_RANGE, clip = 1;
+  float* sample = nullptr; float* pred_xstart = nullptr; float* mean = nullptr; float* log_variance = nullptr;
+  int B = 0, C = 1; int64_t n = 0;       // n = spatial size per (b,c)
+  int64_t noise_step_stride = 0;         // with step_counter: noise += exec_index * stride
+  int T = 0;
+  int use_philox = 0; uint64_t seed = 0;
+};
+int p_sample_update_k(const UpdateArgs& a, cudaStream_t s);
+int step_advance_k(int32_t* step_counter, float* t_model, const ddpm3d_step_scalars* table, int B, cudaStream_t s);
+
+// ---- attention core (K12) --------------------------------------------------------------------
+int attention_k(int dt, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, cudaStream_t s);
+
+}  // namespace ddpm3d

@@ -1,0 +1,194 @@
+/*
+ * ddpm3d.h -- C ABI of the B200-native 3D-DDPM sampling hot path.
+ *
+ * The reference (Zachary-Luk/3D-Denoising-Diffusion-Model) is pure Python/PyTorch and has no
+ * FFI layer; its boundary for this path is the Python API used by scripts/test.py:26-35,61-69.
+ * Each entry point below names the reference interface it replaces (file:line relative to the
+ * reference root).  The Python host mirror in `3d-denoising-diffusion-model_b200/` binds these
+ * with ctypes and re-exposes the reference's own names.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - every function returns 0 on success, <0 on error; ddpm3d_last_error() gives the message
+ *     (thread-local).  No exception crosses the ABI;
+ *   - all device work is enqueued on the caller-supplied cudaStream_t (passed as void*); calls
+ *     are asynchronous unless stated;
+ *   - the caller owns every input/output buffer; the library owns its packed-weight arena and
+ *     its activation workspace;
+ *   - volumes are the reference's NCDHW fp32 tensors, (B, C, Z, H, W) with Z the (never strided)
+ *     long body axis; `t` is the ORIGINAL-numbering timestep the model sees (after
+ *     respace.py:123-128), as fp32 (nn.py:117 casts it to float anyway);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     DDPM3D_ERR_CUDA.
+ */
+#ifndef DDPM3D_H_
+#define DDPM3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDPM3D_ABI_VERSION 1
+
+#define DDPM3D_OK 0
+#define DDPM3D_ERR_ARG (-1)     /* bad argument / unsupported configuration */
+#define DDPM3D_ERR_CUDA (-2)    /* CUDA runtime / driver error (incl. no device) */
+#define DDPM3D_ERR_STATE (-3)   /* call order violated (e.g. forward before finalize) */
+#define DDPM3D_ERR_MISSING (-4) /* state_dict key missing / unknown */
+
+/* precision of the UNet torso (unet.py:1003-1013 convert_to_fp16 -> here bf16 on tcgen05) */
+#define DDPM3D_FP32 0
+#define DDPM3D_BF16 1
+
+/* gaussian_diffusion.py:65-72 ModelMeanType */
+#define DDPM3D_MEAN_PREVIOUS_X 0
+#define DDPM3D_MEAN_START_X 1
+#define DDPM3D_MEAN_EPSILON 2
+/* gaussian_diffusion.py:75-86 ModelVarType */
+#define DDPM3D_VAR_LEARNED 0
+#define DDPM3D_VAR_FIXED_SMALL 1
+#define DDPM3D_VAR_FIXED_LARGE 2
+#define DDPM3D_VAR_LEARNED_RANGE 3
+
+#define DDPM3D_MAX_LEVELS 8
+
+typedef struct ddpm3d_ctx ddpm3d_ctx;
+
+/* Arguments of UNetModel_noatt.__init__ (guided_diffusion/unet.py:751-772) as filled by
+ * sr_create_model (script_util.py:334-450). */
+typedef struct ddpm3d_config {
+  int32_t image_size;      /* large_size; informational */
+  int32_t in_channels;     /* 1; SuperResModel_noatt doubles it for the low_res concat (unet.py:1683) */
+  int32_t model_channels;  /* num_channels */
+  int32_t out_channels;    /* 2 if learn_sigma else 1 */
+  int32_t num_res_blocks;
+  int32_t n_levels;
+  int32_t channel_mult[DDPM3D_MAX_LEVELS];
+  int32_t n_attention_ds;
+  int32_t attention_ds[DDPM3D_MAX_LEVELS]; /* large_size // res, script_util.py:363-365 */
+  int32_t num_classes;     /* 0 = not class conditional */
+  int32_t num_heads;
+  int32_t num_head_channels; /* -1 = use num_heads */
+  int32_t num_heads_upsample; /* -1 = num_heads */
+  int32_t use_scale_shift_norm;
+  int32_t resblock_updown;
+  int32_t use_new_attention_order;
+  int32_t precision;       /* DDPM3D_FP32 | DDPM3D_BF16 */
+} ddpm3d_config;
+
+/* Per-timestep scalars of the respaced process, already rounded to fp32 exactly as
+ * _extract_into_tensor's `.float()` does (gaussian_diffusion.py:897-910).  Computed on the host in
+ * fp64 by the Python mirror (bit-exact restatement of gaussian_diffusion.py:118-169 and
+ * respace.py:72-86). */
+typedef struct ddpm3d_step_scalars {
+  float model_t;                       /* timestep_map[i] (x 1000/T0 if rescale_timesteps) */
+  float sqrt_recip_alphas_cumprod;     /* :328-333 */
+  float sqrt_recipm1_alphas_cumprod;
+  float posterior_mean_coef1;          /* :208-230 */
+  float posterior_mean_coef2;
+  float min_log;                       /* posterior_log_variance_clipped[i]   (:270-272) */
+  float max_log;                       /* log(betas[i])                         (:273)   */
+  float fixed_variance;                /* FIXED_SMALL / FIXED_LARGE tables      (:279-293) */
+  float fixed_log_variance;
+  float recip_coef1;                   /* 1/posterior_mean_coef1                (:335-343) */
+  float coef2_over_coef1;
+  float pad_;
+} ddpm3d_step_scalars;
+
+const char* ddpm3d_last_error(void);
+int ddpm3d_abi_version(void);
+
+/* ---- model lifetime: replaces sr_create_model (script_util.py:334-450) -------------------- */
+int ddpm3d_create(const ddpm3d_config* cfg, ddpm3d_ctx** out);
+void ddpm3d_destroy(ddpm3d_ctx* ctx);
+
+/* The state_dict contract: key i, its shape.  Replaces nn.Module.state_dict()
+ * key enumeration of UNetModel_noatt (unet.py:797-997). */
+int ddpm3d_param_count(const ddpm3d_ctx* ctx);
+int ddpm3d_param_info(const ddpm3d_ctx* ctx, int index, const char** key, int64_t shape[8], int* ndim);
+
+/* Replaces model.load_state_dict(...) + model.to(dev) + model.convert_to_fp16()
+ * (scripts/test.py:29-35).  `data` is fp32, host or device memory, laid out as the reference
+ * tensor (e.g. [Cout,Cin,3,3,3]).  finalize packs everything into the device weight arena
+ * (bf16 [Cout][27*Cin (+skip Cin)] K-major for the tcgen05 path) on CUDA device `device`; it
+ * synchronises. */
+int ddpm3d_load_tensor(ddpm3d_ctx* ctx, const char* key, const float* data, const int64_t* shape, int ndim);
+int ddpm3d_finalize_weights(ddpm3d_ctx* ctx, int device);
+
+/* Bytes of activation workspace the library allocates for a (B,Z,H,W) problem. */
+int64_t ddpm3d_workspace_bytes(ddpm3d_ctx* ctx, int B, int Z, int H, int W);
+
+/* ---- one UNet evaluation: replaces SuperResModel_noatt.forward (unet.py:1687-1694) ---------
+ * x, low_res: device fp32 (B,1,Z,H,W); t: device fp32 (B); y: device int64 (B) or NULL;
+ * out: device fp32 (B,out_channels,Z,H,W). */
+int ddpm3d_unet_forward(ddpm3d_ctx* ctx, const float* x, const float* low_res, const float* t,
+                        const int64_t* y, float* out, int B, int Z, int H, int W, void* stream);
+
+/* ---- sampler: replaces GaussianDiffusion/SpacedDiffusion (gaussian_diffusion.py:232-535) ---
+ * set_schedule uploads the T-entry scalar table (host pointer) and the mean/var modes. */
+int ddpm3d_set_schedule(ddpm3d_ctx* ctx, const ddpm3d_step_scalars* table, int T, int mean_type, int var_type);
+
+/* The elementwise half of p_sample (gaussian_diffusion.py:262-326,430-438): from the raw model
+ * output to x_{t-1}.  x, noise, sample, pred_xstart, mean, log_variance: device fp32 (B,C,n_spatial);
+ * model_out: (B,2C,n) for learned variance else (B,C,n); t_index: device int32 (B) indices into the
+ * schedule table.  pred_xstart / mean / log_variance may be NULL.  One kernel launch. */
+int ddpm3d_p_sample_update(ddpm3d_ctx* ctx, const float* x, const float* model_out, const float* noise,
+                           const int32_t* t_index, int clip_denoised, float* sample, float* pred_xstart,
+                           float* mean, float* log_variance, int B, int C, int64_t n_spatial, void* stream);
+
+/* p_sample (gaussian_diffusion.py:395-439) = UNet + update for step index `i` (same for the whole
+ * batch, as p_sample_loop_progressive :522-525 issues it). */
+int ddpm3d_p_sample(ddpm3d_ctx* ctx, const float* x, const float* low_res, const int64_t* y, const float* noise,
+                    int step_index, int clip_denoised, float* sample, float* pred_xstart,
+                    int B, int Z, int H, int W, void* stream);
+
+/* p_sample_loop (gaussian_diffusion.py:441-485): runs steps i = T-1 ... T-n_steps (n_steps <= 0: all T)
+ * entirely on the device.  noise: device fp32 [n_steps][B*Z*H*W] consumed in execution order
+ * (replaces th.randn_like, :430), or NULL to draw it in-kernel from Philox4x32-10 with `seed`.
+ * x_T, low_res, out: device fp32 (B,1,Z,H,W).  out may alias x_T. */
+int ddpm3d_sample_loop(ddpm3d_ctx* ctx, const float* x_T, const float* low_res, const int64_t* y,
+                       const float* noise, uint64_t seed, int clip_denoised, int n_steps, float* out,
+                       int B, int Z, int H, int W, void* stream);
+
+/* ---- knobs and introspection ------------------------------------------------------------------ */
+/* "cuda_graph" (0/1, default 1): replay one captured graph per UNet evaluation;
+ * "conv_path" (0 = auto, 1 = force SIMT fp32-accumulate kernels, 2 = force tcgen05 where legal);
+ * "profile" (0/1): record a CUDA-event pair around every kernel launch (disables graphs). */
+int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value);
+/* Kernel launches enqueued by this ctx since creation. */
+int64_t ddpm3d_launch_count(const ddpm3d_ctx* ctx);
+/* After a profiled call: synchronises and writes up to `cap` records; returns the record count.
+ * `kind`: 0 conv-tcgen05, 1 conv-simt, 2 gn-stats, 3 gn-finalize, 4 gn-apply, 5 embedding, 6 update,
+ * 7 attention, 8 pack/resample/misc.  `work` = algorithmic flops (conv, attention) or bytes (others). */
+typedef struct ddpm3d_prof_record { int32_t kind; int32_t pad_; float ms; float pad2_; double work; } ddpm3d_prof_record;
+int ddpm3d_profile_read(ddpm3d_ctx* ctx, ddpm3d_prof_record* out, int cap);
+
+/* ---- single kernels on channels-last device buffers, exported for unit tests ------------------
+ * dtype: DDPM3D_FP32 (float) or DDPM3D_BF16 (__nv_bfloat16) for activations and conv weights.
+ * Activations are [B][Z][H][W][C] (NDHWC).  These replace the torch ops behind nn.py:17-32. */
+
+/* 3x3x3 (taps=27) or 1x1x1 (taps=1) "same" convolution, stride (1,s,s) (nn.py:22-32; call sites
+ * unet.py:185,211,219,222).  w: [Cout][taps*Cin] with k = tap*Cin + ci, tap = (dz*3+dh)*3+dw;
+ * bias fp32 [Cout]; residual (optional, [B][Z][Ho][Wo][Cout]) is added in the epilogue.
+ * path: 1 SIMT, 2 tcgen05 (bf16 only, Cin%64==0, Cout%16==0, s==1). */
+int ddpm3d_k_conv3d(int dtype, int path, const void* in, const void* w, const float* bias, const void* residual,
+                    void* out, int B, int Z, int H, int W, int Cin, int Cout, int taps, int stride_hw, void* stream);
+
+/* GroupNorm32(32,C) (+ optional per-(b,c) FiLM scale/shift, unet.py:248-252) (+ optional SiLU)
+ * (+ optional AvgPool (1,2,2) / nearest x2 on (H,W) of the result, unet.py:81-140):
+ * resample 0 none, 1 pool, 2 upsample.  gamma/beta fp32 [C]; film fp32 [B][2C] (scale then shift) or NULL. */
+int ddpm3d_k_groupnorm(int dtype, const void* in, const float* gamma, const float* beta, const float* film,
+                       int silu, int resample, void* out, int B, int Z, int H, int W, int C, void* stream);
+
+/* timestep_embedding (nn.py:103-121): t fp32 [B] -> out fp32 [B][dim]. */
+int ddpm3d_k_timestep_embedding(const float* t, float* out, int B, int dim, void* stream);
+
+/* QKVAttentionLegacy / QKVAttention core (unet.py:328-393): qkv [B][T][3C] channels-last -> out [B][T][C]. */
+int ddpm3d_k_attention(int dtype, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDPM3D_H_ */
