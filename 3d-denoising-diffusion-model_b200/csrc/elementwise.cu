@@ -613,6 +613,17 @@ __global__ void step_advance_kernel(int32_t* counter, float* t_model, const ddpm
     for (int b = threadIdx.x; b < B; b += blockDim.x) t_model[b] = table[next].model_t;
 }
 
+__global__ void step_set_kernel(int32_t* counter, float* t_model, const ddpm3d_step_scalars* table, int B, int index, int exec) {
+  if (threadIdx.x == 0) { counter[0] = index; counter[1] = exec; }
+  for (int b = threadIdx.x; b < B; b += blockDim.x) t_model[b] = table[index].model_t;
+}
+
+int step_set_k(int32_t* counter, float* t_model, const ddpm3d_step_scalars* table, int B, int index, int exec, cudaStream_t s) {
+  step_set_kernel<<<1, 32, 0, s>>>(counter, t_model, table, B, index, exec);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
 int step_advance_k(int32_t* counter, float* t_model, const ddpm3d_step_scalars* table, int B, cudaStream_t s) {
   step_advance_kernel<<<1, 32, 0, s>>>(counter, t_model, table, B);
   DD_CUDA(cudaGetLastError());

@@ -99,6 +99,7 @@ struct UpdateArgs {
   int use_philox = 0; uint64_t seed = 0;
 };
 int p_sample_update_k(const UpdateArgs& a, cudaStream_t s);
+int step_set_k(int32_t* step_counter, float* t_model, const ddpm3d_step_scalars* table, int B, int index, int exec, cudaStream_t s);
 int step_advance_k(int32_t* step_counter, float* t_model, const ddpm3d_step_scalars* table, int B, cudaStream_t s);
 
 // ---- attention core (K12) --------------------------------------------------------------------

@@ -1,0 +1,146 @@
+"""-m gpu: every hot-path kernel, called through the C ABI, against the oracle / torch fp32 ops and
+the fixtures generated from the unmodified reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from ddpm3d_b200 import _native as N
+from ddpm3d_b200 import script_util as su
+from oracle import cases
+from oracle.sampler import p_sample as oracle_p_sample
+from oracle.schedule import make_tables
+
+pytestmark = pytest.mark.gpu
+
+from gpu_util import DEV, conv3d, from_cl, max_rel, pack_weight, stream, to_cl  # noqa: E402
+
+
+@pytest.mark.parametrize("i", range(len(cases.TEMB_CASES)))
+def test_timestep_embedding_matches_reference(golden_dir, i):
+    """nn.py:103-121.  fp32 cos/sin of identical fp32 arguments: <= 2e-6 absolute."""
+    ts, dim = cases.TEMB_CASES[i]
+    want = np.load(os.path.join(golden_dir, "temb.npz"))[str(i)]
+    t = torch.tensor(ts, dtype=torch.float32, device=DEV)
+    out = torch.empty((len(ts), dim), device=DEV)
+    N.check(N.lib().ddpm3d_k_timestep_embedding(N.ptr(t), N.ptr(out), len(ts), dim, stream()))
+    torch.cuda.synchronize()
+    assert np.abs(out.cpu().numpy() - want).max() <= 2e-6
+
+
+@pytest.mark.parametrize("dt", [N.FP32, N.BF16])
+@pytest.mark.parametrize("C,shape,silu,film,resample", [
+    (32, (2, 4, 8, 8), 1, False, 0), (64, (1, 3, 6, 10), 0, True, 0), (128, (1, 8, 16, 16), 1, True, 1),
+    (96, (2, 2, 6, 6), 1, False, 2), (384, (1, 4, 12, 12), 1, True, 0), (1024, (1, 2, 6, 6), 1, False, 0),
+    (256, (1, 96, 12, 12), 1, True, 0),
+])
+def test_groupnorm_film_silu(dt, C, shape, silu, film, resample):
+    """GroupNorm32 (nn.py:17-19) + FiLM (unet.py:248-252) + SiLU + pool/upsample (unet.py:81-140)."""
+    B, Z, H, W = shape
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn((B, C, Z, H, W), generator=g) * 2 + 0.5
+    gamma = 1 + 0.1 * torch.randn(C, generator=g)
+    beta = 0.1 * torch.randn(C, generator=g)
+    fm = torch.randn((B, 2 * C), generator=g) * 0.3 if film else None
+    tdt = torch.bfloat16 if dt == N.BF16 else torch.float32
+    xin = x.to(tdt).float()  # the kernel sees the rounded input
+    ref = F.group_norm(xin, 32, gamma, beta, 1e-5)
+    if film:
+        ref = ref * (1 + fm[:, :C, None, None, None]) + fm[:, C:, None, None, None]
+    if silu:
+        ref = F.silu(ref)
+    Ho, Wo = H, W
+    if resample == 1:
+        ref = F.avg_pool3d(ref, (1, 2, 2), (1, 2, 2)); Ho, Wo = H // 2, W // 2
+    elif resample == 2:
+        ref = F.interpolate(ref, (Z, 2 * H, 2 * W), mode="nearest"); Ho, Wo = 2 * H, 2 * W
+    out = torch.empty((B, Z, Ho, Wo, C), device=DEV, dtype=tdt)
+    N.check(N.lib().ddpm3d_k_groupnorm(dt, N.ptr(to_cl(x, tdt)), N.ptr(gamma.to(DEV)), N.ptr(beta.to(DEV)),
+                                       N.ptr(fm.to(DEV).contiguous()) if film else None, silu, resample, N.ptr(out),
+                                       B, Z, H, W, C, stream()))
+    torch.cuda.synchronize()
+    tol = 1e-5 if dt == N.FP32 else 6e-3  # bf16: one output rounding (2^-8 relative)
+    assert max_rel(from_cl(out), ref) <= tol
+
+
+@pytest.mark.parametrize("dt", [N.FP32, N.BF16])
+@pytest.mark.parametrize("Cin,Cout,shape,taps,stride,res", [
+    (2, 32, (1, 4, 8, 8), 27, 1, False), (32, 32, (2, 3, 8, 6), 27, 1, True), (64, 2, (1, 4, 8, 8), 27, 1, False),
+    (32, 64, (1, 4, 8, 8), 27, 2, False), (64, 96, (1, 2, 4, 4), 1, 1, True), (128, 128, (1, 5, 12, 12), 27, 1, True),
+    (40, 24, (1, 3, 5, 7), 27, 1, False),
+])
+def test_conv3d_simt(dt, Cin, Cout, shape, taps, stride, res):
+    """conv_nd(3, ...) (nn.py:22-32) on the CUDA-core kernel vs F.conv3d fp32."""
+    B, Z, H, W = shape
+    g = torch.Generator().manual_seed(Cin * 7 + Cout)
+    tdt = torch.bfloat16 if dt == N.BF16 else torch.float32
+    x = torch.randn((B, Cin, Z, H, W), generator=g).to(tdt).float()
+    k = 3 if taps == 27 else 1
+    w = (torch.randn((Cout, Cin, k, k, k), generator=g) / np.sqrt(Cin * taps)).to(tdt).float()
+    b = torch.randn(Cout, generator=g)
+    Ho, Wo = H // stride, W // stride
+    r = torch.randn((B, Cout, Z, Ho, Wo), generator=g).to(tdt).float() if res else None
+    ref = F.conv3d(x, w, b, stride=(1, stride, stride), padding=k // 2)
+    if res:
+        ref = ref + r
+    out = conv3d(dt, 1, to_cl(x, tdt), pack_weight(w, tdt), b.to(DEV), to_cl(r, tdt) if res else None,
+                 B, Z, H, W, Cin, Cout, taps, stride)
+    tol = 2e-5 if dt == N.FP32 else 6e-3
+    assert max_rel(from_cl(out), ref) <= tol
+
+
+@pytest.mark.parametrize("i", range(len(cases.PMV_CASES)))
+def test_p_sample_update_matches_reference(golden_dir, i):
+    """gaussian_diffusion.py:232-326,395-439 on the fixtures made by the unmodified reference.
+    mean / pred_xstart / log_variance use only non-fused fp32 mul/add: bit-exact.  sample adds exp():
+    <= 2 ulp of the noise term."""
+    case = cases.PMV_CASES[i]
+    g = np.load(os.path.join(golden_dir, "pmv.npz"))
+    d = su.create_gaussian_diffusion(**case["diffusion"])
+    from ddpm3d_b200 import gaussian_diffusion as gd
+    if case.get("previous_x"):
+        d.model_mean_type = gd.ModelMeanType.PREVIOUS_X
+    if case.get("learned"):
+        d.model_var_type = gd.ModelVarType.LEARNED
+    gen = torch.Generator().manual_seed(100 + i)
+    oc = 2 if case["diffusion"].get("learn_sigma") else 1
+    x = torch.randn((2, 1, 3, 4, 5), generator=gen)
+    mo = torch.randn((2, oc, 3, 4, 5), generator=gen) * 1.5
+    noise = torch.randn((2, 1, 3, 4, 5), generator=gen)
+    t = torch.tensor(case["t"], device=DEV)
+    out = d._posterior(lambda *a, **k: None, mo.to(DEV), x.to(DEV), t, noise.to(DEV), case["clip"])
+    torch.cuda.synchronize()
+    for k in ("mean", "pred_xstart", "log_variance"):
+        got, want = out[k].cpu().numpy(), g[f"{i}/{k}"]
+        assert np.array_equal(got.view(np.int32), want.view(np.int32)), k
+    assert np.allclose(out["variance"].cpu().numpy(), g[f"{i}/variance"], rtol=1e-6, atol=0)
+    assert np.allclose(out["sample"].cpu().numpy(), g[f"{i}/sample"], rtol=0, atol=1e-6)
+    # and the public p_mean_variance with a foreign model callable
+    pm = d.p_mean_variance(lambda x_, t_, **k: mo.to(DEV), x.to(DEV), t, clip_denoised=case["clip"])
+    assert np.array_equal(pm["mean"].cpu().numpy(), out["mean"].cpu().numpy())
+
+
+@pytest.mark.parametrize("dt", [N.FP32, N.BF16])
+@pytest.mark.parametrize("B,T,C,heads,new_order", [(1, 64, 64, 4, 0), (2, 100, 32, 1, 1), (1, 300, 128, 2, 0)])
+def test_attention_core(dt, B, T, C, heads, new_order):
+    """QKVAttentionLegacy / QKVAttention (unet.py:328-393)."""
+    g = torch.Generator().manual_seed(T + C)
+    tdt = torch.bfloat16 if dt == N.BF16 else torch.float32
+    qkv = torch.randn((B, 3 * C, T), generator=g).to(tdt).float()
+    ch = C // heads
+    s = 1 / np.sqrt(np.sqrt(ch))
+    if new_order:
+        q, k, v = qkv.chunk(3, dim=1)
+        q, k, v = (z.reshape(B * heads, ch, T) for z in (q, k, v))
+    else:
+        q, k, v = qkv.reshape(B * heads, 3 * ch, T).split(ch, dim=1)
+    w = torch.softmax(torch.einsum("bct,bcs->bts", q * s, k * s), dim=-1)
+    ref = torch.einsum("bts,bcs->bct", w, v).reshape(B, C, T)
+    out = torch.empty((B, T, C), device=DEV, dtype=tdt)
+    N.check(N.lib().ddpm3d_k_attention(dt, N.ptr(qkv.permute(0, 2, 1).contiguous().to(DEV, tdt)), N.ptr(out),
+                                       B, T, C, heads, new_order, stream()))
+    torch.cuda.synchronize()
+    tol = 1e-5 if dt == N.FP32 else 6e-3
+    assert max_rel(out.float().permute(0, 2, 1).cpu(), ref) <= tol
