@@ -53,6 +53,7 @@ SIGNATURES = {
     "ddpm3d_param_info": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(_I)]),
     "ddpm3d_load_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I]),
     "ddpm3d_finalize_weights": (_I, [_P, _I]),
+    "ddpm3d_set_timestep_freqs": (_I, [_P, _P, _I]),
     "ddpm3d_workspace_bytes": (C.c_int64, [_P, _I, _I, _I, _I]),
     "ddpm3d_unet_forward": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ddpm3d_set_schedule": (_I, [_P, C.POINTER(StepScalars), _I, _I, _I]),
@@ -64,7 +65,7 @@ SIGNATURES = {
     "ddpm3d_profile_read": (_I, [_P, C.POINTER(ProfRecord), _I]),
     "ddpm3d_k_conv3d": (_I, [_I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "ddpm3d_k_groupnorm": (_I, [_I, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
-    "ddpm3d_k_timestep_embedding": (_I, [_P, _P, _I, _I, _P]),
+    "ddpm3d_k_timestep_embedding": (_I, [_P, _P, _P, _I, _I, _P]),
     "ddpm3d_k_attention": (_I, [_I, _P, _P, _I, _I, _I, _I, _I, _P]),
 }
 

@@ -1,6 +1,507 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// 3x3x3 / 1x1x1 convolution as an implicit GEMM on the 5th-generation tensor cores (sm_100a).
+//
+//   D[m, n] = sum_k A[m, k] * W[n, k]      m = output voxel, n = output channel,
+//                                          k = (tap, input channel) [+ channels of 1x1x1 sources]
+//
+// * A is never materialised: every k-step (one tap, 64 channels) is ONE 5-D TMA box
+//   {64 ch, bw, bh, bz, 1} of the channels-last activation tensor, shifted by the tap offset.
+//   Out-of-bounds coordinates (the conv's zero padding, and bricks overhanging the volume) are
+//   zero-filled by the TMA unit, so there is no halo handling in the kernel.
+// * The box lands in shared memory as 128 rows x 128 bytes with the 128-byte swizzle, which is
+//   exactly the canonical K-major SWIZZLE_128B operand layout of tcgen05.mma.
+// * W ([Cout][Ktot] bf16, K contiguous) comes from a 2-D TMA box {64, BN}.
+// * Accumulators live in TMEM (2 x BN fp32 columns, double buffered): the epilogue of tile i
+//   (tcgen05.ld -> +bias -> +residual (plain / 2x2-average / nearest-upsampled) -> bf16 -> global)
+//   overlaps the MMAs of tile i+1.
+// * Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer
+//   (+ TMEM allocation), warps 2-5 = epilogue.  smem ring of NSTAGE {A,B} slots with full/empty
+//   mbarriers; tcgen05.commit releases slots and publishes finished accumulators.
+//
+// The ResBlock skip_connection (1x1x1 conv over the un-normalised block input, which for decoder
+// blocks is a channel concat of two tensors) is folded in as extra k-steps reading those tensors
+// in place (unet.py:222,254-256 and :1040-1042).
+#include <cuda.h>
+
+#include <mutex>
+
 #include "kernels.h"
+
 namespace ddpm3d {
-bool conv_tc_eligible(const ConvArgs&) { return false; }
-int conv_tc(const ConvArgs&, cudaStream_t) { set_error("conv_tc: not built"); return DDPM3D_ERR_ARG; }
+
+namespace {
+
+constexpr int BM = 128;      // UMMA M (rows of the brick, <= 128 valid)
+constexpr int BK = 64;       // channels per k-step (128 bytes of bf16 = one swizzle row)
+constexpr int UMMA_K = 16;
+constexpr int NTHREADS = 192;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+
+struct TcParams {
+  int nsrc;
+  int chunks[3];     // C/64 of each source
+  int n_main_steps;  // taps * chunks[0]
+  int nk;            // total k-steps
+  int taps;          // 27 or 1
+  int bw, bh, bz;    // brick
+  int nWt, nHt, nZt, nNt;
+  int num_tiles;
+  int B, Z, Ho, Wo, Cout;
+  uint32_t a_tx_bytes;  // bytes one A box delivers
+  const float* bias;
+  const bf16* res;
+  int res_mode;
+  bf16* out;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// A pipeline bug must surface as a launch failure, never as a hung GPU: give up after ~2 s.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// K-major, SWIZZLE_128B operand descriptor: rows of 128 bytes, 8-row (1024 B) swizzle atoms.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address
+  d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset: next 8-row atom
+  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D fp32, A = B = bf16, both K-major, M x N.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void add8(float* v, const bf16* p, float scale) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] += scale * __uint_as_float(w[i] << 16);
+    v[2 * i + 1] += scale * __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+template <int BN, int NSTAGE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = 2 * BN;  // 128, 256 or 512: a power of two >= 32
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * NSTAGE + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms are 1024-byte aligned
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * NSTAGE + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 2 + a); };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA0);
+    prefetch_tmap(&mapW);
+    if (p.nsrc > 1) prefetch_tmap(&mapA1);
+    if (p.nsrc > 2) prefetch_tmap(&mapA2);
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {  // TMEM allocation is warp-wide
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.nNt;
+        int m = tile / p.nNt;
+        const int wt = m % p.nWt; m /= p.nWt;
+        const int ht = m % p.nHt; m /= p.nHt;
+        const int zt = m % p.nZt;
+        const int b = m / p.nZt;
+        const int w0 = wt * p.bw, h0 = ht * p.bh, z0 = zt * p.bz, n0 = nt * BN;
+        for (int kk = 0; kk < p.nk; ++kk) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), p.a_tx_bytes + B_BYTES);
+          const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+          const uint32_t b_dst = a_dst + A_BYTES;
+          if (kk < p.n_main_steps) {
+            const int tap = p.taps == 27 ? kk / p.chunks[0] : 13;
+            const int c0 = (kk - (p.taps == 27 ? tap * p.chunks[0] : 0)) * BK;
+            const int dz = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
+            tma_load_5d(a_dst, &mapA0, full_bar(stage), c0, w0 + dw, h0 + dh, z0 + dz, b);
+          } else {
+            const int e = kk - p.n_main_steps;
+            if (e < p.chunks[1]) tma_load_5d(a_dst, &mapA1, full_bar(stage), e * BK, w0, h0, z0, b);
+            else tma_load_5d(a_dst, &mapA2, full_bar(stage), (e - p.chunks[1]) * BK, w0, h0, z0, b);
+          }
+          tma_load_2d(b_dst, &mapW, full_bar(stage), kk * BK, n0);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kk = 0; kk < p.nk; ++kk) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
+          const uint64_t adesc = make_sw128_desc(a_addr);
+          const uint64_t bdesc = make_sw128_desc(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kk | k) != 0);
+          }
+          umma_commit(empty_bar(stage));  // slot is free once these MMAs have read it
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue ==========================================
+    const int sub = warp & 3;  // TMEM sub-partition this warp may read: lanes 32*sub .. 32*sub+31
+    const int row = sub * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.nNt;
+      int m = tile / p.nNt;
+      const int wt = m % p.nWt; m /= p.nWt;
+      const int ht = m % p.nHt; m /= p.nHt;
+      const int zt = m % p.nZt;
+      const int b = m / p.nZt;
+      const int n0 = nt * BN;
+      // row -> voxel of the brick (same enumeration as the TMA box: w fastest, then h, then z)
+      const int rw = row % p.bw, rh = (row / p.bw) % p.bh, rz = row / (p.bw * p.bh);
+      const int w = wt * p.bw + rw, h = ht * p.bh + rh, z = zt * p.bz + rz;
+      const bool valid = rz < p.bz && w < p.Wo && h < p.Ho && z < p.Z;
+      const int64_t vox = (((int64_t)b * p.Z + z) * p.Ho + h) * p.Wo + w;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + (uint32_t)c, r);
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(bp + j);
+            v[4 * j] = __uint_as_float(r[4 * j]) + b4.x;
+            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
+            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+          }
+          if (p.res_mode == RES_SAME) {
+            const bf16* rp = p.res + vox * p.Cout + n0 + c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) add8(v + 8 * j, rp + 8 * j, 1.0f);
+          } else if (p.res_mode == RES_POOL) {  // residual = AvgPool(1,2,2) of a (2Ho, 2Wo) tensor
+            const int Hr = 2 * p.Ho, Wr = 2 * p.Wo;
+            const int64_t r0 = (((int64_t)b * p.Z + z) * Hr + 2 * h) * Wr + 2 * w;
+            float s[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s[j] = 0.f;
+            const int64_t offs[4] = {r0, r0 + 1, r0 + Wr, r0 + Wr + 1};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const bf16* rp = p.res + offs[q] * p.Cout + n0 + c;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) add8(s + 8 * j, rp + 8 * j, 1.0f);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += 0.25f * s[j];
+          } else if (p.res_mode == RES_UP) {  // residual = nearest x2 of a (Ho/2, Wo/2) tensor
+            const int Hr = p.Ho / 2, Wr = p.Wo / 2;
+            const int64_t r0 = (((int64_t)b * p.Z + z) * Hr + h / 2) * Wr + w / 2;
+            const bf16* rp = p.res + r0 * p.Cout + n0 + c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) add8(v + 8 * j, rp + 8 * j, 1.0f);
+          }
+          bf16* op = p.out + vox * p.Cout + n0 + c;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
+              w4[q] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// channels-last activation [B][Z][H][W][C] -> 5-D map, box {64, bw, bh, bz, 1}
+int make_act_map(CUtensorMap* map, const void* ptr, int B, int Z, int H, int W, int C, int bw, int bh, int bz) {
+  EncodeTiledFn enc = get_encode();
+  DD_CHECK(enc != nullptr, DDPM3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Z, (cuuint64_t)B};
+  const cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                                 (cuuint64_t)Z * H * W * C * 2};
+  const cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bz, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DD_CHECK(r == CUDA_SUCCESS, DDPM3D_ERR_CUDA, "cuTensorMapEncodeTiled (activation) failed: " + std::to_string((int)r));
+  return DDPM3D_OK;
+}
+
+int make_w_map(CUtensorMap* map, const void* ptr, int Cout, int Ktot, int bn) {
+  EncodeTiledFn enc = get_encode();
+  DD_CHECK(enc != nullptr, DDPM3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+  const cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DD_CHECK(r == CUDA_SUCCESS, DDPM3D_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed: " + std::to_string((int)r));
+  return DDPM3D_OK;
+}
+
+// brick {bw, bh, bz} with bw*bh*bz <= 128 that wastes the fewest MMA rows
+void choose_brick(int Z, int H, int W, int* bw_, int* bh_, int* bz_) {
+  double best = -1.0;
+  int bbw = 1, bbh = 1, bbz = 1;
+  for (int bw = 1; bw <= std::min(W, BM); ++bw) {
+    for (int bh = 1; bh <= std::min(H, BM / bw); ++bh) {
+      const int bz = std::min(Z, BM / (bw * bh));
+      if (bz < 1) continue;
+      const double tiles = (double)ceil_div(W, bw) * ceil_div(H, bh) * ceil_div(Z, bz);
+      double eff = ((double)W * H * Z) / (tiles * BM);
+      // tie-break: prefer wide-in-W bricks (longer runs of adjacent voxels per TMA box row)
+      eff += 1e-6 * bw + 1e-9 * bh;
+      if (eff > best) { best = eff; bbw = bw; bbh = bh; bbz = bz; }
+    }
+  }
+  *bw_ = bbw; *bh_ = bbh; *bz_ = bbz;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int NSTAGE>
+int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s) {
+  constexpr size_t smem = (size_t)NSTAGE * (A_BYTES + BN * BK * 2) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int grid = std::min(p.num_tiles, sm_count());
+  conv_tc_kernel<BN, NSTAGE><<<grid, NTHREADS, smem, s>>>(maps[0], maps[1], maps[2], mapW, p);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
+}  // namespace
+
+bool conv_tc_eligible(const ConvArgs& a) {
+  if (a.dt != DDPM3D_BF16 || a.out_planar_f32 || a.stride_hw != 1) return false;
+  if (a.taps != 27 && a.taps != 1) return false;
+  if (a.main.C % BK != 0 || a.Cout % 64 != 0) return false;
+  for (int e = 0; e < a.n_extra; ++e)
+    if (a.extra[e].C % BK != 0) return false;
+  auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!aligned(a.main.ptr) || !aligned(a.w) || !aligned(a.out) || !aligned(a.bias)) return false;
+  if (a.residual && !aligned(a.residual)) return false;
+  if (a.residual && a.res_mode == RES_UP && (a.Ho % 2 || a.Wo % 2)) return false;
+  if ((int64_t)a.B * a.Z * a.Ho * a.Wo >= (int64_t)1 << 31) return false;
+  return true;
+}
+
+int conv_tc(const ConvArgs& a, cudaStream_t s) {
+  DD_CHECK(conv_tc_eligible(a), DDPM3D_ERR_ARG, "conv_tc: shape not eligible");
+  TcParams p{};
+  p.nsrc = 1 + a.n_extra;
+  p.chunks[0] = a.main.C / BK;
+  p.taps = a.taps;
+  p.n_main_steps = a.taps * p.chunks[0];
+  p.nk = p.n_main_steps;
+  int Ktot = a.taps * a.main.C;
+  for (int e = 0; e < a.n_extra; ++e) {
+    p.chunks[1 + e] = a.extra[e].C / BK;
+    p.nk += p.chunks[1 + e];
+    Ktot += a.extra[e].C;
+  }
+  choose_brick(a.Z, a.Ho, a.Wo, &p.bw, &p.bh, &p.bz);
+  const int BN = (a.Cout % 128 == 0) ? 128 : 64;
+  p.nWt = (int)ceil_div(a.Wo, p.bw);
+  p.nHt = (int)ceil_div(a.Ho, p.bh);
+  p.nZt = (int)ceil_div(a.Z, p.bz);
+  p.nNt = a.Cout / BN;
+  p.num_tiles = a.B * p.nZt * p.nHt * p.nWt * p.nNt;
+  p.B = a.B; p.Z = a.Z; p.Ho = a.Ho; p.Wo = a.Wo; p.Cout = a.Cout;
+  p.a_tx_bytes = (uint32_t)(p.bw * p.bh * p.bz * BK * 2);
+  p.bias = a.bias;
+  p.res = (const bf16*)a.residual;
+  p.res_mode = a.residual ? a.res_mode : RES_NONE;
+  p.out = (bf16*)a.out;
+
+  CUtensorMap maps[3];
+  DD_TRY(make_act_map(&maps[0], a.main.ptr, a.B, a.Z, a.Ho, a.Wo, a.main.C, p.bw, p.bh, p.bz));
+  maps[1] = maps[0];
+  maps[2] = maps[0];
+  for (int e = 0; e < a.n_extra; ++e)
+    DD_TRY(make_act_map(&maps[1 + e], a.extra[e].ptr, a.B, a.Z, a.Ho, a.Wo, a.extra[e].C, p.bw, p.bh, p.bz));
+  CUtensorMap mapW;
+  DD_TRY(make_w_map(&mapW, a.w, a.Cout, Ktot, BN));
+  if (BN == 128) return launch<128, 6>(maps, mapW, p, s);
+  return launch<64, 8>(maps, mapW, p, s);
+}
+
 }  // namespace ddpm3d

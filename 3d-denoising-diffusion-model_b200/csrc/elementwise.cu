@@ -391,23 +391,24 @@ int resample_hw(int dt, const void* in, void* out, int B, int Z, int H, int W, i
 // =================================================================================================
 // timestep embedding (nn.py:103-121) and the embedding MLPs (unet.py:798-803,199-205)
 // =================================================================================================
-__device__ __forceinline__ float temb_value(float t, int j, int dim) {
+__device__ __forceinline__ float temb_value(float t, int j, int dim, const float* __restrict__ freqs) {
   const int half = dim / 2;
   if (j >= 2 * half) return 0.f;  // odd dim: zero pad
   const int i = j < half ? j : j - half;
-  // th.exp(-math.log(max_period) * arange(half, fp32) / half): fp32 mul, fp32 div, exp
-  const float freq = expf(__fdiv_rn(__fmul_rn(-9.210340371976184f, (float)i), (float)half));
+  // th.exp(-math.log(max_period) * arange(half, fp32) / half): the reference evaluates this on the HOST
+  // (nn.py:113-115, then .to(device)); when the host table is supplied the angles match it bit for bit
+  const float freq = freqs ? freqs[i] : expf(__fdiv_rn(__fmul_rn(-9.210340371976184f, (float)i), (float)half));
   const float ang = __fmul_rn(t, freq);
   return j < half ? cosf(ang) : sinf(ang);
 }
 
-__global__ void temb_kernel(const float* __restrict__ t, float* __restrict__ out, int dim) {
+__global__ void temb_kernel(const float* __restrict__ t, const float* __restrict__ freqs, float* __restrict__ out, int dim) {
   const int b = blockIdx.x;
-  for (int j = threadIdx.x; j < dim; j += blockDim.x) out[(int64_t)b * dim + j] = temb_value(t[b], j, dim);
+  for (int j = threadIdx.x; j < dim; j += blockDim.x) out[(int64_t)b * dim + j] = temb_value(t[b], j, dim, freqs);
 }
 
-int timestep_embedding_k(const float* t, float* out, int B, int dim, cudaStream_t s) {
-  temb_kernel<<<B, 128, 0, s>>>(t, out, dim);
+int timestep_embedding_k(const float* t, const float* freqs, float* out, int B, int dim, cudaStream_t s) {
+  temb_kernel<<<B, 128, 0, s>>>(t, freqs, out, dim);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }
@@ -426,7 +427,7 @@ __global__ void time_embed_kernel(EmbArgs a) {
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const float t = a.t[b];
-  for (int j = threadIdx.x; j < a.model_channels; j += blockDim.x) e0[j] = temb_value(t, j, a.model_channels);
+  for (int j = threadIdx.x; j < a.model_channels; j += blockDim.x) e0[j] = temb_value(t, j, a.model_channels, a.freqs);
   __syncthreads();
   for (int r = warp; r < a.ted; r += nwarp) {
     const float* w = a.w0 + (int64_t)r * a.model_channels;

@@ -139,6 +139,9 @@ struct ddpm3d_ctx {
   size_t img_cap = 0;
   // options
   int use_graph = 1, conv_path = 0, profile = 0;
+  cudaStream_t cap_stream = nullptr;
+  float* d_freqs = nullptr;  // timestep_embedding frequencies computed by the host exactly like nn.py:113-115
+  int n_freqs = 0;
   int64_t launches = 0;
   std::map<GraphKey, cudaGraphExec_t> graphs;
   std::map<GraphKey, int64_t> graph_launches;
@@ -631,6 +634,7 @@ int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, cons
     e.w0 = ctx->te_w0; e.b0 = ctx->te_b0; e.w2 = ctx->te_w2; e.b2 = ctx->te_b2;
     e.label_emb = ctx->cfg.num_classes > 0 ? ctx->label_emb : nullptr;
     DD_CHECK(!e.label_emb || y, DDPM3D_ERR_ARG, "class-conditional model needs y (unet.py:1024-1026)");
+    e.freqs = ctx->d_freqs;
     e.emb_silu = emb_silu;
     e.w_all = ctx->emb_w_all; e.b_all = ctx->emb_b_all; e.rows_total = ctx->emb_rows_total;
     e.emb_out = R.emb_out;
@@ -737,10 +741,13 @@ template <typename F>
 int run_graphed(ddpm3d_ctx* ctx, const GraphKey& key, cudaStream_t s, F&& body) {
   if (!ctx->use_graph || ctx->profile) {
     int n = 0;
-    DD_TRY(body(&n));
+    DD_TRY(body(s, &n));
     ctx->launches += n;
     return DDPM3D_OK;
   }
+  // the caller's stream may be the legacy default stream, which cannot be captured: capture on an
+  // internal stream, replay on the caller's
+  if (!ctx->cap_stream) DD_CUDA(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
   auto it = ctx->graphs.find(key);
   if (it == ctx->graphs.end()) {
     if (ctx->graphs.size() >= 16) {
@@ -750,9 +757,9 @@ int run_graphed(ddpm3d_ctx* ctx, const GraphKey& key, cudaStream_t s, F&& body) 
     }
     cudaGraph_t graph = nullptr;
     int n = 0;
-    DD_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
-    const int r = body(&n);
-    const cudaError_t e = cudaStreamEndCapture(s, &graph);
+    DD_CUDA(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeRelaxed));
+    const int r = body(ctx->cap_stream, &n);
+    const cudaError_t e = cudaStreamEndCapture(ctx->cap_stream, &graph);
     if (r != DDPM3D_OK) {
       if (graph) cudaGraphDestroy(graph);
       return r;
@@ -866,6 +873,8 @@ void ddpm3d_destroy(ddpm3d_ctx* ctx) {
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->d_mo) cudaFree(ctx->d_mo);
     if (ctx->d_img) cudaFree(ctx->d_img);
+    if (ctx->d_freqs) cudaFree(ctx->d_freqs);
+    if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
     for (auto& e : ctx->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   }
   delete ctx;
@@ -945,6 +954,20 @@ int ddpm3d_finalize_weights(ddpm3d_ctx* ctx, int device) {
   return DDPM3D_OK;
 }
 
+int ddpm3d_set_timestep_freqs(ddpm3d_ctx* ctx, const float* freqs, int n) {
+  DD_CHECK(ctx && freqs, DDPM3D_ERR_ARG, "set_timestep_freqs: null argument");
+  DD_CHECK(ctx->finalized, DDPM3D_ERR_STATE, "set_timestep_freqs: finalize weights first");
+  DD_CHECK(n == ctx->cfg.model_channels / 2, DDPM3D_ERR_ARG, "set_timestep_freqs: need model_channels/2 frequencies");
+  DD_CUDA(cudaSetDevice(ctx->device));
+  DD_CUDA(cudaDeviceSynchronize());
+  if (ctx->d_freqs) cudaFree(ctx->d_freqs);
+  ctx->d_freqs = nullptr;
+  DD_CUDA(cudaMalloc((void**)&ctx->d_freqs, (size_t)n * sizeof(float)));
+  DD_CUDA(cudaMemcpy(ctx->d_freqs, freqs, (size_t)n * sizeof(float), cudaMemcpyDefault));
+  ctx->n_freqs = n;
+  return DDPM3D_OK;
+}
+
 int64_t ddpm3d_workspace_bytes(ddpm3d_ctx* ctx, int B, int Z, int H, int W) {
   if (!ctx) { set_error("workspace_bytes: null ctx"); return DDPM3D_ERR_ARG; }
   const int f = 1 << (ctx->cfg.n_levels - 1);
@@ -962,7 +985,7 @@ int ddpm3d_unet_forward(ddpm3d_ctx* ctx, const float* x, const float* low_res, c
   GraphKey key{};
   key.kind = 0; key.B = B; key.Z = Z; key.H = H; key.W = W;
   key.p[0] = x; key.p[1] = low_res; key.p[2] = t; key.p[3] = y; key.p[4] = out; key.p[5] = s;
-  return run_graphed(ctx, key, s, [&](int* n) { return forward_launch(ctx, x, low_res, t, y, out, B, Z, H, W, s, n); });
+  return run_graphed(ctx, key, s, [&](cudaStream_t cs, int* n) { return forward_launch(ctx, x, low_res, t, y, out, B, Z, H, W, cs, n); });
 }
 
 int ddpm3d_set_schedule(ddpm3d_ctx* ctx, const ddpm3d_step_scalars* table, int T, int mean_type, int var_type) {
@@ -1028,14 +1051,14 @@ int ddpm3d_p_sample(ddpm3d_ctx* ctx, const float* x, const float* low_res, const
   key.kind = 1; key.B = B; key.Z = Z; key.H = H; key.W = W;
   key.p[0] = x; key.p[1] = low_res; key.p[2] = y; key.p[3] = noise; key.p[4] = sample; key.p[5] = pred_xstart; key.p[6] = s;
   key.i[0] = clip_denoised;
-  return run_graphed(ctx, key, s, [&](int* nl) {
-    DD_TRY(forward_launch(ctx, x, low_res, ctx->d_tmodel, y, ctx->d_mo, B, Z, H, W, s, nl));
+  return run_graphed(ctx, key, s, [&](cudaStream_t cs, int* nl) {
+    DD_TRY(forward_launch(ctx, x, low_res, ctx->d_tmodel, y, ctx->d_mo, B, Z, H, W, cs, nl));
     UpdateArgs a{};
     a.x = x; a.model_out = ctx->d_mo; a.noise = noise; a.step_counter = ctx->d_counter; a.table = ctx->d_table;
     a.mean_type = ctx->mean_type; a.var_type = ctx->var_type; a.clip = clip_denoised;
     a.sample = sample; a.pred_xstart = pred_xstart;
     a.B = B; a.C = 1; a.n = n; a.T = ctx->T;
-    DD_TRY(p_sample_update_k(a, s));
+    DD_TRY(p_sample_update_k(a, cs));
     *nl += 1;
     return (int)DDPM3D_OK;
   });
@@ -1061,8 +1084,8 @@ int ddpm3d_sample_loop(ddpm3d_ctx* ctx, const float* x_T, const float* low_res, 
   key.p[0] = low_res; key.p[1] = y; key.p[2] = noise; key.p[3] = s;
   key.i[0] = clip_denoised; key.i[1] = (int64_t)seed;
   for (int k = 0; k < n_steps; ++k) {
-    DD_TRY(run_graphed(ctx, key, s, [&](int* nl) {
-      DD_TRY(forward_launch(ctx, img, low_res, ctx->d_tmodel, y, ctx->d_mo, B, Z, H, W, s, nl));
+    DD_TRY(run_graphed(ctx, key, s, [&](cudaStream_t cs, int* nl) {
+      DD_TRY(forward_launch(ctx, img, low_res, ctx->d_tmodel, y, ctx->d_mo, B, Z, H, W, cs, nl));
       UpdateArgs a{};
       a.x = img; a.model_out = ctx->d_mo; a.noise = noise; a.step_counter = ctx->d_counter; a.table = ctx->d_table;
       a.mean_type = ctx->mean_type; a.var_type = ctx->var_type; a.clip = clip_denoised;
@@ -1070,8 +1093,8 @@ int ddpm3d_sample_loop(ddpm3d_ctx* ctx, const float* x_T, const float* low_res, 
       a.B = B; a.C = 1; a.n = n; a.T = ctx->T;
       a.noise_step_stride = (int64_t)B * n;
       a.use_philox = noise == nullptr; a.seed = seed;
-      DD_TRY(p_sample_update_k(a, s));
-      DD_TRY(step_advance_k(ctx->d_counter, ctx->d_tmodel, ctx->d_table, B, s));
+      DD_TRY(p_sample_update_k(a, cs));
+      DD_TRY(step_advance_k(ctx->d_counter, ctx->d_tmodel, ctx->d_table, B, cs));
       *nl += 2;
       return (int)DDPM3D_OK;
     }));
@@ -1157,9 +1180,9 @@ int ddpm3d_k_groupnorm(int dtype, const void* in, const float* gamma, const floa
   return gn_forward(g, (cudaStream_t)stream, &n);
 }
 
-int ddpm3d_k_timestep_embedding(const float* t, float* out, int B, int dim, void* stream) {
+int ddpm3d_k_timestep_embedding(const float* t, const float* freqs, float* out, int B, int dim, void* stream) {
   DD_CHECK(t && out && B >= 1 && dim >= 1, DDPM3D_ERR_ARG, "k_timestep_embedding: bad argument");
-  return timestep_embedding_k(t, out, B, dim, (cudaStream_t)stream);
+  return timestep_embedding_k(t, freqs, out, B, dim, (cudaStream_t)stream);
 }
 
 int ddpm3d_k_attention(int dtype, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, void* stream) {

@@ -70,6 +70,7 @@ int pack_input(int dt, const float* x, const float* low, void* out, int64_t n_vo
 
 struct EmbArgs {
   const float* t = nullptr;          // [B]
+  const float* freqs = nullptr;      // [model_channels/2] host-computed frequencies, or NULL
   const int64_t* y = nullptr;        // [B] or NULL
   int B = 0, model_channels = 0, ted = 0;
   const float *w0, *b0, *w2, *b2;    // time_embed.{0,2}
@@ -80,7 +81,7 @@ struct EmbArgs {
   int rows_total = 0;
   float* emb_out = nullptr;          // [B][rows_total]
 };
-int timestep_embedding_k(const float* t, float* out, int B, int dim, cudaStream_t s);
+int timestep_embedding_k(const float* t, const float* freqs, float* out, int B, int dim, cudaStream_t s);
 int embedding_forward(const EmbArgs& a, cudaStream_t s, int* launches);
 
 // ---- sampler update (K9) ---------------------------------------------------------------------

@@ -48,6 +48,14 @@ def _make_config(*, image_size, model_channels, out_channels, num_res_blocks, at
     return cfg
 
 
+def timestep_freqs(dim, max_period=10000):
+    """nn.py:113-115: the sinusoid frequencies, evaluated on the host in fp32 with torch exactly as the
+    reference does (it then moves the table to the device)."""
+    import torch
+    half = dim // 2
+    return torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half).contiguous()
+
+
 class _Ctx:
     """RAII wrapper of ddpm3d_ctx*."""
 
@@ -268,6 +276,8 @@ class UNetModel_noatt:
             shp = (C.c_int64 * len(shape))(*shape)
             N.check(L.ddpm3d_load_tensor(ctx, key.encode(), N.ptr(t), shp, len(shape)))
         N.check(L.ddpm3d_finalize_weights(ctx, self._device.index))
+        freqs = timestep_freqs(self.model_channels)
+        N.check(L.ddpm3d_set_timestep_freqs(ctx, N.ptr(freqs), freqs.numel()))
         for k, v in self._options.items():
             N.check(L.ddpm3d_set_option(ctx, k.encode(), v))
         self._ctx = ctx

@@ -117,6 +117,12 @@ int ddpm3d_param_info(const ddpm3d_ctx* ctx, int index, const char** key, int64_
 int ddpm3d_load_tensor(ddpm3d_ctx* ctx, const char* key, const float* data, const int64_t* shape, int ndim);
 int ddpm3d_finalize_weights(ddpm3d_ctx* ctx, int device);
 
+/* nn.py:113-115 evaluates freqs = exp(-ln(10000) * arange(half) / half) on the HOST in fp32 and moves the
+ * table to the device; handing the library that very table (host or device pointer, n = model_channels/2)
+ * makes the sinusoid arguments bit-identical to the reference's.  Optional: without it the device computes
+ * the frequencies itself (<= 1 ulp apart, i.e. <= 6e-5 absolute on the embedding at t = 999). */
+int ddpm3d_set_timestep_freqs(ddpm3d_ctx* ctx, const float* freqs, int n);
+
 /* Bytes of activation workspace the library allocates for a (B,Z,H,W) problem. */
 int64_t ddpm3d_workspace_bytes(ddpm3d_ctx* ctx, int B, int Z, int H, int W);
 
@@ -182,8 +188,9 @@ int ddpm3d_k_conv3d(int dtype, int path, const void* in, const void* w, const fl
 int ddpm3d_k_groupnorm(int dtype, const void* in, const float* gamma, const float* beta, const float* film,
                        int silu, int resample, void* out, int B, int Z, int H, int W, int C, void* stream);
 
-/* timestep_embedding (nn.py:103-121): t fp32 [B] -> out fp32 [B][dim]. */
-int ddpm3d_k_timestep_embedding(const float* t, float* out, int B, int dim, void* stream);
+/* timestep_embedding (nn.py:103-121): t fp32 [B] -> out fp32 [B][dim] (cos block first).  freqs: device fp32
+ * [dim/2] host-computed table (see ddpm3d_set_timestep_freqs) or NULL to evaluate exp() on the device. */
+int ddpm3d_k_timestep_embedding(const float* t, const float* freqs, float* out, int B, int dim, void* stream);
 
 /* QKVAttentionLegacy / QKVAttention core (unet.py:328-393): qkv [B][T][3C] channels-last -> out [B][T][C]. */
 int ddpm3d_k_attention(int dtype, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, void* stream);
