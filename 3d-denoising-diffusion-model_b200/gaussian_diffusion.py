@@ -209,7 +209,15 @@ class GaussianDiffusion:
                 ctx, N.ptr(x), N.ptr(model_output), N.ptr(nz), N.ptr(t.to(torch.int32).contiguous()),
                 int(bool(clip_denoised)), N.ptr(out["sample"]), N.ptr(out["pred_xstart"]), N.ptr(out["mean"]),
                 N.ptr(out["log_variance"]), B, C, n_sp, N.current_stream_ptr(x.device)))
-        out["variance"] = torch.exp(out["log_variance"])
+        if learned:
+            out["variance"] = torch.exp(out["log_variance"])
+        else:  # gaussian_diffusion.py:279-293: both tables are gathered, variance is not exp(log_variance) at t = 0
+            if self.model_var_type == ModelVarType.FIXED_LARGE:
+                var = np.append(self.posterior_variance[1], self.betas[1:])
+            else:
+                var = self.posterior_variance
+            v = torch.from_numpy(var).to(x.device)[t.long()].float()
+            out["variance"] = v.view(-1, *([1] * (x.dim() - 1))).expand(x.shape).contiguous()
         if noise is None:
             del out["sample"]
         return out

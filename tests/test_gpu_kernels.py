@@ -64,8 +64,9 @@ def test_groupnorm_film_silu(dt, C, shape, silu, film, resample):
     elif resample == 2:
         ref = F.interpolate(ref, (Z, 2 * H, 2 * W), mode="nearest"); Ho, Wo = 2 * H, 2 * W
     out = torch.empty((B, Z, Ho, Wo, C), device=DEV, dtype=tdt)
-    N.check(N.lib().ddpm3d_k_groupnorm(dt, N.ptr(to_cl(x, tdt)), N.ptr(gamma.to(DEV)), N.ptr(beta.to(DEV)),
-                                       N.ptr(fm.to(DEV).contiguous()) if film else None, silu, resample, N.ptr(out),
+    xd, gd_, bd = to_cl(x, tdt), gamma.to(DEV), beta.to(DEV)  # keep the device tensors alive across the call
+    fd = fm.to(DEV).contiguous() if film else None
+    N.check(N.lib().ddpm3d_k_groupnorm(dt, N.ptr(xd), N.ptr(gd_), N.ptr(bd), N.ptr(fd), silu, resample, N.ptr(out),
                                        B, Z, H, W, C, stream()))
     torch.cuda.synchronize()
     tol = 1e-5 if dt == N.FP32 else 6e-3  # bf16: one output rounding (2^-8 relative)
@@ -146,7 +147,8 @@ def test_attention_core(dt, B, T, C, heads, new_order):
     w = torch.softmax(torch.einsum("bct,bcs->bts", q * s, k * s), dim=-1)
     ref = torch.einsum("bts,bcs->bct", w, v).reshape(B, C, T)
     out = torch.empty((B, T, C), device=DEV, dtype=tdt)
-    N.check(N.lib().ddpm3d_k_attention(dt, N.ptr(qkv.permute(0, 2, 1).contiguous().to(DEV, tdt)), N.ptr(out),
+    qd = qkv.permute(0, 2, 1).contiguous().to(DEV, tdt)
+    N.check(N.lib().ddpm3d_k_attention(dt, N.ptr(qd), N.ptr(out),
                                        B, T, C, heads, new_order, stream()))
     torch.cuda.synchronize()
     tol = 1e-5 if dt == N.FP32 else 6e-3

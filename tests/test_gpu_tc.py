@@ -1,0 +1,75 @@
+"""-m gpu: the tcgen05 implicit-GEMM convolution (csrc/conv_tc.cu) against F.conv3d and against the
+CUDA-core kernel on identical bf16 inputs, plus whole-network parity with the tensor-core path forced."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from ddpm3d_b200 import _native as N
+from oracle import cases
+from oracle.weights import synth_inputs
+
+pytestmark = pytest.mark.gpu
+
+from gpu_util import DEV, conv3d, from_cl, max_rel, pack_weight, to_cl  # noqa: E402
+from test_gpu_model import TOL, build  # noqa: E402
+
+
+@pytest.mark.parametrize("Cin,Cout,shape,taps,res", [
+    (64, 64, (1, 4, 8, 8), 27, False),       # one 128-row brick per z-pair
+    (64, 128, (1, 2, 16, 16), 27, True),     # BN=128
+    (128, 128, (2, 5, 12, 12), 27, True),    # batch 2, bricks overhang the volume (12 not a power of 2)
+    (128, 64, (1, 3, 6, 6), 27, False),      # 6x6 plane: 108-row bricks
+    (192, 384, (1, 4, 12, 12), 27, True),    # 3 K chunks per tap, 3 N tiles
+    (256, 128, (1, 8, 24, 24), 27, False),   # more tiles than one wave of k-steps
+    (64, 192, (1, 4, 8, 8), 1, True),        # 1x1x1 (attention qkv / proj)
+    (128, 128, (1, 96, 6, 6), 27, True),     # the shipped lowest resolution (Z = 96)
+    (128, 128, (1, 7, 48, 48), 27, False),   # odd Z
+])
+def test_conv3d_tcgen05(Cin, Cout, shape, taps, res):
+    B, Z, H, W = shape
+    g = torch.Generator().manual_seed(Cin + 3 * Cout + H)
+    x = torch.randn((B, Cin, Z, H, W), generator=g).bfloat16().float()
+    k = 3 if taps == 27 else 1
+    w = (torch.randn((Cout, Cin, k, k, k), generator=g) / np.sqrt(Cin * taps)).bfloat16().float()
+    b = torch.randn(Cout, generator=g)
+    r = torch.randn((B, Cout, Z, H, W), generator=g).bfloat16().float() if res else None
+    ref = F.conv3d(x, w, b, padding=k // 2)
+    if res:
+        ref = ref + r
+    args = (to_cl(x, torch.bfloat16), pack_weight(w, torch.bfloat16), b.to(DEV),
+            to_cl(r, torch.bfloat16) if res else None, B, Z, H, W, Cin, Cout, taps, 1)
+    tc = conv3d(N.BF16, 2, *args)
+    simt = conv3d(N.BF16, 1, *args)
+    assert max_rel(from_cl(tc), ref) <= 6e-3
+    # same bf16 inputs, fp32 accumulation in both: they may differ by one bf16 rounding at most
+    assert max_rel(tc.float().cpu(), simt.float().cpu()) <= 8e-3
+    frac_equal = float((tc == simt).float().mean())
+    assert frac_equal >= 0.98, frac_equal
+
+
+def test_ineligible_shapes_are_rejected():
+    x = torch.zeros((1, 2, 4, 4, 32), device=DEV, dtype=torch.bfloat16)
+    w = torch.zeros((64, 27 * 32), device=DEV, dtype=torch.bfloat16)
+    b = torch.zeros(64, device=DEV)
+    with pytest.raises(N.NativeError, match="not eligible"):
+        conv3d(N.BF16, 2, x, w, b, None, 1, 2, 4, 4, 32, 64)
+
+
+@pytest.mark.parametrize("name", ["wide"])
+def test_unet_on_tensor_cores_matches_simt(golden_dir, name):
+    """Every eligible convolution on tcgen05 (skip folding, pooled / upsampled residuals,
+    channel-concat sources) against the same network on the CUDA-core kernels."""
+    case = cases.UNET_CASES[name]
+    low, x, _ = synth_inputs(case["shape"], 0)
+    outs = {}
+    for path in (1, 2):
+        model, _, _, _ = build(case["flags"], seed=case.get("seed", 0), fp16=True)
+        model.set_option("conv_path", path)
+        model.set_option("profile", 1)
+        outs[path] = model(x.to(DEV), torch.tensor(case["t"], device=DEV), low_res=low.to(DEV)).cpu()
+        kinds = {k for k, _, _ in model.profile_read()}
+        assert ("conv_tcgen05" in kinds) == (path == 2)
+    assert max_rel(outs[2], outs[1]) <= 5e-3
