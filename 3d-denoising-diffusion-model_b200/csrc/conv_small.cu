@@ -1,0 +1,252 @@
+// The two thin convolutions at the ends of the network, on the CUDA cores:
+//
+//  * stem:  Conv3d(2 -> C, 3x3x3)   (unet.py:809-811)  K = 54: far too short for a tensor-core tile,
+//           bound by writing the (B,Z,H,W,C) result.
+//  * head:  Conv3d(C -> 1|2, 3x3x3) (unet.py:993-997)  N = 1|2: fp32 in the reference (it runs after
+//           h.type(x.dtype), unet.py:1043-1044), bound by reading the fp32 input once.
+//
+// Both stage a haloed input brick in shared memory (zero padding applied while staging) so every
+// input voxel is fetched from L2/HBM once per CTA and reused by the 27 taps from smem.
+#include "kernels.h"
+
+namespace ddpm3d {
+
+namespace {
+
+// =================================================================================================
+// head: C -> COUT (1 or 2), fp32 in, fp32 planar (NCDHW) out
+// =================================================================================================
+constexpr int HW_ = 32, HH_ = 8, HZ_ = 4;       // output brick per CTA: 32 x 8 x 4 voxels
+constexpr int HCC = 8;                          // channels staged per pass
+constexpr int HIW = HW_ + 2, HIH = HH_ + 2, HIZ = HZ_ + 2;
+constexpr int HEAD_THREADS = 256;               // lane -> w; warp -> (h half, z)
+
+template <int COUT>
+__global__ void __launch_bounds__(HEAD_THREADS, 2)
+head_conv_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                 float* __restrict__ out, int B, int Z, int H, int W, int C) {
+  extern __shared__ float4 sm4[];
+  float4* s_in = sm4;                                              // [2][HIZ][HIH][HIW] float4
+  float* s_w = reinterpret_cast<float*>(sm4 + 2 * HIZ * HIH * HIW);  // [27][COUT][HCC]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nWt = (W + HW_ - 1) / HW_, nHt = (H + HH_ - 1) / HH_, nZt = (Z + HZ_ - 1) / HZ_;
+  int t = blockIdx.x;
+  const int wt = t % nWt; t /= nWt;
+  const int ht = t % nHt; t /= nHt;
+  const int zt = t % nZt;
+  const int b = t / nZt;
+  const int w0 = wt * HW_, h0 = ht * HH_, z0 = zt * HZ_;
+  const int lz = warp >> 1, lh0 = (warp & 1) * 4;  // this thread: voxels (lz, lh0..lh0+3, lane)
+
+  float acc[4][COUT];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[i][c] = 0.f;
+
+  const int Ktot = 27 * C;
+  for (int c0 = 0; c0 < C; c0 += HCC) {
+    __syncthreads();
+    // stage the haloed brick: 8 channels (two float4) per voxel
+    for (int i = tid; i < HIZ * HIH * HIW * 2; i += HEAD_THREADS) {
+      const int q = i & 1;
+      int v = i >> 1;
+      const int iw = v % HIW; v /= HIW;
+      const int ih = v % HIH;
+      const int iz = v / HIH;
+      const int gz = z0 + iz - 1, gh = h0 + ih - 1, gw = w0 + iw - 1;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gz >= 0 && gz < Z && gh >= 0 && gh < H && gw >= 0 && gw < W)
+        val = __ldg(reinterpret_cast<const float4*>(in + ((((int64_t)b * Z + gz) * H + gh) * W + gw) * C + c0) + q);
+      s_in[((q * HIZ + iz) * HIH + ih) * HIW + iw] = val;
+    }
+    for (int i = tid; i < 27 * COUT * HCC; i += HEAD_THREADS) {
+      const int c = i % HCC;
+      const int co = (i / HCC) % COUT;
+      const int tap = i / (HCC * COUT);
+      s_w[i] = w[(int64_t)co * Ktot + tap * C + c0 + c];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int dz = 0; dz < 3; ++dz) {
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float4 x[6];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) x[r] = s_in[((q * HIZ + lz + dz) * HIH + lh0 + r) * HIW + lane + dw];
+#pragma unroll
+          for (int dh = 0; dh < 3; ++dh) {
+            const int tap = (dz * 3 + dh) * 3 + dw;
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+              const float4 wv = *reinterpret_cast<const float4*>(s_w + (tap * COUT + co) * HCC + q * 4);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 xv = x[i + dh];
+                acc[i][co] = fmaf(xv.x, wv.x, acc[i][co]);
+                acc[i][co] = fmaf(xv.y, wv.y, acc[i][co]);
+                acc[i][co] = fmaf(xv.z, wv.z, acc[i][co]);
+                acc[i][co] = fmaf(xv.w, wv.w, acc[i][co]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  const int gz = z0 + lz, gw = w0 + lane;
+  if (gz < Z && gw < W) {
+    const int64_t sp = (int64_t)Z * H * W;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gh = h0 + lh0 + i;
+      if (gh >= H) continue;
+      const int64_t pos = ((int64_t)gz * H + gh) * W + gw;
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) out[((int64_t)b * COUT + co) * sp + pos] = acc[i][co] + bias[co];
+    }
+  }
+}
+
+// =================================================================================================
+// stem: 2 -> Cout (multiple of 32), T in / T out, channels-last
+// =================================================================================================
+constexpr int SW_ = 32, SH_ = 8, SZ_ = 2;       // output brick per CTA: 32 x 8 x 2 voxels = 16 rows of 32
+constexpr int SIW = SW_ + 2, SIH = SH_ + 2, SIZ = SZ_ + 2;
+constexpr int STEM_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(STEM_THREADS, 2)
+stem_conv_kernel(const T* __restrict__ in, const T* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
+                 int B, int Z, int H, int W, int Cout) {
+  extern __shared__ float4 sm4[];
+  float* s_w = reinterpret_cast<float*>(sm4);         // [54][Cout]   (k-major so a channel group is contiguous)
+  float* s_b = s_w + 54 * Cout;                       // [Cout]
+  float2* s_in = reinterpret_cast<float2*>(s_b + Cout);  // [SIZ][SIH][SIW] (2 channels)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nWt = (W + SW_ - 1) / SW_, nHt = (H + SH_ - 1) / SH_, nZt = (Z + SZ_ - 1) / SZ_;
+  int t = blockIdx.x;
+  const int wt = t % nWt; t /= nWt;
+  const int ht = t % nHt; t /= nHt;
+  const int zt = t % nZt;
+  const int b = t / nZt;
+  const int w0 = wt * SW_, h0 = ht * SH_, z0 = zt * SZ_;
+
+  for (int i = tid; i < 54 * Cout; i += STEM_THREADS) {
+    const int n = i % Cout, k = i / Cout;  // packed weight: [Cout][54], k = tap*2 + ci
+    s_w[i] = to_f32(w[(int64_t)n * 54 + k]);
+  }
+  for (int i = tid; i < Cout; i += STEM_THREADS) s_b[i] = bias[i];
+  for (int i = tid; i < SIZ * SIH * SIW; i += STEM_THREADS) {
+    int v = i;
+    const int iw = v % SIW; v /= SIW;
+    const int ih = v % SIH;
+    const int iz = v / SIH;
+    const int gz = z0 + iz - 1, gh = h0 + ih - 1, gw = w0 + iw - 1;
+    float2 val = make_float2(0.f, 0.f);
+    if (gz >= 0 && gz < Z && gh >= 0 && gh < H && gw >= 0 && gw < W) {
+      const T* p = in + ((((int64_t)b * Z + gz) * H + gh) * W + gw) * 2;
+      val = make_float2(to_f32(p[0]), to_f32(p[1]));
+    }
+    s_in[i] = val;
+  }
+  __syncthreads();
+
+  const int ngroups = Cout / 32;
+  const int nwork = SZ_ * SH_ * ngroups;  // (row, channel group) pairs, one per warp pass
+  for (int item = warp; item < nwork; item += STEM_THREADS / 32) {
+    const int g = item % ngroups;
+    const int row = item / ngroups;
+    const int lh = row % SH_, lz = row / SH_;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = s_b[g * 32 + j];
+#pragma unroll 1
+    for (int tap = 0; tap < 27; ++tap) {
+      const int dz = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
+      const float2 v = s_in[((lz + dz) * SIH + lh + dh) * SIW + lane + dw];
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const float xk = ci ? v.y : v.x;
+        const float4* wp = reinterpret_cast<const float4*>(s_w + (2 * tap + ci) * Cout + g * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 wv = wp[j];  // same address for the whole warp: broadcast
+          acc[4 * j] = fmaf(xk, wv.x, acc[4 * j]);
+          acc[4 * j + 1] = fmaf(xk, wv.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(xk, wv.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(xk, wv.w, acc[4 * j + 3]);
+        }
+      }
+    }
+    const int gz = z0 + lz, gh = h0 + lh, gw = w0 + lane;
+    if (gz < Z && gh < H && gw < W) {
+      T* op = out + ((((int64_t)b * Z + gz) * H + gh) * W + gw) * Cout + g * 32;
+      constexpr int N = Vec<T>::N;
+#pragma unroll
+      for (int j = 0; j < 32 / N; ++j) {
+        Vec<T> v;
+        v.pack(acc + j * N);
+        v.store(op + j * N);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+bool conv_head_eligible(const ConvArgs& a) {
+  return a.out_planar_f32 && a.dt == DDPM3D_FP32 && a.taps == 27 && a.stride_hw == 1 && a.n_extra == 0 && !a.residual &&
+         (a.Cout == 1 || a.Cout == 2) && a.main.C % HCC == 0 && (reinterpret_cast<uintptr_t>(a.main.ptr) & 15) == 0;
+}
+
+int conv_head(const ConvArgs& a, cudaStream_t s) {
+  DD_CHECK(conv_head_eligible(a), DDPM3D_ERR_ARG, "conv_head: shape not eligible");
+  const int nWt = (int)ceil_div(a.Wo, HW_), nHt = (int)ceil_div(a.Ho, HH_), nZt = (int)ceil_div(a.Z, HZ_);
+  const int grid = a.B * nZt * nHt * nWt;
+  const size_t smem = (size_t)2 * HIZ * HIH * HIW * sizeof(float4) + (size_t)27 * a.Cout * HCC * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    DD_CUDA(cudaFuncSetAttribute(head_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    DD_CUDA(cudaFuncSetAttribute(head_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
+  if (a.Cout == 1)
+    head_conv_kernel<1><<<grid, HEAD_THREADS, smem, s>>>((const float*)a.main.ptr, (const float*)a.w, a.bias, (float*)a.out,
+                                                         a.B, a.Z, a.Ho, a.Wo, a.main.C);
+  else
+    head_conv_kernel<2><<<grid, HEAD_THREADS, smem, s>>>((const float*)a.main.ptr, (const float*)a.w, a.bias, (float*)a.out,
+                                                         a.B, a.Z, a.Ho, a.Wo, a.main.C);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
+bool conv_stem_eligible(const ConvArgs& a) {
+  return !a.out_planar_f32 && a.main.C == 2 && a.taps == 27 && a.stride_hw == 1 && a.n_extra == 0 && !a.residual &&
+         a.Cout % 32 == 0 && a.Cout <= 512 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+}
+
+int conv_stem(const ConvArgs& a, cudaStream_t s) {
+  DD_CHECK(conv_stem_eligible(a), DDPM3D_ERR_ARG, "conv_stem: shape not eligible");
+  const int nWt = (int)ceil_div(a.Wo, SW_), nHt = (int)ceil_div(a.Ho, SH_), nZt = (int)ceil_div(a.Z, SZ_);
+  const int grid = a.B * nZt * nHt * nWt;
+  const size_t smem = (size_t)(54 + 1) * a.Cout * sizeof(float) + (size_t)SIZ * SIH * SIW * sizeof(float2);
+  static bool configured = false;
+  if (!configured) {
+    DD_CUDA(cudaFuncSetAttribute(stem_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    DD_CUDA(cudaFuncSetAttribute(stem_conv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured = true;
+  }
+  if (a.dt == DDPM3D_BF16)
+    stem_conv_kernel<bf16><<<grid, STEM_THREADS, smem, s>>>((const bf16*)a.main.ptr, (const bf16*)a.w, a.bias, (bf16*)a.out,
+                                                            a.B, a.Z, a.Ho, a.Wo, a.Cout);
+  else
+    stem_conv_kernel<float><<<grid, STEM_THREADS, smem, s>>>((const float*)a.main.ptr, (const float*)a.w, a.bias,
+                                                             (float*)a.out, a.B, a.Z, a.Ho, a.Wo, a.Cout);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
+}  // namespace ddpm3d

@@ -442,8 +442,10 @@ struct Run {
     for (int e = 0; e < a.n_extra; ++e) K += a.extra[e].C;
     const double flops = 2.0 * B * Z * a.Ho * a.Wo * (double)a.Cout * K;
     const bool tc = a.dt == DDPM3D_BF16 && ctx->conv_path != 1 && conv_tc_eligible(a);
-    prof_begin(tc ? 0 : 1, flops);
-    const int r = tc ? conv_tc(a, s) : conv_simt(a, s);
+    const bool stem = !tc && ctx->conv_path != 1 && conv_stem_eligible(a);
+    const bool head = !tc && ctx->conv_path != 1 && conv_head_eligible(a);
+    prof_begin(tc ? 0 : ((stem || head) ? 9 : 1), flops);
+    const int r = tc ? conv_tc(a, s) : (stem ? conv_stem(a, s) : (head ? conv_head(a, s) : conv_simt(a, s)));
     prof_end();
     return r;
   }

@@ -33,6 +33,11 @@ struct ConvArgs {
 };
 
 int conv_simt(const ConvArgs& a, cudaStream_t s);
+// thin ends of the network on the CUDA cores with smem-staged halo bricks (conv_small.cu)
+bool conv_stem_eligible(const ConvArgs& a);  // Cin == 2
+int conv_stem(const ConvArgs& a, cudaStream_t s);
+bool conv_head_eligible(const ConvArgs& a);  // Cout <= 2, fp32, planar output
+int conv_head(const ConvArgs& a, cudaStream_t s);
 // tcgen05 path; returns DDPM3D_ERR_ARG (without launching) when the shape is not eligible.
 bool conv_tc_eligible(const ConvArgs& a);
 int conv_tc(const ConvArgs& a, cudaStream_t s);

@@ -160,14 +160,14 @@ int ddpm3d_sample_loop(ddpm3d_ctx* ctx, const float* x_T, const float* low_res, 
 
 /* ---- knobs and introspection ------------------------------------------------------------------ */
 /* "cuda_graph" (0/1, default 1): replay one captured graph per UNet evaluation;
- * "conv_path" (0 = auto, 1 = force SIMT fp32-accumulate kernels, 2 = force tcgen05 where legal);
+ * "conv_path" (0 = auto, 1 = force the generic CUDA-core kernel everywhere, 2 = same as 0);
  * "profile" (0/1): record a CUDA-event pair around every kernel launch (disables graphs). */
 int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value);
 /* Kernel launches enqueued by this ctx since creation. */
 int64_t ddpm3d_launch_count(const ddpm3d_ctx* ctx);
 /* After a profiled call: synchronises and writes up to `cap` records; returns the record count.
  * `kind`: 0 conv-tcgen05, 1 conv-simt, 2 gn-stats, 3 gn-finalize, 4 gn-apply, 5 embedding, 6 update,
- * 7 attention, 8 pack/resample/misc.  `work` = algorithmic flops (conv, attention) or bytes (others). */
+ * 7 attention, 8 pack/resample/misc, 9 conv-small (stem / head direct convolutions).  `work` = algorithmic flops (conv, attention) or bytes (others). */
 typedef struct ddpm3d_prof_record { int32_t kind; int32_t pad_; float ms; float pad2_; double work; } ddpm3d_prof_record;
 int ddpm3d_profile_read(ddpm3d_ctx* ctx, ddpm3d_prof_record* out, int cap);
 

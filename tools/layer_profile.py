@@ -1,0 +1,36 @@
+"""Per-launch table of one C2 UNet evaluation from the library's own profile mode
+(CUDA events around every launch on the launching stream)."""
+import os, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import bench
+from ddpm3d_b200 import script_util as su
+
+dev = torch.device("cuda", 0)
+shape = bench.PATCH
+if len(sys.argv) > 1:
+    z, h, w = (int(v) for v in sys.argv[1].split(","))
+    shape = (1, 1, z, h, w)
+model, diffusion = su.sr_create_model_and_diffusion(**bench.C2_FLAGS)
+model.load_state_dict(bench.synth_weights(model._specs))
+model.to(dev); model.convert_to_fp16(); model.eval()
+g = torch.Generator().manual_seed(0)
+x = torch.randn(shape, generator=g).to(dev); low = torch.rand(shape, generator=g).to(dev)
+t = torch.tensor([500.0], device=dev)
+for _ in range(2):
+    model(x, t, low_res=low)
+model.set_option("profile", 1)
+model(x, t, low_res=low)
+model.profile_read()
+model(x, t, low_res=low)
+recs = model.profile_read()
+tot = sum(r[1] for r in recs)
+print(f"total {tot:.3f} ms over {len(recs)} launches")
+agg = {}
+for i, (kind, ms, work) in enumerate(recs):
+    if kind.startswith("conv") or kind == "attention":
+        rate = f"{work / ms / 1e9:8.1f} TFLOP/s" if ms > 0 else ""
+    else:
+        rate = f"{work / ms / 1e6:8.1f} GB/s" if ms > 0 and work > 0 else ""
+    print(f"{i:3d} {kind:13s} {ms:8.4f} ms  work {work:.4g} {rate}")
