@@ -42,8 +42,9 @@ struct TcParams {
   int n_main_steps;  // taps * chunks[0]
   int nk;            // total k-steps
   int taps;          // 27 or 1
-  int bw, bh, bz;    // brick
-  int nWt, nHt, nZt, nNt;
+  int bw, bh, bz;    // brick (one 128-row MMA tile)
+  int pw, ph, pz;    // offset of the second brick of a CTA tile (MT == 2): exactly one is non-zero
+  int nWt, nHt, nZt, nNt;  // CTA tiles per dimension (a CTA tile = MT bricks)
   int num_tiles;
   int B, Z, Ho, Wo, Cout;
   uint32_t a_tx_bytes;  // bytes one A box delivers
@@ -162,13 +163,15 @@ __device__ __forceinline__ void add8(float* v, const bf16* p, float scale) {
   }
 }
 
-template <int BN, int NSTAGE>
+template <int MT, int BN, int NSTAGE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
   constexpr int B_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = 2 * BN;  // 128, 256 or 512: a power of two >= 32
+  constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
+  constexpr int ACC_COLS = MT * BN;       // fp32 accumulator columns of one CTA tile
+  constexpr int TMEM_COLS = 2 * ACC_COLS;  // double buffered; 128, 256 or 512: a power of two >= 32
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation must be a power of two <= 512");
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * NSTAGE + 4];
   __shared__ uint32_t tmem_base_slot;
@@ -213,22 +216,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int ht = m % p.nHt; m /= p.nHt;
         const int zt = m % p.nZt;
         const int b = m / p.nZt;
-        const int w0 = wt * p.bw, h0 = ht * p.bh, z0 = zt * p.bz, n0 = nt * BN;
+        const int w0 = wt * p.bw * (p.pw ? MT : 1), h0 = ht * p.bh * (p.ph ? MT : 1), z0 = zt * p.bz * (p.pz ? MT : 1);
+        const int n0 = nt * BN;
         for (int kk = 0; kk < p.nk; ++kk) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), p.a_tx_bytes + B_BYTES);
+          mbar_expect_tx(full_bar(stage), MT * p.a_tx_bytes + B_BYTES);
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-          const uint32_t b_dst = a_dst + A_BYTES;
+          const uint32_t b_dst = a_dst + MT * A_BYTES;
+          const CUtensorMap* map;
+          int c0, dz = 0, dh = 0, dw = 0;
           if (kk < p.n_main_steps) {
             const int tap = p.taps == 27 ? kk / p.chunks[0] : 13;
-            const int c0 = (kk - (p.taps == 27 ? tap * p.chunks[0] : 0)) * BK;
-            const int dz = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
-            tma_load_5d(a_dst, &mapA0, full_bar(stage), c0, w0 + dw, h0 + dh, z0 + dz, b);
+            c0 = (kk - (p.taps == 27 ? tap * p.chunks[0] : 0)) * BK;
+            dz = tap / 9 - 1; dh = (tap / 3) % 3 - 1; dw = tap % 3 - 1;
+            map = &mapA0;
           } else {
             const int e = kk - p.n_main_steps;
-            if (e < p.chunks[1]) tma_load_5d(a_dst, &mapA1, full_bar(stage), e * BK, w0, h0, z0, b);
-            else tma_load_5d(a_dst, &mapA2, full_bar(stage), (e - p.chunks[1]) * BK, w0, h0, z0, b);
+            if (e < p.chunks[1]) { map = &mapA1; c0 = e * BK; }
+            else { map = &mapA2; c0 = (e - p.chunks[1]) * BK; }
           }
+#pragma unroll
+          for (int j = 0; j < MT; ++j)
+            tma_load_5d(a_dst + j * A_BYTES, map, full_bar(stage), c0, w0 + j * p.pw + dw, h0 + j * p.ph + dh,
+                        z0 + j * p.pz + dz, b);
           tma_load_2d(b_dst, &mapW, full_bar(stage), kk * BK, n0);
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
@@ -245,17 +255,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
         for (int kk = 0; kk < p.nk; ++kk) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
-          const uint64_t adesc = make_sw128_desc(a_addr);
-          const uint64_t bdesc = make_sw128_desc(a_addr + A_BYTES);
+          const uint64_t bdesc = make_sw128_desc(a_addr + MT * A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kk | k) != 0);
+          for (int j = 0; j < MT; ++j) {
+            const uint64_t adesc = make_sw128_desc(a_addr + j * A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+              umma_bf16(d_tmem + (uint32_t)(j * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kk | k) != 0);
+            }
           }
           umma_commit(empty_bar(stage));  // slot is free once these MMAs have read it
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -280,12 +293,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const int n0 = nt * BN;
       // row -> voxel of the brick (same enumeration as the TMA box: w fastest, then h, then z)
       const int rw = row % p.bw, rh = (row / p.bw) % p.bh, rz = row / (p.bw * p.bh);
-      const int w = wt * p.bw + rw, h = ht * p.bh + rh, z = zt * p.bz + rz;
-      const bool valid = rz < p.bz && w < p.Wo && h < p.Ho && z < p.Z;
-      const int64_t vox = (((int64_t)b * p.Z + z) * p.Ho + h) * p.Wo + w;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+      const int w = wt * p.bw * (p.pw ? MT : 1) + mt * p.pw + rw, h = ht * p.bh * (p.ph ? MT : 1) + mt * p.ph + rh,
+                z = zt * p.bz * (p.pz ? MT : 1) + mt * p.pz + rz;
+      const bool valid = rz < p.bz && w < p.Wo && h < p.Ho && z < p.Z;
+      const int64_t vox = (((int64_t)b * p.Z + z) * p.Ho + h) * p.Wo + w;
+      const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * ACC_COLS + mt * BN);
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
@@ -341,6 +357,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
         }
       }
+      }  // MT
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -434,16 +451,17 @@ int sm_count() {
   return n;
 }
 
-template <int BN, int NSTAGE>
+template <int MT, int BN, int NSTAGE>
 int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s) {
-  constexpr size_t smem = (size_t)NSTAGE * (A_BYTES + BN * BK * 2) + 1024;
+  constexpr size_t smem = (size_t)NSTAGE * (MT * A_BYTES + BN * BK * 2) + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MT, BN, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const int grid = std::min(p.num_tiles, sm_count());
-  conv_tc_kernel<BN, NSTAGE><<<grid, NTHREADS, smem, s>>>(maps[0], maps[1], maps[2], mapW, p);
+  conv_tc_kernel<MT, BN, NSTAGE><<<grid, NTHREADS, smem, s>>>(maps[0], maps[1], maps[2], mapW, p);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }
@@ -479,10 +497,33 @@ int conv_tc(const ConvArgs& a, cudaStream_t s) {
     Ktot += a.extra[e].C;
   }
   choose_brick(a.Z, a.Ho, a.Wo, &p.bw, &p.bh, &p.bz);
-  const int BN = (a.Cout % 128 == 0) ? 128 : 64;
-  p.nWt = (int)ceil_div(a.Wo, p.bw);
-  p.nHt = (int)ceil_div(a.Ho, p.bh);
-  p.nZt = (int)ceil_div(a.Z, p.bz);
+  int nW = (int)ceil_div(a.Wo, p.bw), nH = (int)ceil_div(a.Ho, p.bh), nZ = (int)ceil_div(a.Z, p.bz);
+  // Tile shape.  Bytes pulled through L2 per MMA are what bounds this kernel, so prefer 256 accumulator
+  // columns per k-step: either one brick x 256 output channels, or two bricks sharing one 128-channel
+  // weight tile.  Small layers keep single bricks so that every SM still gets a tile.
+  int BN = (a.Cout % 128 == 0) ? 128 : 64;
+  int MT = 1;
+  const int64_t bricks = (int64_t)a.B * nW * nH * nZ;
+  if (a.Cout % 256 == 0 && bricks * (a.Cout / 256) >= sm_count()) {
+    BN = 256;
+  } else if (BN == 128 && bricks / 2 * (a.Cout / 128) >= sm_count()) {
+    // pair bricks along the dimension that wastes the least (an even brick count wastes nothing)
+    const int n[3] = {nH, nZ, nW};
+    int best = -1;
+    double best_w = 1e9;
+    for (int d = 0; d < 3; ++d) {
+      if (n[d] < 2) continue;
+      const double waste = (double)(2 * ((n[d] + 1) / 2)) / n[d];
+      if (waste < best_w - 1e-9) { best_w = waste; best = d; }
+    }
+    if (best >= 0 && best_w <= 1.13) {
+      MT = 2;
+      if (best == 0) { p.ph = p.bh; nH = (nH + 1) / 2; }
+      else if (best == 1) { p.pz = p.bz; nZ = (nZ + 1) / 2; }
+      else { p.pw = p.bw; nW = (nW + 1) / 2; }
+    }
+  }
+  p.nWt = nW; p.nHt = nH; p.nZt = nZ;
   p.nNt = a.Cout / BN;
   p.num_tiles = a.B * p.nZt * p.nHt * p.nWt * p.nNt;
   p.B = a.B; p.Z = a.Z; p.Ho = a.Ho; p.Wo = a.Wo; p.Cout = a.Cout;
@@ -500,8 +541,10 @@ int conv_tc(const ConvArgs& a, cudaStream_t s) {
     DD_TRY(make_act_map(&maps[1 + e], a.extra[e].ptr, a.B, a.Z, a.Ho, a.Wo, a.extra[e].C, p.bw, p.bh, p.bz));
   CUtensorMap mapW;
   DD_TRY(make_w_map(&mapW, a.w, a.Cout, Ktot, BN));
-  if (BN == 128) return launch<128, 6>(maps, mapW, p, s);
-  return launch<64, 8>(maps, mapW, p, s);
+  if (MT == 2) return launch<2, 128, 4>(maps, mapW, p, s);
+  if (BN == 256) return launch<1, 256, 4>(maps, mapW, p, s);
+  if (BN == 128) return launch<1, 128, 6>(maps, mapW, p, s);
+  return launch<1, 64, 8>(maps, mapW, p, s);
 }
 
 }  // namespace ddpm3d

@@ -37,16 +37,19 @@ int pack_input(int dt, const float* x, const float* low, void* out, int64_t n, c
 // Algorithmic HBM bytes: 2 reads + 1 write of the tensor.
 // =================================================================================================
 int gn_chunks(int64_t rows) {
-  int64_t c = rows / 256;
+  // about four stats CTAs per SM at full size; never fewer than 64 rows per chunk
+  int64_t c = rows / 64;
   if (c < 1) c = 1;
-  if (c > 1024) c = 1024;
+  if (c > 592) c = 592;
   return (int)c;
 }
 
+// thread -> (row lane r, channel vector v); every thread keeps its channel vector for the whole kernel,
+// so a warp always touches whole rows (>= 64 contiguous bytes) and no index arithmetic sits in the loop
 template <typename T>
-__global__ void gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int C1, int64_t rows,
-                                int n_chunks, const float* __restrict__ pre_add, int64_t pre_stride,
-                                float* __restrict__ partials) {
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int C1,
+                                                       int rows, int n_chunks, const float* __restrict__ pre_add,
+                                                       int64_t pre_stride, float* __restrict__ partials) {
   constexpr int N = Vec<T>::N;
   extern __shared__ float sm[];  // [rpi][Ctot][2]
   const int Ctot = C0 + C1;
@@ -54,14 +57,13 @@ __global__ void gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ 
   const int rpi = blockDim.x / nvec;
   const int v = threadIdx.x % nvec, r = threadIdx.x / nvec;
   const int b = blockIdx.y, chunk = blockIdx.x;
-  const int64_t per = ceil_div(rows, (int64_t)n_chunks);
-  const int64_t r0 = chunk * per, r1 = min(rows, r0 + per);
+  const int per = (rows + n_chunks - 1) / n_chunks;
+  const int r0 = chunk * per, r1 = min(rows, r0 + per);
 
   const T* base;
-  int Csrc, coff;
-  if (v < nvec0) { base = s0; Csrc = C0; coff = v * N; }
-  else { base = s1; Csrc = C1; coff = (v - nvec0) * N; }
-  base += (int64_t)b * rows * Csrc + coff;
+  int Csrc;
+  if (v < nvec0) { base = s0 + (int64_t)b * rows * C0 + v * N; Csrc = C0; }
+  else { base = s1 + (int64_t)b * rows * C1 + (v - nvec0) * N; Csrc = C1; }
 
   float add[N];
 #pragma unroll
@@ -74,55 +76,58 @@ __global__ void gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ 
   float s[N], q[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) { s[i] = 0.f; q[i] = 0.f; }
-  int64_t row = r0 + r;
-  // 4 independent 16-byte loads in flight per thread
-  for (; row + 3 * rpi < r1; row += 4 * rpi) {
-    Vec<T> a[4];
+  constexpr int U = 8;  // independent 16-byte loads in flight per thread
+  int row = r0 + r;
+  for (; row + (U - 1) * rpi < r1; row += U * rpi) {
+    Vec<T> a[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) a[u].load(base + (row + (int64_t)u * rpi) * Csrc);
+    for (int u = 0; u < U; ++u) a[u].load(base + (int64_t)(row + u * rpi) * Csrc);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       float f[N];
       a[u].unpack(f);
 #pragma unroll
-      for (int i = 0; i < N; ++i) { const float x = f[i] + add[i]; s[i] += x; q[i] += x * x; }
+      for (int i = 0; i < N; ++i) { const float x = f[i] + add[i]; s[i] += x; q[i] = fmaf(x, x, q[i]); }
     }
   }
   for (; row < r1; row += rpi) {
     Vec<T> a;
-    a.load(base + row * Csrc);
+    a.load(base + (int64_t)row * Csrc);
     float f[N];
     a.unpack(f);
 #pragma unroll
-    for (int i = 0; i < N; ++i) { const float x = f[i] + add[i]; s[i] += x; q[i] += x * x; }
+    for (int i = 0; i < N; ++i) { const float x = f[i] + add[i]; s[i] += x; q[i] = fmaf(x, x, q[i]); }
   }
   float* mine = sm + ((int64_t)r * Ctot + v * N) * 2;
 #pragma unroll
   for (int i = 0; i < N; ++i) { mine[2 * i] = s[i]; mine[2 * i + 1] = q[i]; }
   __syncthreads();
-  // group g sums its channels over the rpi row-lanes in a fixed order
+  // group g sums its channels over the rpi row-lanes in a fixed order (deterministic)
   const int gpc = Ctot / 32;
   if (threadIdx.x < 64) {
     const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
     float acc = 0.f;
     for (int rr = 0; rr < rpi; ++rr)
       for (int c = g * gpc; c < (g + 1) * gpc; ++c) acc += sm[((int64_t)rr * Ctot + c) * 2 + which];
-    partials[(((int64_t)b * n_chunks + chunk) * 32 + g) * 2 + which] = acc;
+    partials[(((int64_t)b * 32 + g) * 2 + which) * n_chunks + chunk] = acc;
   }
 }
 
-__global__ void gn_finalize_kernel(const float* __restrict__ partials, int n_chunks, int Ctot, double inv_count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   const float* __restrict__ film, int64_t film_stride,
-                                   const float* __restrict__ pre_add, int64_t pre_stride, float* __restrict__ ab) {
+// partials: [B][32 groups][2][n_chunks]
+__global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restrict__ partials, int n_chunks, int Ctot,
+                                                           double inv_count, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, const float* __restrict__ film,
+                                                           int64_t film_stride, const float* __restrict__ pre_add,
+                                                           int64_t pre_stride, float* __restrict__ ab) {
   __shared__ float s_mean[32], s_rstd[32];
   const int b = blockIdx.x;
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 1024 threads: one warp per group
+  const float* ps = partials + (((int64_t)b * 32 + g) * 2) * n_chunks;
+  const float* pq = ps + n_chunks;
   double s = 0.0, q = 0.0;
-  for (int c = lane; c < n_chunks; c += 32) {
-    const float* p = partials + (((int64_t)b * n_chunks + c) * 32 + g) * 2;
-    s += (double)p[0];
-    q += (double)p[1];
+  for (int c = lane; c < n_chunks; c += 32) {  // coalesced; fixed order -> deterministic
+    s += (double)ps[c];
+    q += (double)pq[c];
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -156,48 +161,95 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partials, int n_chu
   }
 }
 
+template <typename T, typename TO, int N>
+__device__ __forceinline__ void gn_put(TO* dst, const float* y) {
+  if constexpr (sizeof(TO) == sizeof(T)) {
+    Vec<TO> o;
+    o.pack(y);
+    o.store(dst);
+  } else {  // T = bf16, TO = float: two 16-byte stores
+#pragma unroll
+    for (int k = 0; k < N; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(y[k], y[k + 1], y[k + 2], y[k + 3]);
+  }
+}
+
+// grid (blocks, B); thread -> (row lane, channel vector); the per-(b, c) affine lives in registers.
+// Iteration space: output rows for NONE / POOL, input rows for UP.
 template <typename T, typename TO, int MODE, bool SILU>
-__global__ void gn_apply_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int C1, int B, int Z, int H,
-                                int W, const float* __restrict__ ab, TO* __restrict__ out) {
+__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int C1, int Z,
+                                                       int H, int W, int rows_per_block, const float* __restrict__ ab,
+                                                       TO* __restrict__ out) {
   constexpr int N = Vec<T>::N;
   const int Ctot = C0 + C1;
   const int nvec0 = C0 / N, nvec = Ctot / N;
+  const int rpi = blockDim.x / nvec;
+  const int v = threadIdx.x % nvec, r = threadIdx.x / nvec;
+  const int b = blockIdx.y;
   const int Ho = MODE == RS_POOL ? H / 2 : H, Wo = MODE == RS_POOL ? W / 2 : W;
-  // iteration space: output rows for NONE/POOL, input rows for UP
-  const int64_t rows_it = (int64_t)B * Z * Ho * Wo;
-  const int64_t total = rows_it * nvec;
-  const int64_t rows_b_it = (int64_t)Z * Ho * Wo;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int v = (int)(i % nvec);
-    const int64_t row = i / nvec;
-    const int b = (int)(row / rows_b_it);
-    const T* base;
-    int Csrc, coff;
-    if (v < nvec0) { base = s0; Csrc = C0; coff = v * N; }
-    else { base = s1; Csrc = C1; coff = (v - nvec0) * N; }
-    float A[N], Bv[N];
-    {
-      const float* pa = ab + (int64_t)b * 2 * Ctot + v * N;
+  const int rows_it = Z * Ho * Wo;        // rows iterated per batch element
+  const int rows_in = Z * H * W;
+  const int rows_out = MODE == RS_UP ? 4 * rows_in : rows_it;
+  const T* base;
+  int Csrc;
+  if (v < nvec0) { base = s0 + (int64_t)b * rows_in * C0 + v * N; Csrc = C0; }
+  else { base = s1 + (int64_t)b * rows_in * C1 + (v - nvec0) * N; Csrc = C1; }
+  TO* obase = out + (int64_t)b * rows_out * Ctot + v * N;
+  float A[N], Bv[N];
+  {
+    const float* pa = ab + (int64_t)b * 2 * Ctot + v * N;
 #pragma unroll
-      for (int k = 0; k < N; k += 4) {
-        const float4 a4 = *reinterpret_cast<const float4*>(pa + k);
-        const float4 b4 = *reinterpret_cast<const float4*>(pa + Ctot + k);
-        A[k] = a4.x; A[k + 1] = a4.y; A[k + 2] = a4.z; A[k + 3] = a4.w;
-        Bv[k] = b4.x; Bv[k + 1] = b4.y; Bv[k + 2] = b4.z; Bv[k + 3] = b4.w;
+    for (int k = 0; k < N; k += 4) {
+      const float4 a4 = *reinterpret_cast<const float4*>(pa + k);
+      const float4 b4 = *reinterpret_cast<const float4*>(pa + Ctot + k);
+      A[k] = a4.x; A[k + 1] = a4.y; A[k + 2] = a4.z; A[k + 3] = a4.w;
+      Bv[k] = b4.x; Bv[k + 1] = b4.y; Bv[k + 2] = b4.z; Bv[k + 3] = b4.w;
+    }
+  }
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows_it, r0 + rows_per_block);
+  if (MODE == RS_NONE) {
+    constexpr int U = 4;
+    int row = r0 + r;
+    for (; row + (U - 1) * rpi < r1; row += U * rpi) {
+      Vec<T> a[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) a[u].load(base + (int64_t)(row + u * rpi) * Csrc);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float f[N], y[N];
+        a[u].unpack(f);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const float t = fmaf(f[k], A[k], Bv[k]);
+          y[k] = SILU ? silu_f(t) : t;
+        }
+        gn_put<T, TO, N>(obase + (int64_t)(row + u * rpi) * Ctot, y);
       }
     }
-    float y[N];
-    if (MODE == RS_POOL) {
-      const int wo = (int)(row % Wo);
-      const int64_t t1 = row / Wo;
-      const int ho = (int)(t1 % Ho);
-      const int64_t bz = t1 / Ho;  // b*Z + z
-      const int64_t in_row = (bz * H + 2 * ho) * W + 2 * wo;
+    for (; row < r1; row += rpi) {
+      Vec<T> a;
+      a.load(base + (int64_t)row * Csrc);
+      float f[N], y[N];
+      a.unpack(f);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const float t = fmaf(f[k], A[k], Bv[k]);
+        y[k] = SILU ? silu_f(t) : t;
+      }
+      gn_put<T, TO, N>(obase + (int64_t)row * Ctot, y);
+    }
+  } else if (MODE == RS_POOL) {
+    for (int row = r0 + r; row < r1; row += rpi) {
+      const int wo = row % Wo;
+      const int t1 = row / Wo;
+      const int ho = t1 % Ho;
+      const int z = t1 / Ho;
+      const int in_row = (z * H + 2 * ho) * W + 2 * wo;
       Vec<T> a[4];
-      a[0].load(base + in_row * Csrc + coff);
-      a[1].load(base + (in_row + 1) * Csrc + coff);
-      a[2].load(base + (in_row + W) * Csrc + coff);
-      a[3].load(base + (in_row + W + 1) * Csrc + coff);
+      a[0].load(base + (int64_t)in_row * Csrc);
+      a[1].load(base + (int64_t)(in_row + 1) * Csrc);
+      a[2].load(base + (int64_t)(in_row + W) * Csrc);
+      a[3].load(base + (int64_t)(in_row + W + 1) * Csrc);
+      float y[N];
 #pragma unroll
       for (int k = 0; k < N; ++k) y[k] = 0.f;
 #pragma unroll
@@ -206,62 +258,63 @@ __global__ void gn_apply_kernel(const T* __restrict__ s0, const T* __restrict__ 
         a[u].unpack(f);
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-          float t = f[k] * A[k] + Bv[k];
-          if (SILU) t = silu_f(t);
-          y[k] += t;
+          const float t = fmaf(f[k], A[k], Bv[k]);
+          y[k] += SILU ? silu_f(t) : t;
         }
       }
 #pragma unroll
       for (int k = 0; k < N; ++k) y[k] *= 0.25f;
-    } else {
+      gn_put<T, TO, N>(obase + (int64_t)row * Ctot, y);
+    }
+  } else {  // RS_UP: one input row -> four output rows
+    for (int row = r0 + r; row < r1; row += rpi) {
       Vec<T> a;
-      a.load(base + row * Csrc + coff);
-      float f[N];
+      a.load(base + (int64_t)row * Csrc);
+      float f[N], y[N];
       a.unpack(f);
 #pragma unroll
       for (int k = 0; k < N; ++k) {
-        float t = f[k] * A[k] + Bv[k];
-        if (SILU) t = silu_f(t);
-        y[k] = t;
+        const float t = fmaf(f[k], A[k], Bv[k]);
+        y[k] = SILU ? silu_f(t) : t;
       }
-    }
-    // store (fp32 output uses two 16-byte stores when N == 8)
-    auto put = [&](int64_t orow) {
-      TO* dst = out + orow * Ctot + v * N;
-      if constexpr (sizeof(TO) == sizeof(T)) {
-        Vec<TO> o;
-        o.pack(y);
-        o.store(dst);
-      } else {  // T = bf16, TO = float
-#pragma unroll
-        for (int k = 0; k < N; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(y[k], y[k + 1], y[k + 2], y[k + 3]);
-      }
-    };
-    if (MODE == RS_UP) {
-      const int w = (int)(row % W);
-      const int64_t t1 = row / W;
-      const int h = (int)(t1 % H);
-      const int64_t bz = t1 / H;
-      const int64_t o0 = (bz * (2 * H) + 2 * h) * (2 * W) + 2 * w;
-      put(o0); put(o0 + 1); put(o0 + 2 * W); put(o0 + 2 * W + 1);
-    } else {
-      put(row);
+      const int w = row % W;
+      const int t1 = row / W;
+      const int h = t1 % H;
+      const int z = t1 / H;
+      const int64_t o0 = ((int64_t)(z * 2 * H + 2 * h)) * (2 * W) + 2 * w;
+      gn_put<T, TO, N>(obase + o0 * Ctot, y);
+      gn_put<T, TO, N>(obase + (o0 + 1) * Ctot, y);
+      gn_put<T, TO, N>(obase + (o0 + 2 * W) * Ctot, y);
+      gn_put<T, TO, N>(obase + (o0 + 2 * W + 1) * Ctot, y);
     }
   }
+}
+
+static int gn_threads(int nvec, int* rpi_out) {
+  int rpi = 256 / nvec;
+  if (rpi < 1) rpi = 1;
+  *rpi_out = rpi;
+  return nvec * rpi;
 }
 
 template <typename T, typename TO>
 static int gn_apply_launch(const GnArgs& a, cudaStream_t s) {
   constexpr int N = Vec<T>::N;
   const int Ctot = a.C[0] + a.C[1];
+  const int nvec = Ctot / N;
+  int rpi;
+  const int threads = gn_threads(nvec, &rpi);
   const int Ho = a.resample == RS_POOL ? a.H / 2 : a.H, Wo = a.resample == RS_POOL ? a.W / 2 : a.W;
-  const int64_t total = (int64_t)a.B * a.Z * Ho * Wo * (Ctot / N);
-  const int threads = 256;
-  const int blocks = (int)std::min<int64_t>(ceil_div(total, threads), 148 * 32);
+  const int rows_it = a.Z * Ho * Wo;
+  // ~8 CTAs per SM over the whole launch, at least 4 passes of the row lanes per CTA
+  int blocks = (int)std::min<int64_t>(ceil_div(rows_it, 4 * rpi), std::max(1, 148 * 8 / a.B));
+  const int rows_per_block = (int)ceil_div(rows_it, blocks);
+  blocks = (int)ceil_div(rows_it, rows_per_block);
+  dim3 grid(blocks, a.B);
   const T* s0 = (const T*)a.src[0];
   const T* s1 = (const T*)a.src[1];
 #define GN_LAUNCH(MODE, SILU) \
-  gn_apply_kernel<T, TO, MODE, SILU><<<blocks, threads, 0, s>>>(s0, s1, a.C[0], a.C[1], a.B, a.Z, a.H, a.W, a.ab, (TO*)a.out)
+  gn_apply_kernel<T, TO, MODE, SILU><<<grid, threads, 0, s>>>(s0, s1, a.C[0], a.C[1], a.Z, a.H, a.W, rows_per_block, a.ab, (TO*)a.out)
   if (a.silu) {
     if (a.resample == RS_NONE) GN_LAUNCH(RS_NONE, true);
     else if (a.resample == RS_POOL) GN_LAUNCH(RS_POOL, true);
@@ -281,14 +334,14 @@ static int gn_stats_launch(const GnArgs& a, cudaStream_t s) {
   constexpr int N = Vec<T>::N;
   const int Ctot = a.C[0] + a.C[1];
   const int nvec = Ctot / N;
-  int rpi = 256 / nvec;
-  if (rpi < 1) rpi = 1;
-  const int threads = nvec * rpi;
-  DD_CHECK(threads <= 1024 && threads >= 64, DDPM3D_ERR_ARG, "groupnorm: unsupported channel count");
+  int rpi;
+  const int threads = gn_threads(nvec, &rpi);
+  DD_CHECK(threads <= 256 && threads >= 64, DDPM3D_ERR_ARG, "groupnorm: unsupported channel count");
   const int64_t rows = (int64_t)a.Z * a.H * a.W;
+  DD_CHECK(rows * 4 < ((int64_t)1 << 31), DDPM3D_ERR_ARG, "groupnorm: more than 2^29 voxels per batch element");
   const size_t smem = (size_t)rpi * Ctot * 2 * sizeof(float);
   dim3 grid(a.n_chunks, a.B);
-  gn_stats_kernel<T><<<grid, threads, smem, s>>>((const T*)a.src[0], (const T*)a.src[1], a.C[0], a.C[1], rows, a.n_chunks,
+  gn_stats_kernel<T><<<grid, threads, smem, s>>>((const T*)a.src[0], (const T*)a.src[1], a.C[0], a.C[1], (int)rows, a.n_chunks,
                                                  a.pre_add, a.pre_stride, a.partials);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
