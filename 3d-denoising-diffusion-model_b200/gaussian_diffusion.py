@@ -247,7 +247,7 @@ class GaussianDiffusion:
                                                      model_kwargs=model_kwargs, device=device, progress=progress,
                                                      _final_only=True, **ext):
             final = sample
-        return final["sample"]
+        return final["sample"].clone()  # the native path reuses its output buffers across calls
 
     def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None,
                                   cond_fn=None, model_kwargs=None, device=None, progress=False,

@@ -195,6 +195,22 @@ int ddpm3d_k_timestep_embedding(const float* t, const float* freqs, float* out, 
 /* QKVAttentionLegacy / QKVAttention core (unet.py:328-393): qkv [B][T][3C] channels-last -> out [B][T][C]. */
 int ddpm3d_k_attention(int dtype, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, void* stream);
 
+/* ---- the steps either side of the loop (scripts/test.py) and the ensemble reduction ----------------
+ * extract_patch: scripts/test.py:205-230 -- vol device fp32 (D,H,W); out (P,P,P) in (Z,H,W) order, zero padded. */
+int ddpm3d_k_extract_patch(const float* vol, int D, int H, int W, int z0, int h0, int w0, int P, float* out, void* stream);
+/* hann_accumulate: scripts/test.py:91-137 -- patch (P,P,P) (Z,H,W) order; window = np.hanning(P) as device fp64 [P],
+ * window_max = max(window)^3; arr / wsum device fp32 in the reference's (H,W,Z) output order.  Bit-identical to
+ * the reference's numpy arithmetic (fp32 * fp64 -> fp64 -> stored fp32). */
+int ddpm3d_k_hann_accumulate(const float* patch, const double* window, double window_max, int P, int D, int H, int W,
+                             int z0, int h0, int w0, float* arr, float* wsum, void* stream);
+/* hann_finalize: scripts/test.py:139 -- arr /= wsum where wsum > 0. */
+int ddpm3d_k_hann_finalize(float* arr, const float* wsum, int64_t n, void* stream);
+/* Uncertainty-map ensemble (README.md:44; BASELINE config 5): voxel-wise Welford update with one more sample
+ * (count_after = number of samples including x) and the merge of two partials (a <- a (+) b). */
+int ddpm3d_k_welford_update(float* mean, float* m2, const float* x, int count_after, int64_t n, void* stream);
+int ddpm3d_k_welford_merge(float* mean_a, float* m2_a, int na, const float* mean_b, const float* m2_b, int nb, int64_t n,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,7 +52,36 @@ def ref_model(flags, sd):
     return model, diffusion
 
 
+VOLUME_DIMS = [(200, 96, 3), (36, 16, 3), (16, 16, 3), (50, 16, 3), (130, 96, 3), (20, 16, 1)]
+VOLUME_Z = [(110, 96), (96, 96), (20, 16), (90, 96), (130, 96), (16, 16)]
+HANN_SIZES = [96, 16, 5]
+
+
+def make_volume_golden():
+    """scripts/test.py helpers (the module needs tifffile / mpi4py / blobfile, absent here: stub them; none
+    is used by the three functions called)."""
+    import importlib.util
+    import types
+    for name in ("tifffile", "mpi4py", "blobfile"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["mpi4py"].MPI = types.SimpleNamespace()
+    spec = importlib.util.spec_from_file_location("ref_test_script", "/root/reference/scripts/test.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    z = {}
+    for i, (dim, p, n) in enumerate(VOLUME_DIMS):
+        z[f"xy{i}"] = np.array(ref._calculate_xy_starts_fixed(dim, p, num_patches=n), dtype=np.int64)
+    for i, (dim, p) in enumerate(VOLUME_Z):
+        z[f"z{i}"] = np.array(ref._calculate_z_starts_with_overlap(dim, p), dtype=np.int64)
+    for s_ in HANN_SIZES:
+        z[f"hann{s_}"] = ref.create_3d_hann_window(s_).reshape(-1)[::7 if s_ == 96 else 1]
+    np.savez_compressed(os.path.join(OUT, "volume.npz"), **z)
+
+
 def main():
+    if "--volume-only" in sys.argv:
+        make_volume_golden()
+        return
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
 
@@ -162,6 +191,7 @@ def main():
         "mo_std": np.array([float(m.std()) for m in mos]),
     }
     np.savez_compressed(os.path.join(OUT, "c1_loop.npz"), **z)
+    make_volume_golden()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
