@@ -90,3 +90,9 @@ UNET_CASES = {
     "wide": dict(flags=dict(**{**_TINY, "num_channels": 64, "num_res_blocks": 2, "num_head_channels": 64}),
                  shape=(1, 1, 8, 16, 16), t=[555], seed=9),
 }
+
+
+# scripts/test.py tiling helpers: (dim, patch, num_patches), (dim, patch), window sizes
+VOLUME_DIMS = [(200, 96, 3), (36, 16, 3), (16, 16, 3), (50, 16, 3), (130, 96, 3), (20, 16, 1)]
+VOLUME_Z = [(110, 96), (96, 96), (20, 16), (90, 96), (130, 96), (16, 16)]
+HANN_SIZES = [96, 16, 5]

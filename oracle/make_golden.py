@@ -32,6 +32,7 @@ from guided_diffusion.respace import space_timesteps as ref_space  # noqa: E402
 
 from oracle.cases import (  # noqa: E402
     SCHEDULE_CASES, SPACING_CASES, TEMB_CASES, PMV_CASES, UNET_CASES, C1_FLAGS, C1_SHAPE,
+    VOLUME_DIMS, VOLUME_Z, HANN_SIZES,
     sr_flags, cfg_from_flags,
 )
 from oracle.weights import synth_state_dict, synth_inputs  # noqa: E402
@@ -50,11 +51,6 @@ def ref_model(flags, sd):
     model.load_state_dict(sd, strict=True)  # proves key/shape compatibility
     model.eval()
     return model, diffusion
-
-
-VOLUME_DIMS = [(200, 96, 3), (36, 16, 3), (16, 16, 3), (50, 16, 3), (130, 96, 3), (20, 16, 1)]
-VOLUME_Z = [(110, 96), (96, 96), (20, 16), (90, 96), (130, 96), (16, 16)]
-HANN_SIZES = [96, 16, 5]
 
 
 def make_volume_golden():

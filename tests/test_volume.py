@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 from ddpm3d_b200 import dist_util, volume
 from oracle import volume as ov
-from oracle.make_golden import HANN_SIZES, VOLUME_DIMS, VOLUME_Z
+from oracle.cases import HANN_SIZES, VOLUME_DIMS, VOLUME_Z
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
