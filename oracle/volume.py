@@ -66,5 +66,9 @@ def blend(patches_zhw, vol_shape, resolution):
                 arr[x0:x1, y0:y1, z0:z1] += patch[:hx, :wy, :dz] * win[:hx, :wy, :dz]
                 wsum[x0:x1, y0:y1, z0:z1] += win[:hx, :wy, :dz]
                 k += 1
-    arr = np.divide(arr, wsum, where=wsum > 0)
-    return arr, wsum
+    # scripts/test.py:139 calls np.divide(arr, wsum, where=wsum > 0) WITHOUT `out=`: voxels whose total Hann
+    # weight is 0 (the outer faces of the volume, np.hanning(P)[0] == 0) come back as uninitialised memory in
+    # the reference.  They are pinned to the accumulated value (0) here and in the CUDA path.
+    out = arr.copy()
+    np.divide(arr, wsum, out=out, where=wsum > 0)
+    return out, wsum
