@@ -81,8 +81,9 @@ int launch(const void* qkv, void* out, int B, int T_tok, int C, int heads, int n
 
 int attention_k(int dt, const void* qkv, void* out, int B, int T_tok, int C, int heads, int new_order, cudaStream_t s) {
   DD_CHECK(heads > 0 && C % heads == 0, DDPM3D_ERR_ARG, "attention: C must be divisible by heads");
-  return dt == DDPM3D_BF16 ? launch<bf16>(qkv, out, B, T_tok, C, heads, new_order, s)
-                           : launch<float>(qkv, out, B, T_tok, C, heads, new_order, s);
+  if (dt == DDPM3D_BF16) return launch<bf16>(qkv, out, B, T_tok, C, heads, new_order, s);
+  if (dt == DDPM3D_FP16) return launch<f16>(qkv, out, B, T_tok, C, heads, new_order, s);
+  return launch<float>(qkv, out, B, T_tok, C, heads, new_order, s);
 }
 
 }  // namespace ddpm3d

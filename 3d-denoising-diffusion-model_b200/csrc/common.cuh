@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -39,15 +40,41 @@ void set_error(const std::string& msg);
   } while (0)
 
 typedef __nv_bfloat16 bf16;
+typedef __half f16;
+
+__host__ __device__ inline bool is_half_dt(int dt) { return dt == DDPM3D_BF16 || dt == DDPM3D_FP16; }
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- scalar conversions ------------------------------------------------------------------
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32(f16 v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ f16 from_f32<f16>(float v) { return __float2half_rn(v); }
+
+// two packed 16-bit elements <-> two floats
+template <typename T> __device__ __forceinline__ void unpack2(uint32_t w, float& a, float& b);
+template <> __device__ __forceinline__ void unpack2<bf16>(uint32_t w, float& a, float& b) {
+  a = __uint_as_float(w << 16);
+  b = __uint_as_float(w & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void unpack2<f16>(uint32_t w, float& a, float& b) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+  a = f.x;
+  b = f.y;
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<bf16>(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<f16>(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 
 // ---- 16-byte vectors of activations ---------------------------------------------------------
 // A "vec" is 16 bytes: 4 floats or 8 bf16.  All channel counts on the path are multiples of 8
@@ -82,6 +109,21 @@ template <> struct Vec<bf16> {
       w[i] = *reinterpret_cast<uint32_t*>(&h);
     }
     raw = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+template <> struct Vec<f16> {
+  static constexpr int N = 8;
+  uint4 raw;
+  __device__ __forceinline__ void load(const f16* p) { raw = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(f16* p) const { *reinterpret_cast<uint4*>(p) = raw; }
+  __device__ __forceinline__ void unpack(float* f) const {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) unpack2<f16>(w[i], f[2 * i], f[2 * i + 1]);
+  }
+  __device__ __forceinline__ void pack(const float* f) {
+    raw = make_uint4(pack2<f16>(f[0], f[1]), pack2<f16>(f[2], f[3]), pack2<f16>(f[4], f[5]), pack2<f16>(f[6], f[7]));
   }
 };
 

@@ -47,11 +47,25 @@ template <> struct Ld8<bf16> {
     v.unpack(f);
   }
 };
+template <> struct Ld8<f16> {
+  __device__ static void ld(const f16* p, float* f) {
+    Vec<f16> v;
+    v.load(p);
+    v.unpack(f);
+  }
+};
 template <typename T> struct Ld4;
 template <> struct Ld4<float> {
   __device__ static void ld(const float* p, float* f) {
     const float4 a = *reinterpret_cast<const float4*>(p);
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  }
+};
+template <> struct Ld4<f16> {
+  __device__ static void ld(const f16* p, float* f) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    unpack2<f16>(r.x, f[0], f[1]);
+    unpack2<f16>(r.y, f[2], f[3]);
   }
 };
 template <> struct Ld4<bf16> {
@@ -245,10 +259,9 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(SimtParams p) {
         if constexpr (sizeof(T) == 4) {
           *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
         } else {
-          __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
           uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&lo);
-          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          pk.x = pack2<T>(v[0], v[1]);
+          pk.y = pack2<T>(v[2], v[3]);
           *reinterpret_cast<uint2*>(o) = pk;
         }
       }
@@ -300,6 +313,9 @@ int conv_simt(const ConvArgs& a, cudaStream_t s) {
   if (a.dt == DDPM3D_BF16) {
     if (vec) conv_simt_kernel<bf16, true><<<grid, THREADS, 0, s>>>(p);
     else conv_simt_kernel<bf16, false><<<grid, THREADS, 0, s>>>(p);
+  } else if (a.dt == DDPM3D_FP16) {
+    if (vec) conv_simt_kernel<f16, true><<<grid, THREADS, 0, s>>>(p);
+    else conv_simt_kernel<f16, false><<<grid, THREADS, 0, s>>>(p);
   } else {
     if (vec) conv_simt_kernel<float, true><<<grid, THREADS, 0, s>>>(p);
     else conv_simt_kernel<float, false><<<grid, THREADS, 0, s>>>(p);

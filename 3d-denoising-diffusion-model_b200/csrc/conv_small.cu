@@ -237,11 +237,15 @@ int conv_stem(const ConvArgs& a, cudaStream_t s) {
   if (!configured) {
     DD_CUDA(cudaFuncSetAttribute(stem_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     DD_CUDA(cudaFuncSetAttribute(stem_conv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    DD_CUDA(cudaFuncSetAttribute(stem_conv_kernel<f16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     configured = true;
   }
   if (a.dt == DDPM3D_BF16)
     stem_conv_kernel<bf16><<<grid, STEM_THREADS, smem, s>>>((const bf16*)a.main.ptr, (const bf16*)a.w, a.bias, (bf16*)a.out,
                                                             a.B, a.Z, a.Ho, a.Wo, a.Cout);
+  else if (a.dt == DDPM3D_FP16)
+    stem_conv_kernel<f16><<<grid, STEM_THREADS, smem, s>>>((const f16*)a.main.ptr, (const f16*)a.w, a.bias, (f16*)a.out,
+                                                           a.B, a.Z, a.Ho, a.Wo, a.Cout);
   else
     stem_conv_kernel<float><<<grid, STEM_THREADS, smem, s>>>((const float*)a.main.ptr, (const float*)a.w, a.bias,
                                                              (float*)a.out, a.B, a.Z, a.Ho, a.Wo, a.Cout);

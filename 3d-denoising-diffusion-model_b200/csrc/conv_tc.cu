@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "kernels.h"
 
@@ -49,9 +50,9 @@ struct TcParams {
   int B, Z, Ho, Wo, Cout;
   uint32_t a_tx_bytes;  // bytes one A box delivers
   const float* bias;
-  const bf16* res;
+  const void* res;   // T
   int res_mode;
-  bf16* out;
+  void* out;         // T
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -122,9 +123,10 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D fp32, A = B = bf16, both K-major, M x N.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// kind::f16 instruction descriptor: D fp32, A and B both bf16 (format 1) or both fp16 (format 0), K-major, M x N.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool is_bf16) {
+  return (1u << 4) | ((is_bf16 ? 1u : 0u) << 7) | ((is_bf16 ? 1u : 0u) << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -153,17 +155,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void add8(float* v, const bf16* p, float scale) {
+template <typename T>
+__device__ __forceinline__ void add8(float* v, const T* p, float scale) {
   const uint4 raw = *reinterpret_cast<const uint4*>(p);
   const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    v[2 * i] += scale * __uint_as_float(w[i] << 16);
-    v[2 * i + 1] += scale * __uint_as_float(w[i] & 0xffff0000u);
+    float a, b;
+    unpack2<T>(w[i], a, b);
+    v[2 * i] += scale * a;
+    v[2 * i + 1] += scale * b;
   }
 }
 
-template <int MT, int BN, int NSTAGE>
+template <typename T, int MT, int BN, int NSTAGE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
@@ -247,7 +252,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      constexpr uint32_t idesc = make_idesc(BM, BN, sizeof(T) == 2 && !std::is_same<T, f16>::value);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -319,9 +324,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
           }
           if (p.res_mode == RES_SAME) {
-            const bf16* rp = p.res + vox * p.Cout + n0 + c;
+            const T* rp = (const T*)p.res + vox * p.Cout + n0 + c;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) add8(v + 8 * j, rp + 8 * j, 1.0f);
+            for (int j = 0; j < 4; ++j) add8<T>(v + 8 * j, rp + 8 * j, 1.0f);
           } else if (p.res_mode == RES_POOL) {  // residual = AvgPool(1,2,2) of a (2Ho, 2Wo) tensor
             const int Hr = 2 * p.Ho, Wr = 2 * p.Wo;
             const int64_t r0 = (((int64_t)b * p.Z + z) * Hr + 2 * h) * Wr + 2 * w;
@@ -331,28 +336,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int64_t offs[4] = {r0, r0 + 1, r0 + Wr, r0 + Wr + 1};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const bf16* rp = p.res + offs[q] * p.Cout + n0 + c;
+              const T* rp = (const T*)p.res + offs[q] * p.Cout + n0 + c;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) add8(s + 8 * j, rp + 8 * j, 1.0f);
+              for (int j = 0; j < 4; ++j) add8<T>(s + 8 * j, rp + 8 * j, 1.0f);
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += 0.25f * s[j];
           } else if (p.res_mode == RES_UP) {  // residual = nearest x2 of a (Ho/2, Wo/2) tensor
             const int Hr = p.Ho / 2, Wr = p.Wo / 2;
             const int64_t r0 = (((int64_t)b * p.Z + z) * Hr + h / 2) * Wr + w / 2;
-            const bf16* rp = p.res + r0 * p.Cout + n0 + c;
+            const T* rp = (const T*)p.res + r0 * p.Cout + n0 + c;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) add8(v + 8 * j, rp + 8 * j, 1.0f);
+            for (int j = 0; j < 4; ++j) add8<T>(v + 8 * j, rp + 8 * j, 1.0f);
           }
-          bf16* op = p.out + vox * p.Cout + n0 + c;
+          T* op = (T*)p.out + vox * p.Cout + n0 + c;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint32_t w4[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
-              w4[q] = *reinterpret_cast<uint32_t*>(&h2);
-            }
+            for (int q = 0; q < 4; ++q) w4[q] = pack2<T>(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
             *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
         }
@@ -393,7 +395,8 @@ EncodeTiledFn get_encode() {
 }
 
 // channels-last activation [B][Z][H][W][C] -> 5-D map, box {64, bw, bh, bz, 1}
-int make_act_map(CUtensorMap* map, const void* ptr, int B, int Z, int H, int W, int C, int bw, int bh, int bz) {
+int make_act_map(CUtensorMap* map, CUtensorMapDataType dtype, const void* ptr, int B, int Z, int H, int W, int C, int bw, int bh,
+                 int bz) {
   EncodeTiledFn enc = get_encode();
   DD_CHECK(enc != nullptr, DDPM3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Z, (cuuint64_t)B};
@@ -401,21 +404,21 @@ int make_act_map(CUtensorMap* map, const void* ptr, int B, int Z, int H, int W, 
                                  (cuuint64_t)Z * H * W * C * 2};
   const cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bz, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+  const CUresult r = enc(map, dtype, 5, const_cast<void*>(ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DD_CHECK(r == CUDA_SUCCESS, DDPM3D_ERR_CUDA, "cuTensorMapEncodeTiled (activation) failed: " + std::to_string((int)r));
   return DDPM3D_OK;
 }
 
-int make_w_map(CUtensorMap* map, const void* ptr, int Cout, int Ktot, int bn) {
+int make_w_map(CUtensorMap* map, CUtensorMapDataType dtype, const void* ptr, int Cout, int Ktot, int bn) {
   EncodeTiledFn enc = get_encode();
   DD_CHECK(enc != nullptr, DDPM3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   const cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
   const cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
   const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  const CUresult r = enc(map, dtype, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DD_CHECK(r == CUDA_SUCCESS, DDPM3D_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed: " + std::to_string((int)r));
@@ -451,17 +454,17 @@ int sm_count() {
   return n;
 }
 
-template <int MT, int BN, int NSTAGE>
+template <typename T, int MT, int BN, int NSTAGE>
 int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s) {
   constexpr size_t smem = (size_t)NSTAGE * (MT * A_BYTES + BN * BK * 2) + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MT, BN, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, MT, BN, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const int grid = std::min(p.num_tiles, sm_count());
-  conv_tc_kernel<MT, BN, NSTAGE><<<grid, NTHREADS, smem, s>>>(maps[0], maps[1], maps[2], mapW, p);
+  conv_tc_kernel<T, MT, BN, NSTAGE><<<grid, NTHREADS, smem, s>>>(maps[0], maps[1], maps[2], mapW, p);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }
@@ -469,7 +472,7 @@ int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, 
 }  // namespace
 
 bool conv_tc_eligible(const ConvArgs& a) {
-  if (a.dt != DDPM3D_BF16 || a.out_planar_f32 || a.stride_hw != 1) return false;
+  if (!is_half_dt(a.dt) || a.out_planar_f32 || a.stride_hw != 1) return false;
   if (a.taps != 27 && a.taps != 1) return false;
   if (a.main.C % BK != 0 || a.Cout % 64 != 0) return false;
   for (int e = 0; e < a.n_extra; ++e)
@@ -529,22 +532,29 @@ int conv_tc(const ConvArgs& a, cudaStream_t s) {
   p.B = a.B; p.Z = a.Z; p.Ho = a.Ho; p.Wo = a.Wo; p.Cout = a.Cout;
   p.a_tx_bytes = (uint32_t)(p.bw * p.bh * p.bz * BK * 2);
   p.bias = a.bias;
-  p.res = (const bf16*)a.residual;
+  p.res = a.residual;
   p.res_mode = a.residual ? a.res_mode : RES_NONE;
-  p.out = (bf16*)a.out;
+  p.out = a.out;
 
+  const CUtensorMapDataType tdt = a.dt == DDPM3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap maps[3];
-  DD_TRY(make_act_map(&maps[0], a.main.ptr, a.B, a.Z, a.Ho, a.Wo, a.main.C, p.bw, p.bh, p.bz));
+  DD_TRY(make_act_map(&maps[0], tdt, a.main.ptr, a.B, a.Z, a.Ho, a.Wo, a.main.C, p.bw, p.bh, p.bz));
   maps[1] = maps[0];
   maps[2] = maps[0];
   for (int e = 0; e < a.n_extra; ++e)
-    DD_TRY(make_act_map(&maps[1 + e], a.extra[e].ptr, a.B, a.Z, a.Ho, a.Wo, a.extra[e].C, p.bw, p.bh, p.bz));
+    DD_TRY(make_act_map(&maps[1 + e], tdt, a.extra[e].ptr, a.B, a.Z, a.Ho, a.Wo, a.extra[e].C, p.bw, p.bh, p.bz));
   CUtensorMap mapW;
-  DD_TRY(make_w_map(&mapW, a.w, a.Cout, Ktot, BN));
-  if (MT == 2) return launch<2, 128, 4>(maps, mapW, p, s);
-  if (BN == 256) return launch<1, 256, 4>(maps, mapW, p, s);
-  if (BN == 128) return launch<1, 128, 6>(maps, mapW, p, s);
-  return launch<1, 64, 8>(maps, mapW, p, s);
+  DD_TRY(make_w_map(&mapW, tdt, a.w, a.Cout, Ktot, BN));
+  if (a.dt == DDPM3D_BF16) {
+    if (MT == 2) return launch<bf16, 2, 128, 4>(maps, mapW, p, s);
+    if (BN == 256) return launch<bf16, 1, 256, 4>(maps, mapW, p, s);
+    if (BN == 128) return launch<bf16, 1, 128, 6>(maps, mapW, p, s);
+    return launch<bf16, 1, 64, 8>(maps, mapW, p, s);
+  }
+  if (MT == 2) return launch<f16, 2, 128, 4>(maps, mapW, p, s);
+  if (BN == 256) return launch<f16, 1, 256, 4>(maps, mapW, p, s);
+  if (BN == 128) return launch<f16, 1, 128, 6>(maps, mapW, p, s);
+  return launch<f16, 1, 64, 8>(maps, mapW, p, s);
 }
 
 }  // namespace ddpm3d

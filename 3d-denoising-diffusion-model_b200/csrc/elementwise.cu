@@ -22,6 +22,8 @@ int pack_input(int dt, const float* x, const float* low, void* out, int64_t n, c
   const int blocks = (int)std::min<int64_t>(ceil_div(n, threads), 148 * 16);
   if (dt == DDPM3D_BF16)
     pack_input_kernel<bf16><<<blocks, threads, 0, s>>>(x, low, (bf16*)out, n);
+  else if (dt == DDPM3D_FP16)
+    pack_input_kernel<f16><<<blocks, threads, 0, s>>>(x, low, (f16*)out, n);
   else
     pack_input_kernel<float><<<blocks, threads, 0, s>>>(x, low, (float*)out, n);
   DD_CUDA(cudaGetLastError());
@@ -349,12 +351,13 @@ static int gn_stats_launch(const GnArgs& a, cudaStream_t s) {
 
 int gn_forward(const GnArgs& a, cudaStream_t s, int* launches) {
   const int Ctot = a.C[0] + a.C[1];
-  const int N = a.dt == DDPM3D_BF16 ? 8 : 4;
+  const int N = is_half_dt(a.dt) ? 8 : 4;
   DD_CHECK(Ctot % 32 == 0, DDPM3D_ERR_ARG, "groupnorm: channels must be a multiple of 32");
   DD_CHECK(a.C[0] % N == 0 && a.C[1] % N == 0, DDPM3D_ERR_ARG, "groupnorm: per-source channels must fill 16-byte vectors");
   DD_CHECK(a.resample != RS_POOL || (a.H % 2 == 0 && a.W % 2 == 0), DDPM3D_ERR_ARG, "groupnorm: pool needs even H, W");
   DD_CHECK(!(a.out_f32 && a.dt == DDPM3D_FP32 && false), DDPM3D_ERR_ARG, "");
   if (a.dt == DDPM3D_BF16) DD_TRY(gn_stats_launch<bf16>(a, s));
+  else if (a.dt == DDPM3D_FP16) DD_TRY(gn_stats_launch<f16>(a, s));
   else DD_TRY(gn_stats_launch<float>(a, s));
   const double inv_count = 1.0 / ((double)a.Z * a.H * a.W * (Ctot / 32));
   gn_finalize_kernel<<<a.B, 1024, 0, s>>>(a.partials, a.n_chunks, Ctot, inv_count, a.gamma, a.beta, a.film, a.film_stride,
@@ -363,6 +366,9 @@ int gn_forward(const GnArgs& a, cudaStream_t s, int* launches) {
   if (a.dt == DDPM3D_BF16) {
     if (a.out_f32) DD_TRY((gn_apply_launch<bf16, float>(a, s)));
     else DD_TRY((gn_apply_launch<bf16, bf16>(a, s)));
+  } else if (a.dt == DDPM3D_FP16) {
+    if (a.out_f32) DD_TRY((gn_apply_launch<f16, float>(a, s)));
+    else DD_TRY((gn_apply_launch<f16, f16>(a, s)));
   } else {
     DD_TRY((gn_apply_launch<float, float>(a, s)));
   }
@@ -423,7 +429,7 @@ __global__ void resample_kernel(const T* __restrict__ in, T* __restrict__ out, i
 }
 
 int resample_hw(int dt, const void* in, void* out, int B, int Z, int H, int W, int C, int mode, cudaStream_t s) {
-  const int N = dt == DDPM3D_BF16 ? 8 : 4;
+  const int N = is_half_dt(dt) ? 8 : 4;
   DD_CHECK(C % N == 0, DDPM3D_ERR_ARG, "resample: channels must fill 16-byte vectors");
   DD_CHECK(mode == RS_POOL || mode == RS_UP, DDPM3D_ERR_ARG, "resample: bad mode");
   const int Ho = mode == RS_POOL ? H / 2 : H, Wo = mode == RS_POOL ? W / 2 : W;
@@ -433,6 +439,9 @@ int resample_hw(int dt, const void* in, void* out, int B, int Z, int H, int W, i
   if (dt == DDPM3D_BF16) {
     if (mode == RS_POOL) resample_kernel<bf16, RS_POOL><<<blocks, threads, 0, s>>>((const bf16*)in, (bf16*)out, B, Z, H, W, C);
     else resample_kernel<bf16, RS_UP><<<blocks, threads, 0, s>>>((const bf16*)in, (bf16*)out, B, Z, H, W, C);
+  } else if (dt == DDPM3D_FP16) {
+    if (mode == RS_POOL) resample_kernel<f16, RS_POOL><<<blocks, threads, 0, s>>>((const f16*)in, (f16*)out, B, Z, H, W, C);
+    else resample_kernel<f16, RS_UP><<<blocks, threads, 0, s>>>((const f16*)in, (f16*)out, B, Z, H, W, C);
   } else {
     if (mode == RS_POOL) resample_kernel<float, RS_POOL><<<blocks, threads, 0, s>>>((const float*)in, (float*)out, B, Z, H, W, C);
     else resample_kernel<float, RS_UP><<<blocks, threads, 0, s>>>((const float*)in, (float*)out, B, Z, H, W, C);

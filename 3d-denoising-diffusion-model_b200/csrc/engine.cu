@@ -87,6 +87,29 @@ uint16_t f32_to_bf16_rn(float f) {
   return (uint16_t)(u >> 16);
 }
 
+uint16_t f32_to_f16_rn(float f) {
+  uint32_t x;
+  std::memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  const uint32_t mant = x & 0x007fffffu;
+  const int32_t exp = (int32_t)((x >> 23) & 0xff) - 127 + 15;
+  if (((x >> 23) & 0xff) == 0xff) return (uint16_t)(sign | 0x7c00u | (mant ? 0x200u : 0));  // inf / nan
+  if (exp >= 31) return (uint16_t)(sign | 0x7c00u);                                           // overflow -> inf
+  if (exp <= 0) {                                                                              // subnormal / zero
+    if (exp < -10) return (uint16_t)sign;
+    const uint32_t m = mant | 0x00800000u;
+    const int shift = 14 - exp;
+    uint32_t h = m >> shift;
+    const uint32_t rem = m & ((1u << shift) - 1), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (h & 1))) ++h;
+    return (uint16_t)(sign | h);
+  }
+  uint32_t h = ((uint32_t)exp << 10) | (mant >> 13);
+  const uint32_t rem = mant & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) ++h;  // may carry into the exponent: still correct
+  return (uint16_t)(sign | h);
+}
+
 struct GraphKey {
   int kind;  // 0 forward, 1 p_sample step, 2 loop step
   int B, Z, H, W;
@@ -362,9 +385,10 @@ int pack_conv(ddpm3d_ctx* ctx, int dt, const std::string& wkey, const std::strin
     for (int64_t co = 0; co < Cout; ++co) bias[co] += sb->host[co];
   out->Ktot = (int)Ktot;
   DD_TRY(upload(ctx, bias.data(), bias.size() * sizeof(float), (void**)&out->bias));
-  if (dt == DDPM3D_BF16) {
+  if (is_half_dt(dt)) {
     std::vector<uint16_t> h(packed.size());
-    for (size_t i = 0; i < packed.size(); ++i) h[i] = f32_to_bf16_rn(packed[i]);
+    if (dt == DDPM3D_BF16) for (size_t i = 0; i < packed.size(); ++i) h[i] = f32_to_bf16_rn(packed[i]);
+    else for (size_t i = 0; i < packed.size(); ++i) h[i] = f32_to_f16_rn(packed[i]);
     DD_TRY(upload(ctx, h.data(), h.size() * 2, &out->w));
   } else {
     DD_TRY(upload(ctx, packed.data(), packed.size() * 4, &out->w));
@@ -441,7 +465,7 @@ struct Run {
     double K = (double)a.taps * a.main.C;
     for (int e = 0; e < a.n_extra; ++e) K += a.extra[e].C;
     const double flops = 2.0 * B * Z * a.Ho * a.Wo * (double)a.Cout * K;
-    const bool tc = a.dt == DDPM3D_BF16 && ctx->conv_path != 1 && conv_tc_eligible(a);
+    const bool tc = is_half_dt(a.dt) && ctx->conv_path != 1 && conv_tc_eligible(a);
     const bool stem = !tc && ctx->conv_path != 1 && conv_stem_eligible(a);
     const bool head = !tc && ctx->conv_path != 1 && conv_head_eligible(a);
     prof_begin(tc ? 0 : ((stem || head) ? 9 : 1), flops);
@@ -460,7 +484,7 @@ struct Run {
     launches += 3;
     if (arena.dry) return DDPM3D_OK;
     const double n = (double)B * Z * g.H * g.W * Ctot;
-    const double in_b = g.dt == DDPM3D_BF16 ? 2 : 4, out_b = (g.dt == DDPM3D_BF16 && !g.out_f32) ? 2 : 4;
+    const double in_b = is_half_dt(g.dt) ? 2 : 4, out_b = (is_half_dt(g.dt) && !g.out_f32) ? 2 : 4;
     const double scale = g.resample == RS_POOL ? 0.25 : (g.resample == RS_UP ? 4.0 : 1.0);
     prof_begin(4, n * (2 * in_b + out_b * scale));
     int dummy = 0;
@@ -852,11 +876,11 @@ int ddpm3d_abi_version(void) { return DDPM3D_ABI_VERSION; }
 
 int ddpm3d_create(const ddpm3d_config* cfg, ddpm3d_ctx** out) {
   DD_CHECK(cfg && out, DDPM3D_ERR_ARG, "ddpm3d_create: null argument");
-  DD_CHECK(cfg->precision == DDPM3D_FP32 || cfg->precision == DDPM3D_BF16, DDPM3D_ERR_ARG, "config: bad precision");
+  DD_CHECK(cfg->precision == DDPM3D_FP32 || is_half_dt(cfg->precision), DDPM3D_ERR_ARG, "config: bad precision");
   std::unique_ptr<ddpm3d_ctx> ctx(new ddpm3d_ctx());
   ctx->cfg = *cfg;
   ctx->dt = cfg->precision;
-  ctx->esz = cfg->precision == DDPM3D_BF16 ? 2 : 4;
+  ctx->esz = is_half_dt(cfg->precision) ? 2 : 4;
   DD_TRY(build_topology(ctx.get()));
   *out = ctx.release();
   return DDPM3D_OK;
@@ -1160,7 +1184,7 @@ int ddpm3d_k_conv3d(int dtype, int path, const void* in, const void* w, const fl
   a.residual = residual; a.res_mode = residual ? RES_SAME : RES_NONE;
   a.out = out; a.B = B; a.Z = Z; a.Ho = H / stride_hw; a.Wo = W / stride_hw; a.Cout = Cout;
   if (path == 2) {
-    DD_CHECK(dtype == DDPM3D_BF16 && conv_tc_eligible(a), DDPM3D_ERR_ARG, "k_conv3d: shape not eligible for the tcgen05 path");
+    DD_CHECK(is_half_dt(dtype) && conv_tc_eligible(a), DDPM3D_ERR_ARG, "k_conv3d: shape not eligible for the tcgen05 path");
     return conv_tc(a, (cudaStream_t)stream);
   }
   return conv_simt(a, (cudaStream_t)stream);

@@ -56,6 +56,11 @@ def timestep_freqs(dim, max_period=10000):
     return torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half).contiguous()
 
 
+def _half_from_env():
+    import os
+    return {"bf16": N.BF16, "fp16": N.FP16}[os.environ.get("DDPM3D_HALF_DTYPE", "bf16").lower()]
+
+
 class _Ctx:
     """RAII wrapper of ddpm3d_ctx*."""
 
@@ -136,7 +141,8 @@ class UNetModel_noatt:
         self.resblock_updown = resblock_updown
         self.use_new_attention_order = use_new_attention_order
         self.training = True
-        self._precision = N.BF16 if use_fp16 else N.FP32
+        self._half = _half_from_env()
+        self._precision = self._half if use_fp16 else N.FP32
         self._device = torch.device("cpu")
         self._ctx = None
         self._ctx_sig = None
@@ -238,11 +244,24 @@ class UNetModel_noatt:
         return self
 
     def convert_to_fp16(self):
-        """unet.py:999-1005.  The torso (input/middle/output blocks) runs in bf16 on tcgen05 tensor cores;
+        """unet.py:999-1005.  The torso (input/middle/output blocks) runs in 16-bit on tcgen05 tensor cores
+        (bf16 by default as BASELINE.json names it; the reference's own fp16 with set_half_dtype("fp16"));
         time_embed, emb_layers, GroupNorm statistics and the `out` head stay fp32 like the reference."""
-        if self._precision != N.BF16:
-            self._precision = N.BF16
+        if self._precision != self._half:
+            self._precision = self._half
             self._drop_ctx()
+
+    def set_half_dtype(self, name):
+        """Which 16-bit type `use_fp16` / convert_to_fp16() means: "bf16" (default, or env DDPM3D_HALF_DTYPE)
+        or "fp16" (the reference's dtype: same tensor-core rate, 3 more mantissa bits, smaller range)."""
+        half = {"bf16": N.BF16, "fp16": N.FP16}[name]
+        if half != self._half:
+            was_half = self._precision in (N.BF16, N.FP16)
+            self._half = half
+            if was_half:
+                self._precision = half
+                self._drop_ctx()
+        return self
 
     def convert_to_fp32(self):
         """unet.py:1007-1013."""

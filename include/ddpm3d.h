@@ -41,6 +41,7 @@ extern "C" {
 /* precision of the UNet torso (unet.py:1003-1013 convert_to_fp16 -> here bf16 on tcgen05) */
 #define DDPM3D_FP32 0
 #define DDPM3D_BF16 1
+#define DDPM3D_FP16 2 /* the reference's own torso dtype; same tcgen05 rate as bf16, 3 more mantissa bits */
 
 /* gaussian_diffusion.py:65-72 ModelMeanType */
 #define DDPM3D_MEAN_PREVIOUS_X 0
@@ -75,7 +76,7 @@ typedef struct ddpm3d_config {
   int32_t use_scale_shift_norm;
   int32_t resblock_updown;
   int32_t use_new_attention_order;
-  int32_t precision;       /* DDPM3D_FP32 | DDPM3D_BF16 */
+  int32_t precision;       /* DDPM3D_FP32 | DDPM3D_BF16 | DDPM3D_FP16 */
 } ddpm3d_config;
 
 /* Per-timestep scalars of the respaced process, already rounded to fp32 exactly as
@@ -172,13 +173,13 @@ typedef struct ddpm3d_prof_record { int32_t kind; int32_t pad_; float ms; float 
 int ddpm3d_profile_read(ddpm3d_ctx* ctx, ddpm3d_prof_record* out, int cap);
 
 /* ---- single kernels on channels-last device buffers, exported for unit tests ------------------
- * dtype: DDPM3D_FP32 (float) or DDPM3D_BF16 (__nv_bfloat16) for activations and conv weights.
+ * dtype: DDPM3D_FP32 (float), DDPM3D_BF16 (__nv_bfloat16) or DDPM3D_FP16 (__half) for activations and conv weights.
  * Activations are [B][Z][H][W][C] (NDHWC).  These replace the torch ops behind nn.py:17-32. */
 
 /* 3x3x3 (taps=27) or 1x1x1 (taps=1) "same" convolution, stride (1,s,s) (nn.py:22-32; call sites
  * unet.py:185,211,219,222).  w: [Cout][taps*Cin] with k = tap*Cin + ci, tap = (dz*3+dh)*3+dw;
  * bias fp32 [Cout]; residual (optional, [B][Z][Ho][Wo][Cout]) is added in the epilogue.
- * path: 1 SIMT, 2 tcgen05 (bf16 only, Cin%64==0, Cout%16==0, s==1). */
+ * path: 1 SIMT, 2 tcgen05 (bf16 / fp16, Cin%64==0, Cout%64==0, s==1). */
 int ddpm3d_k_conv3d(int dtype, int path, const void* in, const void* w, const float* bias, const void* residual,
                     void* out, int B, int Z, int H, int W, int Cin, int Cout, int taps, int stride_hw, void* stream);
 

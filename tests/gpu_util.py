@@ -35,8 +35,13 @@ def max_rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
+TDT = {N.FP32: torch.float32, N.BF16: torch.bfloat16, N.FP16: torch.float16}
+# one output rounding of the element type (plus fp32 accumulation-order noise)
+ROUND_TOL = {N.FP32: 2e-5, N.BF16: 6e-3, N.FP16: 8e-4}
+
+
 def conv3d(dt, path, x_cl, w_packed, bias, res_cl, B, Z, H, W, Cin, Cout, taps=27, stride=1):
-    tdt = torch.bfloat16 if dt == N.BF16 else torch.float32
+    tdt = TDT[dt]
     out = torch.empty((B, Z, H // stride, W // stride, Cout), device=DEV, dtype=tdt)
     N.check(N.lib().ddpm3d_k_conv3d(dt, path, N.ptr(x_cl), N.ptr(w_packed), N.ptr(bias), N.ptr(res_cl), N.ptr(out),
                                     B, Z, H, W, Cin, Cout, taps, stride, stream()))

@@ -15,7 +15,7 @@ from oracle.schedule import make_tables
 
 pytestmark = pytest.mark.gpu
 
-from gpu_util import DEV, conv3d, from_cl, max_rel, pack_weight, stream, to_cl  # noqa: E402
+from gpu_util import DEV, ROUND_TOL, TDT, conv3d, from_cl, max_rel, pack_weight, stream, to_cl  # noqa: E402
 
 
 @pytest.mark.parametrize("i", range(len(cases.TEMB_CASES)))
@@ -37,7 +37,7 @@ def test_timestep_embedding_matches_reference(golden_dir, i):
     assert np.abs(out.cpu().numpy() - want).max() <= 1.5e-4
 
 
-@pytest.mark.parametrize("dt", [N.FP32, N.BF16])
+@pytest.mark.parametrize("dt", [N.FP32, N.BF16, N.FP16])
 @pytest.mark.parametrize("C,shape,silu,film,resample", [
     (32, (2, 4, 8, 8), 1, False, 0), (64, (1, 3, 6, 10), 0, True, 0), (128, (1, 8, 16, 16), 1, True, 1),
     (96, (2, 2, 6, 6), 1, False, 2), (384, (1, 4, 12, 12), 1, True, 0), (1024, (1, 2, 6, 6), 1, False, 0),
@@ -51,7 +51,7 @@ def test_groupnorm_film_silu(dt, C, shape, silu, film, resample):
     gamma = 1 + 0.1 * torch.randn(C, generator=g)
     beta = 0.1 * torch.randn(C, generator=g)
     fm = torch.randn((B, 2 * C), generator=g) * 0.3 if film else None
-    tdt = torch.bfloat16 if dt == N.BF16 else torch.float32
+    tdt = TDT[dt]
     xin = x.to(tdt).float()  # the kernel sees the rounded input
     ref = F.group_norm(xin, 32, gamma, beta, 1e-5)
     if film:
@@ -69,11 +69,11 @@ def test_groupnorm_film_silu(dt, C, shape, silu, film, resample):
     N.check(N.lib().ddpm3d_k_groupnorm(dt, N.ptr(xd), N.ptr(gd_), N.ptr(bd), N.ptr(fd), silu, resample, N.ptr(out),
                                        B, Z, H, W, C, stream()))
     torch.cuda.synchronize()
-    tol = 1e-5 if dt == N.FP32 else 6e-3  # bf16: one output rounding (2^-8 relative)
+    tol = ROUND_TOL[dt]  # one output rounding of the element type
     assert max_rel(from_cl(out), ref) <= tol
 
 
-@pytest.mark.parametrize("dt", [N.FP32, N.BF16])
+@pytest.mark.parametrize("dt", [N.FP32, N.BF16, N.FP16])
 @pytest.mark.parametrize("Cin,Cout,shape,taps,stride,res", [
     (2, 32, (1, 4, 8, 8), 27, 1, False), (32, 32, (2, 3, 8, 6), 27, 1, True), (64, 2, (1, 4, 8, 8), 27, 1, False),
     (32, 64, (1, 4, 8, 8), 27, 2, False), (64, 96, (1, 2, 4, 4), 1, 1, True), (128, 128, (1, 5, 12, 12), 27, 1, True),
@@ -83,7 +83,7 @@ def test_conv3d_simt(dt, Cin, Cout, shape, taps, stride, res):
     """conv_nd(3, ...) (nn.py:22-32) on the CUDA-core kernel vs F.conv3d fp32."""
     B, Z, H, W = shape
     g = torch.Generator().manual_seed(Cin * 7 + Cout)
-    tdt = torch.bfloat16 if dt == N.BF16 else torch.float32
+    tdt = TDT[dt]
     x = torch.randn((B, Cin, Z, H, W), generator=g).to(tdt).float()
     k = 3 if taps == 27 else 1
     w = (torch.randn((Cout, Cin, k, k, k), generator=g) / np.sqrt(Cin * taps)).to(tdt).float()
@@ -95,7 +95,7 @@ def test_conv3d_simt(dt, Cin, Cout, shape, taps, stride, res):
         ref = ref + r
     out = conv3d(dt, 1, to_cl(x, tdt), pack_weight(w, tdt), b.to(DEV), to_cl(r, tdt) if res else None,
                  B, Z, H, W, Cin, Cout, taps, stride)
-    tol = 2e-5 if dt == N.FP32 else 6e-3
+    tol = ROUND_TOL[dt]
     assert max_rel(from_cl(out), ref) <= tol
 
 
@@ -130,12 +130,12 @@ def test_p_sample_update_matches_reference(golden_dir, i):
     assert np.array_equal(pm["mean"].cpu().numpy(), out["mean"].cpu().numpy())
 
 
-@pytest.mark.parametrize("dt", [N.FP32, N.BF16])
+@pytest.mark.parametrize("dt", [N.FP32, N.BF16, N.FP16])
 @pytest.mark.parametrize("B,T,C,heads,new_order", [(1, 64, 64, 4, 0), (2, 100, 32, 1, 1), (1, 300, 128, 2, 0)])
 def test_attention_core(dt, B, T, C, heads, new_order):
     """QKVAttentionLegacy / QKVAttention (unet.py:328-393)."""
     g = torch.Generator().manual_seed(T + C)
-    tdt = torch.bfloat16 if dt == N.BF16 else torch.float32
+    tdt = TDT[dt]
     qkv = torch.randn((B, 3 * C, T), generator=g).to(tdt).float()
     ch = C // heads
     s = 1 / np.sqrt(np.sqrt(ch))
@@ -151,5 +151,5 @@ def test_attention_core(dt, B, T, C, heads, new_order):
     N.check(N.lib().ddpm3d_k_attention(dt, N.ptr(qd), N.ptr(out),
                                        B, T, C, heads, new_order, stream()))
     torch.cuda.synchronize()
-    tol = 1e-5 if dt == N.FP32 else 6e-3
+    tol = ROUND_TOL[dt]
     assert max_rel(out.float().permute(0, 2, 1).cpu(), ref) <= tol
