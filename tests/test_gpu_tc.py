@@ -52,7 +52,8 @@ def test_conv3d_tcgen05(Cin, Cout, shape, taps, res, dt):
     # same 16-bit inputs, fp32 accumulation in both: they may differ by one output rounding at most
     assert max_rel(tc.float().cpu(), simt.float().cpu()) <= 1.5 * ROUND_TOL[dt]
     frac_equal = float((tc == simt).float().mean())
-    assert frac_equal >= 0.98, frac_equal
+    # fp16 keeps 3 more mantissa bits, so fp32 summation-order differences flip the last bit more often
+    assert frac_equal >= (0.98 if dt == N.BF16 else 0.90), frac_equal
 
 
 def test_ineligible_shapes_are_rejected():
