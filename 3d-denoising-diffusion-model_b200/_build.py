@@ -64,7 +64,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         for log in logs:
             print(log)
     if jobs or force or _stale(LIB, objs):
-        run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+        run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
     return LIB
 
 

@@ -39,7 +39,7 @@ class ProfRecord(C.Structure):
 
 
 PROF_KINDS = ["conv_tcgen05", "conv_simt", "gn_stats", "gn_finalize", "groupnorm", "embedding", "update",
-              "attention", "misc", "conv_small"]
+              "attention", "misc", "conv_small", "halo_exchange"]
 
 _P = C.c_void_p
 _I = C.c_int
@@ -60,6 +60,9 @@ SIGNATURES = {
     "ddpm3d_p_sample_update": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, C.c_int64, _P]),
     "ddpm3d_p_sample": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P]),
     "ddpm3d_sample_loop": (_I, [_P, _P, _P, _P, _P, C.c_uint64, _I, _I, _P, _I, _I, _I, _I, _P]),
+    "ddpm3d_comm_unique_id": (_I, [_P]),
+    "ddpm3d_set_comm": (_I, [_P, _P, _I, _I]),
+    "ddpm3d_set_slab": (_I, [_P, _I, _I]),
     "ddpm3d_set_option": (_I, [_P, C.c_char_p, C.c_int64]),
     "ddpm3d_launch_count": (C.c_int64, [_P]),
     "ddpm3d_profile_read": (_I, [_P, C.POINTER(ProfRecord), _I]),

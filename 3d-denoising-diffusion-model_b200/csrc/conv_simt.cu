@@ -30,6 +30,7 @@ struct SimtParams {
   void* out;
   int planar;
   int B, Z, Ho, Wo, Hin, Win, Cout, Ktot;
+  int zp;  // halo planes of source 0
   int64_t M;
 };
 
@@ -121,9 +122,10 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(SimtParams p) {
         const int dz = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
         const int st = s == 0 ? p.stride : 1;
         const int Hs = s == 0 ? p.Hin : p.Ho, Ws = s == 0 ? p.Win : p.Wo;
-        const int zi = az + dz, hi = aho * st + dh, wi = awo * st + dw;
-        if (zi >= 0 && zi < p.Z && hi >= 0 && hi < Hs && wi >= 0 && wi < Ws) {
-          const T* src = (const T*)p.src[s] + ((((int64_t)ab * p.Z + zi) * Hs + hi) * Ws + wi) * C + ci;
+        const int zpl = s == 0 ? p.zp : 0, Zs = p.Z + 2 * zpl;
+        const int zi = az + dz + zpl, hi = aho * st + dh, wi = awo * st + dw;
+        if (zi >= 0 && zi < Zs && hi >= 0 && hi < Hs && wi >= 0 && wi < Ws) {
+          const T* src = (const T*)p.src[s] + ((((int64_t)ab * Zs + zi) * Hs + hi) * Ws + wi) * C + ci;
           Ld8<T>::ld(src, ra);
         }
       }
@@ -142,9 +144,10 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(SimtParams p) {
           const int dz = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
           const int st = s == 0 ? p.stride : 1;
           const int Hs = s == 0 ? p.Hin : p.Ho, Ws = s == 0 ? p.Win : p.Wo;
-          const int zi = az + dz, hi = aho * st + dh, wi = awo * st + dw;
-          if (zi >= 0 && zi < p.Z && hi >= 0 && hi < Hs && wi >= 0 && wi < Ws)
-            ra[j] = to_f32(((const T*)p.src[s])[((((int64_t)ab * p.Z + zi) * Hs + hi) * Ws + wi) * C + ci]);
+          const int zpl = s == 0 ? p.zp : 0, Zs = p.Z + 2 * zpl;
+          const int zi = az + dz + zpl, hi = aho * st + dh, wi = awo * st + dw;
+          if (zi >= 0 && zi < Zs && hi >= 0 && hi < Hs && wi >= 0 && wi < Ws)
+            ra[j] = to_f32(((const T*)p.src[s])[((((int64_t)ab * Zs + zi) * Hs + hi) * Ws + wi) * C + ci]);
         }
       }
     }
@@ -297,6 +300,7 @@ int conv_simt(const ConvArgs& a, cudaStream_t s) {
   vec = vec && (p.Ktot % 4 == 0);
   p.taps = a.taps;
   p.stride = a.stride_hw;
+  p.zp = a.in_zpad;
   p.w = a.w;
   p.bias = a.bias;
   p.res = a.residual;

@@ -24,7 +24,7 @@ constexpr int HEAD_THREADS = 256;               // lane -> w; warp -> (h half, z
 template <int COUT>
 __global__ void __launch_bounds__(HEAD_THREADS, 2)
 head_conv_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-                 float* __restrict__ out, int B, int Z, int H, int W, int C) {
+                 float* __restrict__ out, int B, int Z, int H, int W, int C, int zp) {
   extern __shared__ float4 sm4[];
   float4* s_in = sm4;                                              // [2][HIZ][HIH][HIW] float4
   float* s_w = reinterpret_cast<float*>(sm4 + 2 * HIZ * HIH * HIW);  // [27][COUT][HCC]
@@ -56,8 +56,8 @@ head_conv_kernel(const float* __restrict__ in, const float* __restrict__ w, cons
       const int iz = v / HIH;
       const int gz = z0 + iz - 1, gh = h0 + ih - 1, gw = w0 + iw - 1;
       float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gz >= 0 && gz < Z && gh >= 0 && gh < H && gw >= 0 && gw < W)
-        val = __ldg(reinterpret_cast<const float4*>(in + ((((int64_t)b * Z + gz) * H + gh) * W + gw) * C + c0) + q);
+      if (gz >= -zp && gz < Z + zp && gh >= 0 && gh < H && gw >= 0 && gw < W)
+        val = __ldg(reinterpret_cast<const float4*>(in + ((((int64_t)b * (Z + 2 * zp) + gz + zp) * H + gh) * W + gw) * C + c0) + q);
       s_in[((q * HIZ + iz) * HIH + ih) * HIW + iw] = val;
     }
     for (int i = tid; i < 27 * COUT * HCC; i += HEAD_THREADS) {
@@ -120,7 +120,7 @@ constexpr int STEM_THREADS = 256;
 template <typename T>
 __global__ void __launch_bounds__(STEM_THREADS, 2)
 stem_conv_kernel(const T* __restrict__ in, const T* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
-                 int B, int Z, int H, int W, int Cout) {
+                 int B, int Z, int H, int W, int Cout, int zp) {
   extern __shared__ float4 sm4[];
   float* s_w = reinterpret_cast<float*>(sm4);         // [54][Cout]   (k-major so a channel group is contiguous)
   float* s_b = s_w + 54 * Cout;                       // [Cout]
@@ -146,8 +146,8 @@ stem_conv_kernel(const T* __restrict__ in, const T* __restrict__ w, const float*
     const int iz = v / SIH;
     const int gz = z0 + iz - 1, gh = h0 + ih - 1, gw = w0 + iw - 1;
     float2 val = make_float2(0.f, 0.f);
-    if (gz >= 0 && gz < Z && gh >= 0 && gh < H && gw >= 0 && gw < W) {
-      const T* p = in + ((((int64_t)b * Z + gz) * H + gh) * W + gw) * 2;
+    if (gz >= -zp && gz < Z + zp && gh >= 0 && gh < H && gw >= 0 && gw < W) {
+      const T* p = in + ((((int64_t)b * (Z + 2 * zp) + gz + zp) * H + gh) * W + gw) * 2;
       val = make_float2(to_f32(p[0]), to_f32(p[1]));
     }
     s_in[i] = val;
@@ -215,10 +215,10 @@ int conv_head(const ConvArgs& a, cudaStream_t s) {
   }
   if (a.Cout == 1)
     head_conv_kernel<1><<<grid, HEAD_THREADS, smem, s>>>((const float*)a.main.ptr, (const float*)a.w, a.bias, (float*)a.out,
-                                                         a.B, a.Z, a.Ho, a.Wo, a.main.C);
+                                                         a.B, a.Z, a.Ho, a.Wo, a.main.C, a.in_zpad);
   else
     head_conv_kernel<2><<<grid, HEAD_THREADS, smem, s>>>((const float*)a.main.ptr, (const float*)a.w, a.bias, (float*)a.out,
-                                                         a.B, a.Z, a.Ho, a.Wo, a.main.C);
+                                                         a.B, a.Z, a.Ho, a.Wo, a.main.C, a.in_zpad);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }
@@ -242,13 +242,13 @@ int conv_stem(const ConvArgs& a, cudaStream_t s) {
   }
   if (a.dt == DDPM3D_BF16)
     stem_conv_kernel<bf16><<<grid, STEM_THREADS, smem, s>>>((const bf16*)a.main.ptr, (const bf16*)a.w, a.bias, (bf16*)a.out,
-                                                            a.B, a.Z, a.Ho, a.Wo, a.Cout);
+                                                            a.B, a.Z, a.Ho, a.Wo, a.Cout, a.in_zpad);
   else if (a.dt == DDPM3D_FP16)
     stem_conv_kernel<f16><<<grid, STEM_THREADS, smem, s>>>((const f16*)a.main.ptr, (const f16*)a.w, a.bias, (f16*)a.out,
-                                                           a.B, a.Z, a.Ho, a.Wo, a.Cout);
+                                                           a.B, a.Z, a.Ho, a.Wo, a.Cout, a.in_zpad);
   else
     stem_conv_kernel<float><<<grid, STEM_THREADS, smem, s>>>((const float*)a.main.ptr, (const float*)a.w, a.bias,
-                                                             (float*)a.out, a.B, a.Z, a.Ho, a.Wo, a.Cout);
+                                                             (float*)a.out, a.B, a.Z, a.Ho, a.Wo, a.Cout, a.in_zpad);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }

@@ -43,6 +43,7 @@ struct TcParams {
   int n_main_steps;  // taps * chunks[0]
   int nk;            // total k-steps
   int taps;          // 27 or 1
+  int zoff;          // halo planes in front of the main source (z-slab sharding)
   int bw, bh, bz;    // brick (one 128-row MMA tile)
   int pw, ph, pz;    // offset of the second brick of a CTA tile (MT == 2): exactly one is non-zero
   int nWt, nHt, nZt, nNt;  // CTA tiles per dimension (a CTA tile = MT bricks)
@@ -233,7 +234,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           if (kk < p.n_main_steps) {
             const int tap = p.taps == 27 ? kk / p.chunks[0] : 13;
             c0 = (kk - (p.taps == 27 ? tap * p.chunks[0] : 0)) * BK;
-            dz = tap / 9 - 1; dh = (tap / 3) % 3 - 1; dw = tap % 3 - 1;
+            dz = tap / 9 - 1 + p.zoff; dh = (tap / 3) % 3 - 1; dw = tap % 3 - 1;
             map = &mapA0;
           } else {
             const int e = kk - p.n_main_steps;
@@ -491,6 +492,7 @@ int conv_tc(const ConvArgs& a, cudaStream_t s) {
   p.nsrc = 1 + a.n_extra;
   p.chunks[0] = a.main.C / BK;
   p.taps = a.taps;
+  p.zoff = a.in_zpad;
   p.n_main_steps = a.taps * p.chunks[0];
   p.nk = p.n_main_steps;
   int Ktot = a.taps * a.main.C;
@@ -538,7 +540,7 @@ int conv_tc(const ConvArgs& a, cudaStream_t s) {
 
   const CUtensorMapDataType tdt = a.dt == DDPM3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap maps[3];
-  DD_TRY(make_act_map(&maps[0], tdt, a.main.ptr, a.B, a.Z, a.Ho, a.Wo, a.main.C, p.bw, p.bh, p.bz));
+  DD_TRY(make_act_map(&maps[0], tdt, a.main.ptr, a.B, a.Z + 2 * a.in_zpad, a.Ho, a.Wo, a.main.C, p.bw, p.bh, p.bz));
   maps[1] = maps[0];
   maps[2] = maps[0];
   for (int e = 0; e < a.n_extra; ++e)

@@ -8,24 +8,28 @@ namespace ddpm3d {
 // pack_input: cat([x, low_res], dim=1) + cast (unet.py:1690-1693, :1035)
 // =================================================================================================
 template <typename T>
-__global__ void pack_input_kernel(const float* __restrict__ x, const float* __restrict__ low, T* __restrict__ out, int64_t n) {
+__global__ void pack_input_kernel(const float* __restrict__ x, const float* __restrict__ low, T* __restrict__ out, int64_t n,
+                                  int64_t per_b, int64_t pad_vox) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    out[2 * i] = from_f32<T>(x[i]);
-    out[2 * i + 1] = from_f32<T>(low[i]);
+    const int64_t b = pad_vox ? i / per_b : 0;
+    const int64_t o = i + (2 * b + 1) * pad_vox;  // skip the leading halo planes of batches 0..b
+    out[2 * o] = from_f32<T>(x[i]);
+    out[2 * o + 1] = from_f32<T>(low[i]);
   }
 }
 
-int pack_input(int dt, const float* x, const float* low, void* out, int64_t n, cudaStream_t s) {
+int pack_input(int dt, const float* x, const float* low, void* out, int B, int Z, int64_t plane, int out_zpad, cudaStream_t s) {
+  const int64_t n = (int64_t)B * Z * plane, per_b = (int64_t)Z * plane, pad_vox = (int64_t)out_zpad * plane;
   const int threads = 256;
   const int blocks = (int)std::min<int64_t>(ceil_div(n, threads), 148 * 16);
   if (dt == DDPM3D_BF16)
-    pack_input_kernel<bf16><<<blocks, threads, 0, s>>>(x, low, (bf16*)out, n);
+    pack_input_kernel<bf16><<<blocks, threads, 0, s>>>(x, low, (bf16*)out, n, per_b, pad_vox);
   else if (dt == DDPM3D_FP16)
-    pack_input_kernel<f16><<<blocks, threads, 0, s>>>(x, low, (f16*)out, n);
+    pack_input_kernel<f16><<<blocks, threads, 0, s>>>(x, low, (f16*)out, n, per_b, pad_vox);
   else
-    pack_input_kernel<float><<<blocks, threads, 0, s>>>(x, low, (float*)out, n);
+    pack_input_kernel<float><<<blocks, threads, 0, s>>>(x, low, (float*)out, n, per_b, pad_vox);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }
@@ -163,6 +167,71 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restri
   }
 }
 
+// z-slab sharding: this rank's fp64 sums [B][32][2] from its partials (fixed order)
+__global__ void __launch_bounds__(1024) gn_reduce_local_kernel(const float* __restrict__ partials, int n_chunks,
+                                                               double* __restrict__ sums) {
+  const int b = blockIdx.x;
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* ps = partials + (((int64_t)b * 32 + g) * 2) * n_chunks;
+  const float* pq = ps + n_chunks;
+  double s = 0.0, q = 0.0;
+  for (int c = lane; c < n_chunks; c += 32) {
+    s += (double)ps[c];
+    q += (double)pq[c];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    sums[((int64_t)b * 32 + g) * 2] = s;
+    sums[((int64_t)b * 32 + g) * 2 + 1] = q;
+  }
+}
+
+// finalize from the all-gathered per-rank sums: gathered[world][B][32][2], summed in rank order
+__global__ void __launch_bounds__(1024) gn_finalize_multi_kernel(const double* __restrict__ gathered, int world, int B, int Ctot,
+                                                                 double inv_count, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, const float* __restrict__ film,
+                                                                 int64_t film_stride, const float* __restrict__ pre_add,
+                                                                 int64_t pre_stride, float* __restrict__ ab) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int b = blockIdx.x;
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x;
+    double s = 0.0, q = 0.0;
+    for (int r = 0; r < world; ++r) {
+      const double* p = gathered + (((int64_t)r * B + b) * 32 + g) * 2;
+      s += p[0];
+      q += p[1];
+    }
+    const double mean = s * inv_count;
+    double var = q * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = (float)mean;
+    s_rstd[g] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  const int gpc = Ctot / 32;
+  float* A = ab + (int64_t)b * 2 * Ctot;
+  float* Bv = A + Ctot;
+  for (int c = threadIdx.x; c < Ctot; c += blockDim.x) {
+    const int gg = c / gpc;
+    float a = s_rstd[gg] * gamma[c];
+    float o = beta[c] - s_mean[gg] * a;
+    if (film) {
+      const float sc = 1.0f + film[(int64_t)b * film_stride + c];
+      const float sh = film[(int64_t)b * film_stride + Ctot + c];
+      a *= sc;
+      o = o * sc + sh;
+    }
+    if (pre_add) o += pre_add[(int64_t)b * pre_stride + c] * a;
+    A[c] = a;
+    Bv[c] = o;
+  }
+}
+
 template <typename T, typename TO, int N>
 __device__ __forceinline__ void gn_put(TO* dst, const float* y) {
   if constexpr (sizeof(TO) == sizeof(T)) {
@@ -180,7 +249,7 @@ __device__ __forceinline__ void gn_put(TO* dst, const float* y) {
 template <typename T, typename TO, int MODE, bool SILU>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int C1, int Z,
                                                        int H, int W, int rows_per_block, const float* __restrict__ ab,
-                                                       TO* __restrict__ out) {
+                                                       TO* __restrict__ out, int out_zpad) {
   constexpr int N = Vec<T>::N;
   const int Ctot = C0 + C1;
   const int nvec0 = C0 / N, nvec = Ctot / N;
@@ -195,7 +264,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0,
   int Csrc;
   if (v < nvec0) { base = s0 + (int64_t)b * rows_in * C0 + v * N; Csrc = C0; }
   else { base = s1 + (int64_t)b * rows_in * C1 + (v - nvec0) * N; Csrc = C1; }
-  TO* obase = out + (int64_t)b * rows_out * Ctot + v * N;
+  const int plane_out = rows_out / Z;
+  TO* obase = out + ((int64_t)b * (Z + 2 * out_zpad) + out_zpad) * plane_out * Ctot + v * N;
   float A[N], Bv[N];
   {
     const float* pa = ab + (int64_t)b * 2 * Ctot + v * N;
@@ -316,7 +386,7 @@ static int gn_apply_launch(const GnArgs& a, cudaStream_t s) {
   const T* s0 = (const T*)a.src[0];
   const T* s1 = (const T*)a.src[1];
 #define GN_LAUNCH(MODE, SILU) \
-  gn_apply_kernel<T, TO, MODE, SILU><<<grid, threads, 0, s>>>(s0, s1, a.C[0], a.C[1], a.Z, a.H, a.W, rows_per_block, a.ab, (TO*)a.out)
+  gn_apply_kernel<T, TO, MODE, SILU><<<grid, threads, 0, s>>>(s0, s1, a.C[0], a.C[1], a.Z, a.H, a.W, rows_per_block, a.ab, (TO*)a.out, a.out_zpad)
   if (a.silu) {
     if (a.resample == RS_NONE) GN_LAUNCH(RS_NONE, true);
     else if (a.resample == RS_POOL) GN_LAUNCH(RS_POOL, true);
@@ -349,31 +419,55 @@ static int gn_stats_launch(const GnArgs& a, cudaStream_t s) {
   return DDPM3D_OK;
 }
 
-int gn_forward(const GnArgs& a, cudaStream_t s, int* launches) {
+static int gn_check(const GnArgs& a) {
   const int Ctot = a.C[0] + a.C[1];
   const int N = is_half_dt(a.dt) ? 8 : 4;
   DD_CHECK(Ctot % 32 == 0, DDPM3D_ERR_ARG, "groupnorm: channels must be a multiple of 32");
   DD_CHECK(a.C[0] % N == 0 && a.C[1] % N == 0, DDPM3D_ERR_ARG, "groupnorm: per-source channels must fill 16-byte vectors");
   DD_CHECK(a.resample != RS_POOL || (a.H % 2 == 0 && a.W % 2 == 0), DDPM3D_ERR_ARG, "groupnorm: pool needs even H, W");
-  DD_CHECK(!(a.out_f32 && a.dt == DDPM3D_FP32 && false), DDPM3D_ERR_ARG, "");
-  if (a.dt == DDPM3D_BF16) DD_TRY(gn_stats_launch<bf16>(a, s));
-  else if (a.dt == DDPM3D_FP16) DD_TRY(gn_stats_launch<f16>(a, s));
-  else DD_TRY(gn_stats_launch<float>(a, s));
+  return DDPM3D_OK;
+}
+
+static int gn_stats_any(const GnArgs& a, cudaStream_t s) {
+  if (a.dt == DDPM3D_BF16) return gn_stats_launch<bf16>(a, s);
+  if (a.dt == DDPM3D_FP16) return gn_stats_launch<f16>(a, s);
+  return gn_stats_launch<float>(a, s);
+}
+
+static int gn_apply_any(const GnArgs& a, cudaStream_t s) {
+  if (a.dt == DDPM3D_BF16) return a.out_f32 ? gn_apply_launch<bf16, float>(a, s) : gn_apply_launch<bf16, bf16>(a, s);
+  if (a.dt == DDPM3D_FP16) return a.out_f32 ? gn_apply_launch<f16, float>(a, s) : gn_apply_launch<f16, f16>(a, s);
+  return gn_apply_launch<float, float>(a, s);
+}
+
+int gn_forward(const GnArgs& a, cudaStream_t s, int* launches) {
+  DD_TRY(gn_check(a));
+  const int Ctot = a.C[0] + a.C[1];
+  DD_TRY(gn_stats_any(a, s));
   const double inv_count = 1.0 / ((double)a.Z * a.H * a.W * (Ctot / 32));
   gn_finalize_kernel<<<a.B, 1024, 0, s>>>(a.partials, a.n_chunks, Ctot, inv_count, a.gamma, a.beta, a.film, a.film_stride,
                                           a.pre_add, a.pre_stride, a.ab);
   DD_CUDA(cudaGetLastError());
-  if (a.dt == DDPM3D_BF16) {
-    if (a.out_f32) DD_TRY((gn_apply_launch<bf16, float>(a, s)));
-    else DD_TRY((gn_apply_launch<bf16, bf16>(a, s)));
-  } else if (a.dt == DDPM3D_FP16) {
-    if (a.out_f32) DD_TRY((gn_apply_launch<f16, float>(a, s)));
-    else DD_TRY((gn_apply_launch<f16, f16>(a, s)));
-  } else {
-    DD_TRY((gn_apply_launch<float, float>(a, s)));
-  }
+  DD_TRY(gn_apply_any(a, s));
   if (launches) *launches += 3;
   return DDPM3D_OK;
+}
+
+int gn_stats_local(const GnArgs& a, double* sums, cudaStream_t s) {
+  DD_TRY(gn_check(a));
+  DD_TRY(gn_stats_any(a, s));
+  gn_reduce_local_kernel<<<a.B, 1024, 0, s>>>(a.partials, a.n_chunks, sums);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
+int gn_finalize_apply(const GnArgs& a, cudaStream_t s) {
+  const int Ctot = a.C[0] + a.C[1];
+  DD_CHECK(a.gathered != nullptr && a.world >= 1, DDPM3D_ERR_STATE, "groupnorm: gathered statistics missing");
+  gn_finalize_multi_kernel<<<a.B, 1024, 0, s>>>(a.gathered, a.world, a.B, Ctot, a.inv_count_global, a.gamma, a.beta, a.film,
+                                                a.film_stride, a.pre_add, a.pre_stride, a.ab);
+  DD_CUDA(cudaGetLastError());
+  return gn_apply_any(a, s);
 }
 
 // =================================================================================================
@@ -597,7 +691,8 @@ __global__ void p_sample_update_kernel(UpdateArgs a) {
       const float4 n4 = *reinterpret_cast<const float4*>(noise + i);
       z[0] = n4.x; z[1] = n4.y; z[2] = n4.z; z[3] = n4.w;
     } else {
-      Philox::normal4(a.seed, (uint64_t)i4, (uint32_t)exec, z);
+      const uint64_t gi = a.idx_bstride ? (uint64_t)(((int64_t)b * a.idx_bstride + a.idx_offset + off) >> 2) : (uint64_t)i4;
+      Philox::normal4(a.seed, gi, (uint32_t)exec, z);
     }
     const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ms[4] = {m4.x, m4.y, m4.z, m4.w}, vs[4] = {v4.x, v4.y, v4.z, v4.w};
     float smp[4], x0s[4], mus[4], lvs[4];

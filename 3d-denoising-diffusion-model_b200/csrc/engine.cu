@@ -11,6 +11,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "comm.h"
 #include "kernels.h"
 
 namespace ddpm3d {
@@ -166,6 +167,7 @@ struct ddpm3d_ctx {
   float* d_freqs = nullptr;  // timestep_embedding frequencies computed by the host exactly like nn.py:113-115
   int n_freqs = 0;
   int64_t launches = 0;
+  SlabComm slab;  // z-slab sharding of one volume over ranks (inactive unless ddpm3d_set_comm was called with world > 1)
   std::map<GraphKey, cudaGraphExec_t> graphs;
   std::map<GraphKey, int64_t> graph_launches;
   std::vector<ProfEntry> prof;
@@ -440,7 +442,22 @@ struct Run {
   int launches = 0;
   float* emb_out = nullptr;  // [B][rows_total]
 
+  int zp = 0;                // halo planes on conv-input tensors (1 in z-slab mode)
+
   size_t act_bytes(int H, int W, int C) const { return (size_t)B * Z * H * W * C * ctx->esz; }
+  // a tensor a 3x3x3 conv will read: carries the halo planes in z-slab mode
+  size_t conv_in_bytes(int H, int W, int C, size_t esz) const { return (size_t)B * (Z + 2 * zp) * H * W * C * esz; }
+
+  // after a conv-input tensor has been produced: fetch the neighbours' boundary planes
+  int halo(void* t, int H, int W, int C, size_t esz) {
+    if (!zp) return DDPM3D_OK;
+    launches += 1;
+    if (arena.dry) return DDPM3D_OK;
+    prof_begin(10, (double)B * 2 * H * W * C * esz);
+    const int r = comm_halo_exchange(ctx->slab, t, B, Z, (size_t)H * W * C * esz, s);
+    prof_end();
+    return r;
+  }
 
   void prof_begin(int kind, double work) {
     if (!ctx->profile || arena.dry) return;
@@ -465,6 +482,7 @@ struct Run {
     double K = (double)a.taps * a.main.C;
     for (int e = 0; e < a.n_extra; ++e) K += a.extra[e].C;
     const double flops = 2.0 * B * Z * a.Ho * a.Wo * (double)a.Cout * K;
+    if (a.taps == 27) a.in_zpad = zp;
     const bool tc = is_half_dt(a.dt) && ctx->conv_path != 1 && conv_tc_eligible(a);
     const bool stem = !tc && ctx->conv_path != 1 && conv_stem_eligible(a);
     const bool head = !tc && ctx->conv_path != 1 && conv_head_eligible(a);
@@ -481,14 +499,33 @@ struct Run {
     g.n_chunks = gn_chunks((int64_t)Z * g.H * g.W);
     g.partials = (float*)arena.alloc((size_t)B * g.n_chunks * 64 * sizeof(float));
     g.ab = (float*)arena.alloc((size_t)B * 2 * Ctot * sizeof(float));
+    double* sums = nullptr;
+    double* gathered = nullptr;
+    if (zp) {
+      sums = (double*)arena.alloc((size_t)B * 64 * sizeof(double));
+      gathered = (double*)arena.alloc((size_t)ctx->slab.world * B * 64 * sizeof(double));
+      launches += 2;
+    }
     launches += 3;
     if (arena.dry) return DDPM3D_OK;
     const double n = (double)B * Z * g.H * g.W * Ctot;
     const double in_b = is_half_dt(g.dt) ? 2 : 4, out_b = (is_half_dt(g.dt) && !g.out_f32) ? 2 : 4;
     const double scale = g.resample == RS_POOL ? 0.25 : (g.resample == RS_UP ? 4.0 : 1.0);
     prof_begin(4, n * (2 * in_b + out_b * scale));
-    int dummy = 0;
-    const int r = gn_forward(g, s, &dummy);
+    int r;
+    if (zp) {  // z-slab sharding: statistics span all ranks (fp64 sums all-gathered, summed in rank order)
+      r = gn_stats_local(g, sums, s);
+      if (r == DDPM3D_OK) r = comm_allgather_f64(ctx->slab, sums, gathered, (size_t)B * 64, s);
+      if (r == DDPM3D_OK) {
+        g.gathered = gathered;
+        g.world = ctx->slab.world;
+        g.inv_count_global = 1.0 / ((double)ctx->slab.z_total * g.H * g.W * (Ctot / 32));
+        r = gn_finalize_apply(g, s);
+      }
+    } else {
+      int dummy = 0;
+      r = gn_forward(g, s, &dummy);
+    }
     prof_end();
     return r;
   }
@@ -510,8 +547,9 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   const size_t mark = R.arena.off;
 
   // in_layers: GN32 -> SiLU (-> h_upd)                                   unet.py:237-244
-  void* h1 = R.arena.alloc(R.act_bytes(Ho, Wo, Cin));
+  void* h1 = R.arena.alloc(R.conv_in_bytes(Ho, Wo, Cin, ctx->esz));
   GnArgs g{};
+  g.out_zpad = R.zp;
   g.dt = dt;
   for (int i = 0; i < nsrc; ++i) { g.src[i] = src[i].p; g.C[i] = src[i].C; }
   g.H = H; g.W = W;
@@ -520,6 +558,7 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   g.resample = L.down ? RS_POOL : (L.up ? RS_UP : RS_NONE);
   g.out = h1;
   DD_TRY(R.gn(g));
+  DD_TRY(R.halo(h1, Ho, Wo, Cin, ctx->esz));
   // in_layers[-1]: conv 3x3x3
   void* h2 = R.arena.alloc(R.act_bytes(Ho, Wo, L.cout));
   ConvArgs c{};
@@ -530,8 +569,9 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   c.out = h2; c.Ho = Ho; c.Wo = Wo; c.Cout = L.cout;
   DD_TRY(R.conv(c));
   // out_layers: GN32 (FiLM | +emb) -> SiLU -> conv                       unet.py:245-255
-  void* h3 = R.arena.alloc(R.act_bytes(Ho, Wo, L.cout));
+  void* h3 = R.arena.alloc(R.conv_in_bytes(Ho, Wo, L.cout, ctx->esz));
   GnArgs g2{};
+  g2.out_zpad = R.zp;
   g2.dt = dt;
   g2.src[0] = h2; g2.C[0] = L.cout;
   g2.H = Ho; g2.W = Wo;
@@ -542,6 +582,7 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   g2.silu = 1;
   g2.out = h3;
   DD_TRY(R.gn(g2));
+  DD_TRY(R.halo(h3, Ho, Wo, L.cout, ctx->esz));
   ConvArgs c2{};
   c2.dt = dt;
   c2.main = {h3, L.cout};
@@ -564,6 +605,7 @@ int run_attn(Run& R, const Layer& L, const Act& x, Act* out) {
   ddpm3d_ctx* ctx = R.ctx;
   const int dt = ctx->dt, C = L.cin, H = x.H, W = x.W;
   DD_CHECK(x.C == C, DDPM3D_ERR_STATE, "internal: attention channel mismatch");
+  DD_CHECK(!R.zp, DDPM3D_ERR_ARG, "z-slab sharding does not support attention blocks yet (K/V all-gather)");
   out->C = C; out->H = H; out->W = W;
   out->p = R.arena.alloc(R.act_bytes(H, W, C));
   const size_t mark = R.arena.off;
@@ -596,6 +638,8 @@ int run_conv_layer(Run& R, const Layer& L, const Act& x, Act* out) {
   ddpm3d_ctx* ctx = R.ctx;
   const int dt = ctx->dt;
   DD_CHECK(x.C == L.cin, DDPM3D_ERR_STATE, "internal: conv channel mismatch at " + L.prefix);
+  DD_CHECK(!R.zp || L.prefix == "input_blocks.0.0", DDPM3D_ERR_ARG,
+           "z-slab sharding needs resblock_updown=True (bare Downsample / Upsample convs read un-haloed tensors)");
   int Ho = x.H, Wo = x.W;
   const void* in = x.p;
   size_t mark = 0;
@@ -673,14 +717,15 @@ int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, cons
   // cat([x, low_res], 1).type(dtype)
   Act h;
   h.C = 2; h.H = H; h.W = W;
-  h.p = R.arena.alloc(R.act_bytes(H, W, 2));
+  h.p = R.arena.alloc(R.conv_in_bytes(H, W, 2, ctx->esz));
   ++R.launches;
   if (!R.arena.dry) {
     R.prof_begin(8, (double)B * Z * H * W * (8.0 + 2.0 * ctx->esz));
-    const int r = pack_input(dt, x, low, h.p, (int64_t)B * Z * H * W, R.s);
+    const int r = pack_input(dt, x, low, h.p, B, Z, (int64_t)H * W, R.zp, R.s);
     R.prof_end();
     DD_TRY(r);
   }
+  DD_TRY(R.halo(h.p, H, W, 2, ctx->esz));
   std::vector<Act> skips;
   for (auto& blk : ctx->input_blocks) {
     Act o;
@@ -703,11 +748,13 @@ int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, cons
   }
   DD_CHECK(h.H == H && h.W == W && h.C == ctx->out_norm_ch, DDPM3D_ERR_STATE, "internal: output geometry mismatch");
   // h.type(x.dtype); out = GN32 -> SiLU -> conv (fp32)                 unet.py:1043-1044
-  float* hn = (float*)R.arena.alloc((size_t)B * Z * H * W * h.C * sizeof(float));
+  float* hn = (float*)R.arena.alloc(R.conv_in_bytes(H, W, h.C, sizeof(float)));
   GnArgs g{};
+  g.out_zpad = R.zp;
   g.dt = dt; g.src[0] = h.p; g.C[0] = h.C; g.H = H; g.W = W; g.gamma = ctx->out_gn_g; g.beta = ctx->out_gn_b; g.silu = 1;
   g.out = hn; g.out_f32 = 1;
   DD_TRY(R.gn(g));
+  DD_TRY(R.halo(hn, H, W, h.C, sizeof(float)));
   ConvArgs c{};
   c.dt = DDPM3D_FP32; c.main = {hn, h.C}; c.taps = 27; c.w = ctx->out_conv.w; c.bias = ctx->out_conv.bias;
   c.out = out; c.out_planar_f32 = 1; c.Ho = H; c.Wo = W; c.Cout = ctx->cfg.out_channels;
@@ -721,11 +768,15 @@ int check_geometry(ddpm3d_ctx* ctx, int B, int Z, int H, int W) {
   const int f = 1 << (ctx->cfg.n_levels - 1);
   DD_CHECK(H % f == 0 && W % f == 0, DDPM3D_ERR_ARG, "H and W must be divisible by 2^(levels-1)");
   DD_CHECK(((int64_t)Z * H * W) % 4 == 0, DDPM3D_ERR_ARG, "Z*H*W must be a multiple of 4");
+  if (ctx->slab.active())
+    DD_CHECK(ctx->slab.z_total >= Z && ctx->slab.z_begin + Z <= ctx->slab.z_total, DDPM3D_ERR_STATE,
+             "z-slab sharding: call ddpm3d_set_slab(z_begin, z_total) for this volume first");
   return DDPM3D_OK;
 }
 
 int64_t dry_bytes(ddpm3d_ctx* ctx, int B, int Z, int H, int W, int* launches) {
   Run R{ctx, B, Z, nullptr};
+  R.zp = ctx->slab.active() ? 1 : 0;
   R.arena.dry = true;
   if (forward_impl(ctx, R, nullptr, nullptr, nullptr, nullptr, nullptr, H, W) != DDPM3D_OK) return -1;
   if (launches) *launches = R.launches;
@@ -753,6 +804,7 @@ int ensure_workspace(ddpm3d_ctx* ctx, int B, int Z, int H, int W) {
 int forward_launch(ddpm3d_ctx* ctx, const float* x, const float* low, const float* t, const int64_t* y, float* out, int B,
                    int Z, int H, int W, cudaStream_t s, int* launches) {
   Run R{ctx, B, Z, s};
+  R.zp = ctx->slab.active() ? 1 : 0;
   R.arena.dry = false;
   R.arena.base = ctx->ws;
   R.arena.cap = ctx->ws_cap;
@@ -765,7 +817,7 @@ int forward_launch(ddpm3d_ctx* ctx, const float* x, const float* low, const floa
 // Runs `body` (which enqueues work on `s`) either directly or through a cached CUDA graph.
 template <typename F>
 int run_graphed(ddpm3d_ctx* ctx, const GraphKey& key, cudaStream_t s, F&& body) {
-  if (!ctx->use_graph || ctx->profile) {
+  if (!ctx->use_graph || ctx->profile || ctx->slab.active()) {  // NCCL calls are issued eagerly, in rank-identical order
     int n = 0;
     DD_TRY(body(s, &n));
     ctx->launches += n;
@@ -900,6 +952,7 @@ void ddpm3d_destroy(ddpm3d_ctx* ctx) {
     if (ctx->d_mo) cudaFree(ctx->d_mo);
     if (ctx->d_img) cudaFree(ctx->d_img);
     if (ctx->d_freqs) cudaFree(ctx->d_freqs);
+    comm_destroy(&ctx->slab);
     if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
     for (auto& e : ctx->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   }
@@ -1119,6 +1172,10 @@ int ddpm3d_sample_loop(ddpm3d_ctx* ctx, const float* x_T, const float* low_res, 
       a.B = B; a.C = 1; a.n = n; a.T = ctx->T;
       a.noise_step_stride = (int64_t)B * n;
       a.use_philox = noise == nullptr; a.seed = seed;
+      if (ctx->slab.active()) {  // one noise field for the whole volume, each slab draws its part
+        a.idx_bstride = (int64_t)ctx->slab.z_total * H * W;
+        a.idx_offset = (int64_t)ctx->slab.z_begin * H * W;
+      }
       DD_TRY(p_sample_update_k(a, cs));
       DD_TRY(step_advance_k(ctx->d_counter, ctx->d_tmodel, ctx->d_table, B, cs));
       *nl += 2;
@@ -1126,6 +1183,30 @@ int ddpm3d_sample_loop(ddpm3d_ctx* ctx, const float* x_T, const float* low_res, 
     }));
   }
   DD_CUDA(cudaMemcpyAsync(out, img, (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return DDPM3D_OK;
+}
+
+int ddpm3d_comm_unique_id(void* out128) {
+  DD_CHECK(out128, DDPM3D_ERR_ARG, "comm_unique_id: null argument");
+  return comm_unique_id(out128);
+}
+
+int ddpm3d_set_comm(ddpm3d_ctx* ctx, const void* id128, int rank, int world) {
+  DD_CHECK(ctx && id128, DDPM3D_ERR_ARG, "set_comm: null argument");
+  DD_CHECK(ctx->finalized, DDPM3D_ERR_STATE, "set_comm: finalize weights first");
+  DD_CUDA(cudaSetDevice(ctx->device));
+  DD_CUDA(cudaDeviceSynchronize());
+  for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+  ctx->graphs.clear();
+  ctx->graph_launches.clear();
+  return comm_init(&ctx->slab, id128, rank, world);
+}
+
+int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total) {
+  DD_CHECK(ctx, DDPM3D_ERR_ARG, "set_slab: null ctx");
+  DD_CHECK(z_begin >= 0 && z_total >= 1 && z_begin < z_total, DDPM3D_ERR_ARG, "set_slab: bad bounds");
+  ctx->slab.z_begin = z_begin;
+  ctx->slab.z_total = z_total;
   return DDPM3D_OK;
 }
 

@@ -19,6 +19,8 @@ struct ConvSrc {
 struct ConvArgs {
   int dt = DDPM3D_FP32;       // element type of main/extra sources and of w
   ConvSrc main;               // 3x3x3 (taps=27) or 1x1x1 (taps=1) source
+  int in_zpad = 0;            // main source carries this many halo planes on each side of Z (z-slab sharding):
+                              // [B][Z + 2*in_zpad][Hin][Win][C]; the conv then never pads in Z itself
   int taps = 27;
   int stride_hw = 1;          // Downsample(use_conv=True): (1,2,2)  (unet.py:129-133)
   ConvSrc extra[2];           // 1x1x1 sources appended along K (skip_connection folded in; K11 concat elision)
@@ -58,6 +60,12 @@ struct GnArgs {
   int resample = RS_NONE;
   void* out = nullptr;                      // dt (or fp32 when out_f32)
   int out_f32 = 0;
+  int out_zpad = 0;                         // output tensor has this many halo planes on each side of Z (left untouched)
+  // cross-rank statistics (z-slab sharding): when gathered != NULL the finalize pass reads
+  // gathered[world][B][32][2] (fp64 sums, rank order) instead of the local partials
+  const double* gathered = nullptr;
+  int world = 1;
+  double inv_count_global = 0.0;
   // scratch (owned by the caller / workspace)
   float* partials = nullptr;                // [B][n_chunks][32][2]
   float* ab = nullptr;                      // [B][2][Ctot]
@@ -65,13 +73,17 @@ struct GnArgs {
 };
 int gn_chunks(int64_t rows_per_batch);      // number of stats chunks per batch element
 int gn_forward(const GnArgs& a, cudaStream_t s, int* launches);
+// split form for the sharded path: stats -> local fp64 sums [B][32][2] -> (all-gather) -> finalize + apply
+int gn_stats_local(const GnArgs& a, double* sums, cudaStream_t s);
+int gn_finalize_apply(const GnArgs& a, cudaStream_t s);
 
 // plain resample (Upsample(use_conv=True) front half, unet.py:100-105)
 int resample_hw(int dt, const void* in, void* out, int B, int Z, int H, int W, int C, int mode, cudaStream_t s);
 
 // ---- network input / embedding -----------------------------------------------------------------
 // cat([x, low_res], 1) + cast (unet.py:1690-1693,1035): two fp32 (B,1,Z,H,W) -> [B][Z][H][W][2]
-int pack_input(int dt, const float* x, const float* low, void* out, int64_t n_vox_total, cudaStream_t s);
+// out_zpad: halo planes on each side of Z in `out` ([B][Z+2p][H][W][2]); plane = H*W voxels
+int pack_input(int dt, const float* x, const float* low, void* out, int B, int Z, int64_t plane, int out_zpad, cudaStream_t s);
 
 struct EmbArgs {
   const float* t = nullptr;          // [B]
@@ -103,6 +115,9 @@ struct UpdateArgs {
   int64_t noise_step_stride = 0;         // with step_counter: noise += exec_index * stride
   int T = 0;
   int use_philox = 0; uint64_t seed = 0;
+  // Philox counter = global element index b*idx_bstride + idx_offset + (local offset): slabs of one volume draw
+  // disjoint parts of one noise field.  idx_bstride == 0 -> the local index (single GPU).
+  int64_t idx_offset = 0, idx_bstride = 0;
 };
 int p_sample_update_k(const UpdateArgs& a, cudaStream_t s);
 int step_set_k(int32_t* step_counter, float* t_model, const ddpm3d_step_scalars* table, int B, int index, int exec, cudaStream_t s);

@@ -311,6 +311,28 @@ class UNetModel_noatt:
                 N.check(N.lib().ddpm3d_set_schedule(ctx, tab, len(tab), diffusion.mean_code, diffusion.var_code))
             self._bound = diffusion
 
+    # ---- one large volume as z-slabs over the ranks of a process group ---------
+    def enable_slab_sharding(self, group=None):
+        """Creates the library's NCCL communicator over `group` (one process per GPU).  Afterwards forward /
+        p_sample / the sampling loop take this rank's z-slab; call set_slab() with its position first."""
+        import torch.distributed as dist
+        ctx = self._ensure_ctx()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        buf = (C.c_char * 128)()
+        if rank == 0:
+            N.check(N.lib().ddpm3d_comm_unique_id(buf))
+        obj = [bytes(buf) if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        idbuf = (C.c_char * 128).from_buffer_copy(obj[0])
+        import torch
+        with torch.cuda.device(self._device):
+            N.check(N.lib().ddpm3d_set_comm(ctx, idbuf, rank, world))
+        self._slab = (rank, world)
+        return self
+
+    def set_slab(self, z_begin, z_total):
+        N.check(N.lib().ddpm3d_set_slab(self._ensure_ctx(), int(z_begin), int(z_total)))
+
     def launch_count(self):
         return int(N.lib().ddpm3d_launch_count(self._ctx)) if self._ctx is not None else 0
 

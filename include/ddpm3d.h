@@ -159,6 +159,18 @@ int ddpm3d_sample_loop(ddpm3d_ctx* ctx, const float* x_T, const float* low_res, 
                        const float* noise, uint64_t seed, int clip_denoised, int n_steps, float* out,
                        int B, int Z, int H, int W, void* stream);
 
+/* ---- one large volume as z-slabs over ranks (not in the reference) ---------------
+ * Z is never strided by the network (unet.py:102-105,129), so every 3x3x3 conv needs exactly one halo plane
+ * from each z-neighbour and GroupNorm needs the global per-group sums.  After ddpm3d_set_comm (world > 1) the
+ * forward / sampler entry points take THIS RANK'S slab (B,1,Zl,H,W): conv-input tensors carry two halo planes
+ * filled by NCCL send/recv, GroupNorm all-gathers fp64 partial sums and adds them in rank order (deterministic).
+ * comm_unique_id: rank 0 creates the 128-byte NCCL id, the host broadcasts it (torch.distributed), every
+ * rank calls set_comm.  set_slab: where this rank's slab sits in the global volume (GroupNorm count, Philox
+ * counters).  Requires resblock_updown=1 and no attention levels. */
+int ddpm3d_comm_unique_id(void* out128);
+int ddpm3d_set_comm(ddpm3d_ctx* ctx, const void* id128, int rank, int world);
+int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total);
+
 /* ---- knobs and introspection ------------------------------------------------------------------ */
 /* "cuda_graph" (0/1, default 1): replay one captured graph per UNet evaluation;
  * "conv_path" (0 = auto, 1 = force the generic CUDA-core kernel everywhere, 2 = same as 0);
@@ -168,7 +180,7 @@ int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value);
 int64_t ddpm3d_launch_count(const ddpm3d_ctx* ctx);
 /* After a profiled call: synchronises and writes up to `cap` records; returns the record count.
  * `kind`: 0 conv-tcgen05, 1 conv-simt, 2 gn-stats, 3 gn-finalize, 4 gn-apply, 5 embedding, 6 update,
- * 7 attention, 8 pack/resample/misc, 9 conv-small (stem / head direct convolutions).  `work` = algorithmic flops (conv, attention) or bytes (others). */
+ * 7 attention, 8 pack/resample/misc, 9 conv-small (stem / head direct convolutions), 10 halo exchange (NCCL).  `work` = algorithmic flops (conv, attention) or bytes (others). */
 typedef struct ddpm3d_prof_record { int32_t kind; int32_t pad_; float ms; float pad2_; double work; } ddpm3d_prof_record;
 int ddpm3d_profile_read(ddpm3d_ctx* ctx, ddpm3d_prof_record* out, int cap);
 

@@ -1,0 +1,86 @@
+"""-m gpu, needs >= 2 GPUs (skipped otherwise; run with `gpurun --gpus 2`): one volume sharded as z-slabs
+over two ranks (halo exchange + GroupNorm all-gather over NCCL) must reproduce the single-GPU result."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from ddpm3d_b200 import script_util as su, slab
+    from oracle import cases
+    from oracle.weights import synth_inputs, synth_state_dict
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    res = {}
+    try:
+        for mode, shape, tol in ((False, (1, 1, 10, 16, 16), 2e-5), (False, (2, 1, 9, 16, 32), 2e-5),
+                                 (True, (1, 1, 12, 32, 32), 3e-2)):
+            over = dict(large_size=16, small_size=16, num_channels=64, num_res_blocks=2, num_head_channels=64,
+                        timestep_respacing="3", use_fp16=bool(mode))
+            flags = cases.sr_flags(**over)
+            cfg = cases.cfg_from_flags(flags)
+            sd = synth_state_dict(cfg, seed=11)
+
+            def make():
+                m, d = su.sr_create_model_and_diffusion(**flags)
+                m.load_state_dict(sd)
+                m.to(dev)
+                if mode:
+                    m.convert_to_fp16()
+                return m.eval(), d
+
+            single, diffusion = make()
+            sharded, _ = make()
+            sharded.enable_slab_sharding()
+            low, x_T, _ = synth_inputs(shape, 0)
+            low, x_T = low.to(dev), x_T.to(dev)
+            B, _, Z, H, W = shape
+            # (a) one evaluation
+            t = torch.tensor([555.0] * B, device=dev)
+            want = single(x_T, t, low_res=low)
+            bounds = slab.slab_bounds(Z, world)
+            z0, z1 = bounds[rank], bounds[rank + 1]
+            sharded.set_slab(z0, Z)
+            part = sharded(x_T[:, :, z0:z1].contiguous(), t, low_res=low[:, :, z0:z1].contiguous())
+            got = slab.gather_slabs(part, bounds)
+            e1 = float((got - want).abs().max() / want.abs().max())
+            # (b) the whole loop, philox noise (one global field)
+            want_s = diffusion.p_sample_loop(single, shape, noise=x_T, model_kwargs={"low_res": low}, rng="philox", seed=5)
+            got_s = slab.sample_volume_slabs(sharded, diffusion, low, noise=x_T, rng="philox", seed=5)
+            e2 = float((got_s - want_s).abs().max() / want_s.abs().max())
+            res[str((mode, shape))] = (e1, e2, tol, sharded.launch_count())
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_slab_sharding_matches_single_gpu():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 200)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    out = dict(q.get(timeout=10) for _ in range(2))
+    for rank in (0, 1):
+        for key, (e1, e2, tol, launches) in out[rank].items():
+            print(f"rank {rank} {key}: forward max-rel {e1:.2e}, loop max-rel {e2:.2e}, launches {launches}")
+            assert e1 <= tol, (key, e1)
+            assert e2 <= (1e-3 if tol < 1e-3 else 2e-1), (key, e2)

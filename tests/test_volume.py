@@ -97,3 +97,12 @@ def test_tiff_and_npz_roundtrip(tmp_path):
     assert v.shape == (4, 6, 6) and np.allclose(v, (pair[0] / 4).transpose(2, 0, 1))
     with pytest.raises(ValueError):
         io_formats.read_volume("x.png")
+
+
+def test_slab_bounds():
+    from ddpm3d_b200.slab import slab_bounds
+    assert slab_bounds(640, 8) == [0, 80, 160, 240, 320, 400, 480, 560, 640]
+    assert slab_bounds(110, 8) == [0, 14, 28, 42, 56, 70, 84, 97, 110]
+    assert slab_bounds(9, 2) == [0, 5, 9]
+    with pytest.raises(ValueError):
+        slab_bounds(3, 4)
