@@ -29,7 +29,7 @@ def _worker(rank, world, port, q):
         for mode, shape, tol in ((False, (1, 1, 10, 16, 16), 2e-5), (False, (2, 1, 9, 16, 32), 2e-5),
                                  (True, (1, 1, 12, 32, 32), 3e-2)):
             over = dict(large_size=16, small_size=16, num_channels=64, num_res_blocks=2, num_head_channels=64,
-                        timestep_respacing="3", use_fp16=bool(mode))
+                        timestep_respacing="10", use_fp16=bool(mode))
             flags = cases.sr_flags(**over)
             cfg = cases.cfg_from_flags(flags)
             sd = synth_state_dict(cfg, seed=11)
@@ -60,7 +60,7 @@ def _worker(rank, world, port, q):
             # (b) the whole loop, philox noise (one global field)
             want_s = diffusion.p_sample_loop(single, shape, noise=x_T, model_kwargs={"low_res": low}, rng="philox", seed=5)
             got_s = slab.sample_volume_slabs(sharded, diffusion, low, noise=x_T, rng="philox", seed=5)
-            e2 = float((got_s - want_s).abs().max() / want_s.abs().max())
+            e2 = float((got_s - want_s).pow(2).mean().sqrt() / want_s.pow(2).mean().sqrt())  # NRMSE of the volume
             res[str((mode, shape))] = (e1, e2, tol, sharded.launch_count())
         q.put((rank, res))
     finally:
@@ -81,6 +81,8 @@ def test_slab_sharding_matches_single_gpu():
     out = dict(q.get(timeout=10) for _ in range(2))
     for rank in (0, 1):
         for key, (e1, e2, tol, launches) in out[rank].items():
-            print(f"rank {rank} {key}: forward max-rel {e1:.2e}, loop max-rel {e2:.2e}, launches {launches}")
+            print(f"rank {rank} {key}: forward max-rel {e1:.2e}, loop NRMSE {e2:.2e}, launches {launches}")
             assert e1 <= tol, (key, e1)
-            assert e2 <= (1e-3 if tol < 1e-3 else 2e-1), (key, e2)
+            # fp32: only the GroupNorm summation order differs; bf16: two roundings-equivalent evaluations
+            # of a 10-step loop (the C1 bf16-vs-fp32 loop NRMSE is 8e-3, tests/test_gpu_model.py)
+            assert e2 <= (1e-4 if tol < 1e-3 else 5e-2), (key, e2)
