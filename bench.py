@@ -169,6 +169,85 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_c4(args, rank, world, dev):
+    """BASELINE.json config 4: one whole-body volume, Z split over the ranks (halo exchange + GroupNorm sums
+    over NCCL inside the library).  value = whole-volume UNet evals/s; scaling is strong."""
+    import torch.distributed as dist
+    from ddpm3d_b200 import script_util as su, slab
+    shape = (1, 1, 640, 192, 192)
+    if args.shape:
+        z, h, w = (int(v) for v in args.shape.split(","))
+        shape = (1, 1, z, h, w)
+    Z = shape[2]
+    model, diffusion = su.sr_create_model_and_diffusion(**C2_FLAGS)
+    model.load_state_dict(synth_weights(model._specs))
+    model.to(dev)
+    model.convert_to_fp16()
+    model.eval()
+    bounds = slab.slab_bounds(Z, world)
+    z0, z1 = bounds[rank], bounds[rank + 1]
+    if world > 1:
+        model.enable_slab_sharding()
+        model.set_slab(z0, Z)
+    g = torch.Generator().manual_seed(1234)
+    lshape = (1, 1, z1 - z0, shape[3], shape[4])
+    low = torch.rand(lshape, generator=g).to(dev)
+    x_T = torch.randn(lshape, generator=g).to(dev)
+    kw = {"low_res": low}
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model._sample_loop(diffusion, x_T, kw, None, 1, True, n_steps=Wm)
+    barrier()
+    l0 = model.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev.index) as clocks:
+        barrier()
+        e0.record()
+        out = model._sample_loop(diffusion, x_T, kw, None, 1, True, n_steps=K)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = model.launch_count() - l0
+    assert torch.isfinite(out).all()
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt[0])
+    breakdown = {}
+    if rank == 0 or world > 1:  # the profiled pass contains collectives: every rank runs it
+        model.set_option("profile", 1)
+        model._sample_loop(diffusion, x_T, kw, None, 1, True, n_steps=1)
+        for kind, t_ms, work in model.profile_read():
+            b = breakdown.setdefault(kind, {"ms": 0.0, "work": 0.0, "launches": 0})
+            b["ms"] += t_ms
+            b["work"] += work
+            b["launches"] += 1
+        model.set_option("profile", 0)
+    if rank == 0:
+        vox = shape[2] * shape[3] * shape[4]
+        flops = FLOPS_PER_EVAL * vox / 96 ** 3
+        line = {
+            "metric": "unet_evals_per_sec", "value": K / (ms * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"C4: paper-default 3D UNet on ONE {shape[2]}x{shape[3]}x{shape[4]} volume, Z split into "
+                                   f"{world} slab(s); one DDPM reverse step per bench step",
+                       "parallelism": f"z-slabs x{world}: 1-plane halo per 3x3x3 conv (NCCL send/recv), GroupNorm fp64 sums "
+                                      "all-gathered"},
+            "tflops_total": flops * K / (ms * 1e-3) / 1e12, "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "kernel_breakdown_ms_per_step_rank0": breakdown,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,6 +257,9 @@ def main():
     ap.add_argument("--conv-path", type=int, default=0, help="0 auto, 1 force SIMT, 2 force tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shape", default="", help="override Z,H,W (debug only; invalidates the metric)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2 (default, the driver's metric): one 96^3 patch per GPU; c4: ONE 640x192x192 volume "
+                         "sharded as z-slabs over the GPUs (strong scaling; extra measurement, BASELINE config 4)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -197,6 +279,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.workload == "c4":
+        return run_c4(args, rank, world, dev)
     shape = PATCH
     if args.shape:
         z, h, w = (int(v) for v in args.shape.split(","))
