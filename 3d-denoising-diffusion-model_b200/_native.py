@@ -30,7 +30,7 @@ class StepScalars(C.Structure):
     _fields_ = [(n, C.c_float) for n in (
         "model_t", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
         "posterior_mean_coef2", "min_log", "max_log", "fixed_variance", "fixed_log_variance",
-        "recip_coef1", "coef2_over_coef1", "pad_")]
+        "recip_coef1", "coef2_over_coef1", "alphas_cumprod", "alphas_cumprod_prev", "pad0_", "pad1_", "pad2_")]
 
 
 class ProfRecord(C.Structure):
@@ -57,6 +57,7 @@ SIGNATURES = {
     "ddpm3d_workspace_bytes": (C.c_int64, [_P, _I, _I, _I, _I]),
     "ddpm3d_unet_forward": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ddpm3d_set_schedule": (_I, [_P, C.POINTER(StepScalars), _I, _I, _I]),
+    "ddpm3d_set_sampler": (_I, [_P, _I, C.c_float]),
     "ddpm3d_p_sample_update": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, C.c_int64, _P]),
     "ddpm3d_p_sample": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P]),
     "ddpm3d_sample_loop": (_I, [_P, _P, _P, _P, _P, C.c_uint64, _I, _I, _P, _I, _I, _I, _I, _P]),

@@ -719,8 +719,19 @@ __global__ void p_sample_update_kernel(UpdateArgs a) {
         if (CLIP) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
         mu = __fadd_rn(__fmul_rn(sc.posterior_mean_coef1, x0), __fmul_rn(sc.posterior_mean_coef2, xs[k]));
       }
-      const float sd = expf(__fmul_rn(0.5f, logvar));
-      smp[k] = __fadd_rn(mu, __fmul_rn(__fmul_rn(mask, sd), z[k]));
+      if (a.ddim) {
+        // eps re-derived from x0 (:345-349), sigma and the Equation-12 mean (:563-580); op order as in the reference
+        const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(sc.sqrt_recip_alphas_cumprod, xs[k]), x0), sc.sqrt_recipm1_alphas_cumprod);
+        const float ab = sc.alphas_cumprod, abp = sc.alphas_cumprod_prev;
+        const float sigma = __fmul_rn(__fmul_rn(a.eta, __fsqrt_rn(__fdiv_rn(__fsub_rn(1.0f, abp), __fsub_rn(1.0f, ab)))),
+                                      __fsqrt_rn(__fsub_rn(1.0f, __fdiv_rn(ab, abp))));
+        const float mean_pred = __fadd_rn(__fmul_rn(x0, __fsqrt_rn(abp)),
+                                          __fmul_rn(__fsqrt_rn(__fsub_rn(__fsub_rn(1.0f, abp), __fmul_rn(sigma, sigma))), eps));
+        smp[k] = __fadd_rn(mean_pred, __fmul_rn(__fmul_rn(mask, sigma), z[k]));
+      } else {
+        const float sd = expf(__fmul_rn(0.5f, logvar));
+        smp[k] = __fadd_rn(mu, __fmul_rn(__fmul_rn(mask, sd), z[k]));
+      }
       x0s[k] = x0; mus[k] = mu; lvs[k] = logvar;
     }
     *reinterpret_cast<float4*>(a.sample + i) = make_float4(smp[0], smp[1], smp[2], smp[3]);

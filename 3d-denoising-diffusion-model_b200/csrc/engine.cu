@@ -154,6 +154,8 @@ struct ddpm3d_ctx {
   // sampler
   ddpm3d_step_scalars* d_table = nullptr;
   int T = 0, mean_type = DDPM3D_MEAN_EPSILON, var_type = DDPM3D_VAR_LEARNED_RANGE;
+  int ddim = 0;
+  float eta = 0.f;
   float* d_tmodel = nullptr;
   int32_t* d_counter = nullptr;
   int loop_B = 0;
@@ -1096,6 +1098,21 @@ int ddpm3d_set_schedule(ddpm3d_ctx* ctx, const ddpm3d_step_scalars* table, int T
   return DDPM3D_OK;
 }
 
+int ddpm3d_set_sampler(ddpm3d_ctx* ctx, int kind, float eta) {
+  DD_CHECK(ctx && (kind == 0 || kind == 1), DDPM3D_ERR_ARG, "set_sampler: kind must be 0 (DDPM) or 1 (DDIM)");
+  if (ctx->ddim == kind && ctx->eta == eta) return DDPM3D_OK;
+  if (ctx->device >= 0) {  // cached graphs bake the sampler in
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+    ctx->graphs.clear();
+    ctx->graph_launches.clear();
+  }
+  ctx->ddim = kind;
+  ctx->eta = eta;
+  return DDPM3D_OK;
+}
+
 int ddpm3d_p_sample_update(ddpm3d_ctx* ctx, const float* x, const float* model_out, const float* noise, const int32_t* t_index,
                            int clip_denoised, float* sample, float* pred_xstart, float* mean, float* log_variance, int B, int C,
                            int64_t n_spatial, void* stream) {
@@ -1105,6 +1122,7 @@ int ddpm3d_p_sample_update(ddpm3d_ctx* ctx, const float* x, const float* model_o
   UpdateArgs a{};
   a.x = x; a.model_out = model_out; a.noise = noise; a.t_index = t_index; a.table = ctx->d_table;
   a.mean_type = ctx->mean_type; a.var_type = ctx->var_type; a.clip = clip_denoised;
+    a.ddim = ctx->ddim; a.eta = ctx->eta;
   a.sample = sample; a.pred_xstart = pred_xstart; a.mean = mean; a.log_variance = log_variance;
   a.B = B; a.C = C; a.n = n_spatial; a.T = ctx->T;
   DD_TRY(p_sample_update_k(a, (cudaStream_t)stream));
@@ -1135,6 +1153,7 @@ int ddpm3d_p_sample(ddpm3d_ctx* ctx, const float* x, const float* low_res, const
     UpdateArgs a{};
     a.x = x; a.model_out = ctx->d_mo; a.noise = noise; a.step_counter = ctx->d_counter; a.table = ctx->d_table;
     a.mean_type = ctx->mean_type; a.var_type = ctx->var_type; a.clip = clip_denoised;
+    a.ddim = ctx->ddim; a.eta = ctx->eta;
     a.sample = sample; a.pred_xstart = pred_xstart;
     a.B = B; a.C = 1; a.n = n; a.T = ctx->T;
     DD_TRY(p_sample_update_k(a, cs));
@@ -1168,6 +1187,7 @@ int ddpm3d_sample_loop(ddpm3d_ctx* ctx, const float* x_T, const float* low_res, 
       UpdateArgs a{};
       a.x = img; a.model_out = ctx->d_mo; a.noise = noise; a.step_counter = ctx->d_counter; a.table = ctx->d_table;
       a.mean_type = ctx->mean_type; a.var_type = ctx->var_type; a.clip = clip_denoised;
+    a.ddim = ctx->ddim; a.eta = ctx->eta;
       a.sample = img;  // in place: purely elementwise
       a.B = B; a.C = 1; a.n = n; a.T = ctx->T;
       a.noise_step_stride = (int64_t)B * n;

@@ -114,6 +114,7 @@ struct UpdateArgs {
   int B = 0, C = 1; int64_t n = 0;       // n = spatial size per (b,c)
   int64_t noise_step_stride = 0;         // with step_counter: noise += exec_index * stride
   int T = 0;
+  int ddim = 0; float eta = 0.f;         // gaussian_diffusion.py:537-585 instead of :430-438
   int use_philox = 0; uint64_t seed = 0;
   // Philox counter = global element index b*idx_bstride + idx_offset + (local offset): slabs of one volume draw
   // disjoint parts of one noise field.  idx_bstride == 0 -> the local index (single GPU).

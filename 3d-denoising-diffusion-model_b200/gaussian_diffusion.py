@@ -142,6 +142,8 @@ class GaussianDiffusion:
             s.fixed_log_variance = np.float32(logvar[i])
             s.recip_coef1 = np.float32(recip_c1[i])
             s.coef2_over_coef1 = np.float32(c2_over_c1[i])
+            s.alphas_cumprod = np.float32(self.alphas_cumprod[i])
+            s.alphas_cumprod_prev = np.float32(self.alphas_cumprod_prev[i])
         return arr
 
     @property
@@ -193,7 +195,10 @@ class GaussianDiffusion:
         model_output = model(x, self._map_timesteps(t), **model_kwargs)
         return self._posterior(model, model_output, x, t, None, clip_denoised)
 
-    def _posterior(self, model, model_output, x, t, noise, clip_denoised):
+    def _set_sampler(self, ctx, ddim, eta):
+        N.check(N.lib().ddpm3d_set_sampler(ctx, 1 if ddim else 0, float(eta)))
+
+    def _posterior(self, model, model_output, x, t, noise, clip_denoised, ddim=False, eta=0.0):
         import torch
         B, C = x.shape[:2]
         learned = self.model_var_type in (ModelVarType.LEARNED, ModelVarType.LEARNED_RANGE)
@@ -204,6 +209,7 @@ class GaussianDiffusion:
         nz = noise.contiguous().float() if noise is not None else x
         n_sp = int(np.prod(x.shape[2:]))
         L = N.lib()
+        self._set_sampler(ctx, ddim, eta)
         with torch.cuda.device(x.device):
             N.check(L.ddpm3d_p_sample_update(
                 ctx, N.ptr(x), N.ptr(model_output), N.ptr(nz), N.ptr(t.to(torch.int32).contiguous()),
@@ -235,6 +241,38 @@ class GaussianDiffusion:
         out = self._posterior(model, model_output, x, t, noise, clip_denoised)
         return {"sample": out["sample"], "pred_xstart": out["pred_xstart"]}
 
+    # ---- DDIM (gaussian_diffusion.py:537-585, 625-707) ---------------------------------------------
+    def ddim_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, eta=0.0,
+                    noise=None):
+        """gaussian_diffusion.py:537-585.  `noise` (extension) replaces th.randn_like(x)."""
+        import torch
+        self._unsupported(denoised_fn, cond_fn)
+        model_kwargs = model_kwargs or {}
+        x = x.contiguous().float()
+        if noise is None:
+            noise = torch.randn_like(x)
+        model_output = model(x, self._map_timesteps(t), **model_kwargs)
+        out = self._posterior(model, model_output, x, t, noise, clip_denoised, ddim=True, eta=eta)
+        return {"sample": out["sample"], "pred_xstart": out["pred_xstart"]}
+
+    def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                         model_kwargs=None, device=None, progress=False, eta=0.0, **ext):
+        """gaussian_diffusion.py:625-657."""
+        final = None
+        for sample in self.p_sample_loop_progressive(model, shape, noise=noise, clip_denoised=clip_denoised,
+                                                     denoised_fn=denoised_fn, cond_fn=cond_fn, model_kwargs=model_kwargs,
+                                                     device=device, progress=progress, _final_only=True, _ddim=True,
+                                                     _eta=eta, **ext):
+            final = sample
+        return final["sample"].clone()
+
+    def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                                     model_kwargs=None, device=None, progress=False, eta=0.0, **ext):
+        """gaussian_diffusion.py:659-707."""
+        yield from self.p_sample_loop_progressive(model, shape, noise=noise, clip_denoised=clip_denoised,
+                                                  denoised_fn=denoised_fn, cond_fn=cond_fn, model_kwargs=model_kwargs,
+                                                  device=device, progress=progress, _ddim=True, _eta=eta, **ext)
+
     def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                       model_kwargs=None, device=None, progress=False, **ext):
         """gaussian_diffusion.py:441-485.  Extensions (keyword only): `step_noise` = iterable of
@@ -251,7 +289,7 @@ class GaussianDiffusion:
 
     def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None,
                                   cond_fn=None, model_kwargs=None, device=None, progress=False,
-                                  step_noise=None, rng="torch", seed=0, _final_only=False):
+                                  step_noise=None, rng="torch", seed=0, _final_only=False, _ddim=False, _eta=0.0):
         """gaussian_diffusion.py:487-535."""
         import torch
         from .unet import UNetModel_noatt
@@ -267,6 +305,9 @@ class GaussianDiffusion:
             from tqdm.auto import tqdm
             indices = tqdm(indices)
         native = isinstance(model, UNetModel_noatt)
+        if native:
+            model._bind_schedule(self)
+            self._set_sampler(model._ctx, _ddim, _eta)
         if native and _final_only and (rng == "philox" or isinstance(step_noise, torch.Tensor)):
             # whole reverse loop on the device: one CUDA graph per step, no host round trips
             out = model._sample_loop(self, img, model_kwargs, step_noise, seed, clip_denoised)
@@ -284,6 +325,10 @@ class GaussianDiffusion:
                 out = model._p_sample(self, img, nz, i, model_kwargs, clip_denoised, clone=not _final_only)
             else:
                 t = torch.tensor([i] * B, device=device)
-                out = self.p_sample(model, img, t, clip_denoised=clip_denoised, model_kwargs=model_kwargs, noise=nz)
+                if _ddim:
+                    out = self.ddim_sample(model, img, t, clip_denoised=clip_denoised, model_kwargs=model_kwargs,
+                                           eta=_eta, noise=nz)
+                else:
+                    out = self.p_sample(model, img, t, clip_denoised=clip_denoised, model_kwargs=model_kwargs, noise=nz)
             yield out
             img = out["sample"]

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DDPM3D_ABI_VERSION 1
+#define DDPM3D_ABI_VERSION 2
 
 #define DDPM3D_OK 0
 #define DDPM3D_ERR_ARG (-1)     /* bad argument / unsupported configuration */
@@ -95,7 +95,9 @@ typedef struct ddpm3d_step_scalars {
   float fixed_log_variance;
   float recip_coef1;                   /* 1/posterior_mean_coef1                (:335-343) */
   float coef2_over_coef1;
-  float pad_;
+  float alphas_cumprod;                /* DDIM (:567-568) */
+  float alphas_cumprod_prev;
+  float pad_[3];
 } ddpm3d_step_scalars;
 
 const char* ddpm3d_last_error(void);
@@ -144,6 +146,11 @@ int ddpm3d_set_schedule(ddpm3d_ctx* ctx, const ddpm3d_step_scalars* table, int T
 int ddpm3d_p_sample_update(ddpm3d_ctx* ctx, const float* x, const float* model_out, const float* noise,
                            const int32_t* t_index, int clip_denoised, float* sample, float* pred_xstart,
                            float* mean, float* log_variance, int B, int C, int64_t n_spatial, void* stream);
+
+/* DDIM (gaussian_diffusion.py:537-585): kind 0 = ancestral DDPM update (default), 1 = DDIM with `eta`.  Applies to
+ * ddpm3d_p_sample_update / ddpm3d_p_sample / ddpm3d_sample_loop (= ddim_sample / ddim_sample_loop, :625-707).  The
+ * DDIM update has no exp(): every output is bit-identical to the reference's fp32 torch ops. */
+int ddpm3d_set_sampler(ddpm3d_ctx* ctx, int kind, float eta);
 
 /* p_sample (gaussian_diffusion.py:395-439) = UNet + update for step index `i` (same for the whole
  * batch, as p_sample_loop_progressive :522-525 issues it). */

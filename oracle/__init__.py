@@ -32,5 +32,5 @@ from .schedule import (  # noqa: F401
     make_tables,
 )
 from .unet import UNetConfig, build_plan, param_specs, unet_forward, timestep_embedding  # noqa: F401
-from .sampler import p_mean_variance, p_sample, p_sample_loop  # noqa: F401
+from .sampler import ddim_sample, p_mean_variance, p_sample, p_sample_loop  # noqa: F401
 from .weights import synth_state_dict, synth_inputs  # noqa: F401

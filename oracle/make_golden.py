@@ -74,9 +74,41 @@ def make_volume_golden():
     np.savez_compressed(os.path.join(OUT, "volume.npz"), **z)
 
 
+DDIM_ETAS = [0.0, 0.5, 1.0]
+
+
+def make_ddim_golden():
+    """ddim_sample (gaussian_diffusion.py:537-585) of the reference on the PMV cases' inputs, three etas."""
+    z = {}
+    for i, case in enumerate(PMV_CASES):
+        if case.get("previous_x") or case.get("learned"):
+            continue
+        d = su.create_gaussian_diffusion(**case["diffusion"])
+        g = torch.Generator().manual_seed(100 + i)
+        oc = 2 if case["diffusion"].get("learn_sigma") else 1
+        shape = (2, 1, 3, 4, 5)
+        x = torch.randn(shape, generator=g)
+        mo = torch.randn((2, oc, 3, 4, 5), generator=g) * 1.5
+        noise = torch.randn(shape, generator=g)
+        t = torch.tensor(case["t"])
+        for eta in DDIM_ETAS:
+            orig = torch.randn_like
+            torch.randn_like = lambda _x: noise
+            try:
+                out = d.ddim_sample(lambda *_a, **_k: mo, x, t, clip_denoised=case["clip"], eta=eta)
+            finally:
+                torch.randn_like = orig
+            z[f"{i}/{eta}/sample"] = out["sample"].numpy()
+            z[f"{i}/{eta}/pred_xstart"] = out["pred_xstart"].contiguous().numpy()
+    np.savez_compressed(os.path.join(OUT, "ddim.npz"), **z)
+
+
 def main():
     if "--volume-only" in sys.argv:
         make_volume_golden()
+        return
+    if "--ddim-only" in sys.argv:
+        make_ddim_golden()
         return
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -188,6 +220,7 @@ def main():
     }
     np.savez_compressed(os.path.join(OUT, "c1_loop.npz"), **z)
     make_volume_golden()
+    make_ddim_golden()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -78,6 +78,19 @@ def p_sample(tabs: DiffusionTables, model_output, x, t, noise, clip_denoised=Tru
     return dict(sample=sample, pred_xstart=out["pred_xstart"], **{k: out[k] for k in ("mean", "log_variance")})
 
 
+def ddim_sample(tabs: DiffusionTables, model_output, x, t, noise, clip_denoised=True, eta=0.0) -> dict:
+    """gaussian_diffusion.py:537-585 (cond_fn=None), same fp32 op order."""
+    out = p_mean_variance(tabs, model_output, x, t, clip_denoised)
+    x0 = out["pred_xstart"]
+    eps = (_pick(tabs.sqrt_recip_alphas_cumprod, t, x) * x - x0) / _pick(tabs.sqrt_recipm1_alphas_cumprod, t, x)
+    ab = _pick(tabs.alphas_cumprod, t, x)
+    abp = _pick(tabs.alphas_cumprod_prev, t, x)
+    sigma = eta * torch.sqrt((1 - abp) / (1 - ab)) * torch.sqrt(1 - ab / abp)
+    mean_pred = x0 * torch.sqrt(abp) + torch.sqrt(1 - abp - sigma ** 2) * eps
+    mask = (t != 0).float().view(-1, *([1] * (x.dim() - 1)))
+    return dict(sample=mean_pred + mask * sigma * noise, pred_xstart=x0)
+
+
 @torch.no_grad()
 def p_sample_loop(tabs: DiffusionTables, model: Callable, x_T: torch.Tensor, noises,
                   clip_denoised: bool = True, on_step: Optional[Callable] = None) -> torch.Tensor:

@@ -153,3 +153,24 @@ def test_attention_core(dt, B, T, C, heads, new_order):
     torch.cuda.synchronize()
     tol = ROUND_TOL[dt]
     assert max_rel(out.float().permute(0, 2, 1).cpu(), ref) <= tol
+
+
+@pytest.mark.parametrize("i", [i for i, c in enumerate(cases.PMV_CASES) if not (c.get("previous_x") or c.get("learned"))])
+def test_ddim_update_bit_exact(golden_dir, i):
+    """ddim_sample (gaussian_diffusion.py:537-585) against the unmodified reference's outputs: the DDIM update
+    has no exp(), so sample and pred_xstart are bit-identical."""
+    case = cases.PMV_CASES[i]
+    g = np.load(os.path.join(golden_dir, "ddim.npz"))
+    d = su.create_gaussian_diffusion(**case["diffusion"])
+    gen = torch.Generator().manual_seed(100 + i)
+    oc = 2 if case["diffusion"].get("learn_sigma") else 1
+    x = torch.randn((2, 1, 3, 4, 5), generator=gen)
+    mo = torch.randn((2, oc, 3, 4, 5), generator=gen) * 1.5
+    noise = torch.randn((2, 1, 3, 4, 5), generator=gen)
+    t = torch.tensor(case["t"], device=DEV)
+    for eta in (0.0, 0.5, 1.0):
+        out = d.ddim_sample(lambda x_, t_, **k: mo.to(DEV), x.to(DEV), t, clip_denoised=case["clip"], eta=eta,
+                            noise=noise.to(DEV))
+        torch.cuda.synchronize()
+        assert np.array_equal(out["sample"].cpu().numpy().view(np.int32), g[f"{i}/{eta}/sample"].view(np.int32)), eta
+        assert np.array_equal(out["pred_xstart"].cpu().numpy().view(np.int32), g[f"{i}/{eta}/pred_xstart"].view(np.int32))

@@ -35,11 +35,11 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/ddpm3d.h but not exported"
     assert declared == set(N.SIGNATURES), "ctypes binding and header disagree"
-    assert N.lib().ddpm3d_abi_version() == 1
+    assert N.lib().ddpm3d_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(N.StepScalars) == 48
+    assert C.sizeof(N.StepScalars) == 64
     assert C.sizeof(N.ProfRecord) == 24
     assert C.sizeof(N.Config) == 4 * (6 + 8 + 1 + 8 + 8)
 
