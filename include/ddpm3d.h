@@ -149,7 +149,7 @@ int ddpm3d_p_sample_update(ddpm3d_ctx* ctx, const float* x, const float* model_o
 
 /* DDIM (gaussian_diffusion.py:537-585): kind 0 = ancestral DDPM update (default), 1 = DDIM with `eta`.  Applies to
  * ddpm3d_p_sample_update / ddpm3d_p_sample / ddpm3d_sample_loop (= ddim_sample / ddim_sample_loop, :625-707).  The
- * DDIM update has no exp(): every output is bit-identical to the reference's fp32 torch ops. */
+ * DDIM update has no exp(): with correctly rounded sqrt / div it matches the reference's fp32 torch ops to the bit on CUDA. */
 int ddpm3d_set_sampler(ddpm3d_ctx* ctx, int kind, float eta);
 
 /* p_sample (gaussian_diffusion.py:395-439) = UNet + update for step index `i` (same for the whole
