@@ -63,8 +63,6 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ s0,
   const int rpi = blockDim.x / nvec;
   const int v = threadIdx.x % nvec, r = threadIdx.x / nvec;
   const int b = blockIdx.y, chunk = blockIdx.x;
-  const int per = (rows + n_chunks - 1) / n_chunks;
-  const int r0 = chunk * per, r1 = min(rows, r0 + per);
 
   const T* base;
   int Csrc;
@@ -82,27 +80,34 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ s0,
   float s[N], q[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  // Row blocks of U*rpi rows are dealt round-robin to the chunks, so at any moment the whole grid streams one
+  // narrow window of the tensor (DRAM page / TLB locality on multi-GB tensors); each chunk still sums its rows
+  // in a fixed order.
   constexpr int U = 8;  // independent 16-byte loads in flight per thread
-  int row = r0 + r;
-  for (; row + (U - 1) * rpi < r1; row += U * rpi) {
-    Vec<T> a[U];
+  const int RB = U * rpi;
+  for (int rb0 = chunk * RB; rb0 < rows; rb0 += n_chunks * RB) {
+    const int row = rb0 + r;
+    if (rb0 + RB <= rows) {
+      Vec<T> a[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) a[u].load(base + (int64_t)(row + u * rpi) * Csrc);
+      for (int u = 0; u < U; ++u) a[u].load(base + (int64_t)(row + u * rpi) * Csrc);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float f[N];
-      a[u].unpack(f);
+      for (int u = 0; u < U; ++u) {
+        float f[N];
+        a[u].unpack(f);
 #pragma unroll
-      for (int i = 0; i < N; ++i) { const float x = f[i] + add[i]; s[i] += x; q[i] = fmaf(x, x, q[i]); }
+        for (int i = 0; i < N; ++i) { const float x = f[i] + add[i]; s[i] += x; q[i] = fmaf(x, x, q[i]); }
+      }
+    } else {
+      for (int rr = row; rr < rows; rr += rpi) {
+        Vec<T> a;
+        a.load(base + (int64_t)rr * Csrc);
+        float f[N];
+        a.unpack(f);
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const float x = f[i] + add[i]; s[i] += x; q[i] = fmaf(x, x, q[i]); }
+      }
     }
-  }
-  for (; row < r1; row += rpi) {
-    Vec<T> a;
-    a.load(base + (int64_t)row * Csrc);
-    float f[N];
-    a.unpack(f);
-#pragma unroll
-    for (int i = 0; i < N; ++i) { const float x = f[i] + add[i]; s[i] += x; q[i] = fmaf(x, x, q[i]); }
   }
   float* mine = sm + ((int64_t)r * Ctot + v * N) * 2;
 #pragma unroll
@@ -277,40 +282,44 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0,
       Bv[k] = b4.x; Bv[k + 1] = b4.y; Bv[k + 2] = b4.z; Bv[k + 3] = b4.w;
     }
   }
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows_it, r0 + rows_per_block);
+  // row blocks are dealt round-robin to the CTAs (see gn_stats_kernel)
   if (MODE == RS_NONE) {
     constexpr int U = 4;
-    int row = r0 + r;
-    for (; row + (U - 1) * rpi < r1; row += U * rpi) {
-      Vec<T> a[U];
+    const int RB = U * rpi;
+    for (int rb0 = blockIdx.x * RB; rb0 < rows_it; rb0 += gridDim.x * RB) {
+      const int row = rb0 + r;
+      if (rb0 + RB <= rows_it) {
+        Vec<T> a[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) a[u].load(base + (int64_t)(row + u * rpi) * Csrc);
+        for (int u = 0; u < U; ++u) a[u].load(base + (int64_t)(row + u * rpi) * Csrc);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        float f[N], y[N];
-        a[u].unpack(f);
+        for (int u = 0; u < U; ++u) {
+          float f[N], y[N];
+          a[u].unpack(f);
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-          const float t = fmaf(f[k], A[k], Bv[k]);
-          y[k] = SILU ? silu_f(t) : t;
+          for (int k = 0; k < N; ++k) {
+            const float t = fmaf(f[k], A[k], Bv[k]);
+            y[k] = SILU ? silu_f(t) : t;
+          }
+          gn_put<T, TO, N>(obase + (int64_t)(row + u * rpi) * Ctot, y);
         }
-        gn_put<T, TO, N>(obase + (int64_t)(row + u * rpi) * Ctot, y);
-      }
-    }
-    for (; row < r1; row += rpi) {
-      Vec<T> a;
-      a.load(base + (int64_t)row * Csrc);
-      float f[N], y[N];
-      a.unpack(f);
+      } else {
+        for (int rr = row; rr < rows_it; rr += rpi) {
+          Vec<T> a;
+          a.load(base + (int64_t)rr * Csrc);
+          float f[N], y[N];
+          a.unpack(f);
 #pragma unroll
-      for (int k = 0; k < N; ++k) {
-        const float t = fmaf(f[k], A[k], Bv[k]);
-        y[k] = SILU ? silu_f(t) : t;
+          for (int k = 0; k < N; ++k) {
+            const float t = fmaf(f[k], A[k], Bv[k]);
+            y[k] = SILU ? silu_f(t) : t;
+          }
+          gn_put<T, TO, N>(obase + (int64_t)rr * Ctot, y);
+        }
       }
-      gn_put<T, TO, N>(obase + (int64_t)row * Ctot, y);
     }
   } else if (MODE == RS_POOL) {
-    for (int row = r0 + r; row < r1; row += rpi) {
+    for (int row = blockIdx.x * rpi + r; row < rows_it; row += gridDim.x * rpi) {
       const int wo = row % Wo;
       const int t1 = row / Wo;
       const int ho = t1 % Ho;
@@ -339,7 +348,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0,
       gn_put<T, TO, N>(obase + (int64_t)row * Ctot, y);
     }
   } else {  // RS_UP: one input row -> four output rows
-    for (int row = r0 + r; row < r1; row += rpi) {
+    for (int row = blockIdx.x * rpi + r; row < rows_it; row += gridDim.x * rpi) {
       Vec<T> a;
       a.load(base + (int64_t)row * Csrc);
       float f[N], y[N];
