@@ -129,5 +129,9 @@ template <> struct Vec<f16> {
 
 // accurate expf: the GN/SiLU kernels are HBM-bound, the extra ALU is hidden
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+// 16-bit outputs: ex2.approx + fast division (<= 4 ulp fp32, far below the 2^-9 / 2^-12 output rounding) keeps
+// the apply pass HBM-bound instead of ALU-bound
+__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+template <typename T> __device__ __forceinline__ float silu_t(float v) { return sizeof(T) == 2 ? silu_fast(v) : silu_f(v); }
 
 }  // namespace ddpm3d

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0,
 #pragma unroll
           for (int k = 0; k < N; ++k) {
             const float t = fmaf(f[k], A[k], Bv[k]);
-            y[k] = SILU ? silu_f(t) : t;
+            y[k] = SILU ? silu_t<TO>(t) : t;
           }
           gn_put<T, TO, N>(obase + (int64_t)(row + u * rpi) * Ctot, y);
         }
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0,
 #pragma unroll
           for (int k = 0; k < N; ++k) {
             const float t = fmaf(f[k], A[k], Bv[k]);
-            y[k] = SILU ? silu_f(t) : t;
+            y[k] = SILU ? silu_t<TO>(t) : t;
           }
           gn_put<T, TO, N>(obase + (int64_t)rr * Ctot, y);
         }
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0,
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           const float t = fmaf(f[k], A[k], Bv[k]);
-          y[k] += SILU ? silu_f(t) : t;
+          y[k] += SILU ? silu_t<TO>(t) : t;
         }
       }
 #pragma unroll
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0,
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const float t = fmaf(f[k], A[k], Bv[k]);
-        y[k] = SILU ? silu_f(t) : t;
+        y[k] = SILU ? silu_t<TO>(t) : t;
       }
       const int w = row % W;
       const int t1 = row / W;
