@@ -36,6 +36,7 @@ constexpr int BK = 64;       // channels per k-step (128 bytes of bf16 = one swi
 constexpr int UMMA_K = 16;
 constexpr int NTHREADS = 192;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+constexpr int CS_SMEM_MAX = 32 * 1024;  // channel-sum accumulators: 4 warps x B x Cout x 2 floats
 
 struct TcParams {
   int nsrc;
@@ -54,6 +55,8 @@ struct TcParams {
   const void* res;   // T
   int res_mode;
   void* out;         // T
+  float* chsum;      // [B][CHSUM_SLOTS][Cout][2] per-CTA channel sums of the output, or NULL
+  uint32_t cs_off;   // byte offset of the channel-sum accumulators in dynamic smem
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -287,6 +290,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     // ===================================== epilogue ==========================================
     const int sub = warp & 3;  // TMEM sub-partition this warp may read: lanes 32*sub .. 32*sub+31
     const int row = sub * 32 + lane;
+    float* cs_acc = reinterpret_cast<float*>(smem_raw + p.cs_off);  // [4 warps][B][Cout][2], one slot per warp
+    if (p.chsum)
+      for (int i = lane; i < p.B * p.Cout * 2; i += 32) cs_acc[(size_t)sub * p.B * p.Cout * 2 + i] = 0.f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -313,8 +319,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         uint32_t r[32];
         tmem_ld32(t_row + (uint32_t)c, r);
         tmem_ld_wait();
+        float v[32];
         if (valid) {
-          float v[32];
           const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -358,6 +364,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             for (int q = 0; q < 4; ++q) w4[q] = pack2<T>(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
             *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (p.chsum) {
+          // column sums over the warp's 32 rows by a reduce-scatter butterfly (31 shuffles per quantity):
+          // lane L ends up with channel c + L
+          float q2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) q2[j] = v[j] * v[j];
+#pragma unroll
+          for (int half = 16; half >= 1; half >>= 1) {
+            const bool upper = (lane & half) != 0;
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+              const float send_s = upper ? v[j] : v[j + half], keep_s = upper ? v[j + half] : v[j];
+              const float send_q = upper ? q2[j] : q2[j + half], keep_q = upper ? q2[j + half] : q2[j];
+              v[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, half);
+              q2[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, half);
+            }
+          }
+          float* acc = cs_acc + (((size_t)sub * p.B + b) * p.Cout + n0 + c + lane) * 2;
+          acc[0] += v[0];
+          acc[1] += q2[0];
         }
       }
       }  // MT
@@ -365,6 +395,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.chsum) {  // combine the four warps' slots in a fixed order and publish this CTA's partial
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = (warp - 2) * 32 + lane, n = p.B * p.Cout * 2;
+      for (int i = et; i < n; i += 128) {
+        const float t = ((cs_acc[i] + cs_acc[n + i]) + cs_acc[2 * n + i]) + cs_acc[3 * n + i];
+        const int bb = i / (p.Cout * 2), rem = i - bb * p.Cout * 2;
+        p.chsum[((size_t)bb * CHSUM_SLOTS + blockIdx.x) * p.Cout * 2 + rem] = t;
+      }
     }
   }
 
@@ -457,15 +496,24 @@ int sm_count() {
 
 template <typename T, int MT, int BN, int NSTAGE>
 int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s) {
-  constexpr size_t smem = (size_t)NSTAGE * (MT * A_BYTES + BN * BK * 2) + 1024;
-  static_assert(smem <= 227 * 1024, "shared memory budget");
+  constexpr size_t stage_smem = (size_t)NSTAGE * (MT * A_BYTES + BN * BK * 2) + 1024;
+  constexpr size_t smem_max = stage_smem + CS_SMEM_MAX;
+  static_assert(smem_max <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, MT, BN, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, MT, BN, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     configured = true;
   }
   const int grid = std::min(p.num_tiles, sm_count());
-  conv_tc_kernel<T, MT, BN, NSTAGE><<<grid, NTHREADS, smem, s>>>(maps[0], maps[1], maps[2], mapW, p);
+  TcParams q = p;
+  size_t smem = stage_smem;
+  if (q.chsum) {
+    q.cs_off = (uint32_t)stage_smem;
+    smem += (size_t)4 * q.B * q.Cout * 2 * sizeof(float);
+    if (grid < CHSUM_SLOTS)  // slots of CTAs that do not exist must read as zero
+      DD_CUDA(cudaMemsetAsync(q.chsum, 0, (size_t)q.B * CHSUM_SLOTS * q.Cout * 2 * sizeof(float), s));
+  }
+  conv_tc_kernel<T, MT, BN, NSTAGE><<<grid, NTHREADS, smem, s>>>(maps[0], maps[1], maps[2], mapW, q);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }
@@ -486,9 +534,14 @@ bool conv_tc_eligible(const ConvArgs& a) {
   return true;
 }
 
-int conv_tc(const ConvArgs& a, cudaStream_t s) {
+int conv_tc(ConvArgs& a, cudaStream_t s) {
   DD_CHECK(conv_tc_eligible(a), DDPM3D_ERR_ARG, "conv_tc: shape not eligible");
   TcParams p{};
+  a.chsum_written = 0;
+  if (a.chsum_out && (size_t)4 * a.B * a.Cout * 2 * sizeof(float) <= (size_t)CS_SMEM_MAX && sm_count() <= CHSUM_SLOTS) {
+    p.chsum = a.chsum_out;
+    a.chsum_written = 1;
+  }
   p.nsrc = 1 + a.n_extra;
   p.chunks[0] = a.main.C / BK;
   p.taps = a.taps;

@@ -237,6 +237,51 @@ __global__ void __launch_bounds__(1024) gn_finalize_multi_kernel(const double* _
   }
 }
 
+// finalize from per-CTA channel sums written by the convolution epilogues: chsum_s[B][P][C_s][2].
+// grid (32 groups, B), 128 threads; fixed reduction order -> deterministic.
+__global__ void __launch_bounds__(128) gn_finalize_chsum_kernel(const float* __restrict__ cs0, const float* __restrict__ cs1,
+                                                                int C0, int C1, int P, double inv_count,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                const float* __restrict__ film, int64_t film_stride,
+                                                                float* __restrict__ ab) {
+  __shared__ double sh[2][128];
+  const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int Ctot = C0 + C1, gpc = Ctot / 32;
+  const int n = P * gpc;  // (slot, channel-in-group) pairs of this group
+  double s = 0.0, q = 0.0;
+  for (int i = tid; i < n; i += 128) {
+    const int slot = i / gpc, c = g * gpc + i % gpc;
+    const float* src = c < C0 ? cs0 + (((int64_t)b * P + slot) * C0 + c) * 2 : cs1 + (((int64_t)b * P + slot) * C1 + (c - C0)) * 2;
+    s += (double)src[0];
+    q += (double)src[1];
+  }
+  sh[0][tid] = s;
+  sh[1][tid] = q;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (tid < o) { sh[0][tid] += sh[0][tid + o]; sh[1][tid] += sh[1][tid + o]; }
+    __syncthreads();
+  }
+  const double mean = sh[0][0] * inv_count;
+  double var = sh[1][0] * inv_count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float fmean = (float)mean, rstd = (float)(1.0 / sqrt(var + 1e-5));
+  float* A = ab + (int64_t)b * 2 * Ctot;
+  float* Bv = A + Ctot;
+  for (int c = g * gpc + tid; c < (g + 1) * gpc; c += 128) {
+    float a = rstd * gamma[c];
+    float o = beta[c] - fmean * a;
+    if (film) {
+      const float sc = 1.0f + film[(int64_t)b * film_stride + c];
+      const float sh2 = film[(int64_t)b * film_stride + Ctot + c];
+      a *= sc;
+      o = o * sc + sh2;
+    }
+    A[c] = a;
+    Bv[c] = o;
+  }
+}
+
 template <typename T, typename TO, int N>
 __device__ __forceinline__ void gn_put(TO* dst, const float* y) {
   if constexpr (sizeof(TO) == sizeof(T)) {
@@ -460,6 +505,17 @@ int gn_forward(const GnArgs& a, cudaStream_t s, int* launches) {
   DD_TRY(gn_apply_any(a, s));
   if (launches) *launches += 3;
   return DDPM3D_OK;
+}
+
+int gn_forward_chsum(const GnArgs& a, cudaStream_t s) {
+  DD_TRY(gn_check(a));
+  const int Ctot = a.C[0] + a.C[1];
+  DD_CHECK(a.chsum[0] && (a.C[1] == 0 || a.chsum[1]) && !a.pre_add, DDPM3D_ERR_STATE, "groupnorm: channel sums missing");
+  const double inv_count = 1.0 / ((double)a.Z * a.H * a.W * (Ctot / 32));
+  gn_finalize_chsum_kernel<<<dim3(32, a.B), 128, 0, s>>>(a.chsum[0], a.chsum[1], a.C[0], a.C[1], CHSUM_SLOTS, inv_count, a.gamma,
+                                                         a.beta, a.film, a.film_stride, a.ab);
+  DD_CUDA(cudaGetLastError());
+  return gn_apply_any(a, s);
 }
 
 int gn_stats_local(const GnArgs& a, double* sums, cudaStream_t s) {

@@ -61,6 +61,7 @@ struct Param {
 struct Act {
   void* p = nullptr;
   int C = 0, H = 0, W = 0;
+  float* chsum = nullptr;  // per-CTA channel sums of this tensor from the producing conv's epilogue (or NULL)
 };
 
 struct Arena {
@@ -164,7 +165,7 @@ struct ddpm3d_ctx {
   float* d_img = nullptr;
   size_t img_cap = 0;
   // options
-  int use_graph = 1, conv_path = 0, profile = 0;
+  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1;
   cudaStream_t cap_stream = nullptr;
   float* d_freqs = nullptr;  // timestep_embedding frequencies computed by the host exactly like nn.py:113-115
   int n_freqs = 0;
@@ -476,9 +477,12 @@ struct Run {
     cudaEventRecord(ctx->prof.back().b, s);
   }
 
+  float* alloc_chsum(int C) { return (float*)arena.alloc((size_t)B * CHSUM_SLOTS * C * 2 * sizeof(float)); }
+
   int conv(ConvArgs& a) {
     a.B = B;
     a.Z = Z;
+    if (zp || !ctx->fuse_stats) a.chsum_out = nullptr;  // sharded statistics take the all-gather path
     ++launches;
     if (arena.dry) return DDPM3D_OK;
     double K = (double)a.taps * a.main.C;
@@ -489,6 +493,7 @@ struct Run {
     const bool stem = !tc && ctx->conv_path != 1 && conv_stem_eligible(a);
     const bool head = !tc && ctx->conv_path != 1 && conv_head_eligible(a);
     prof_begin(tc ? 0 : ((stem || head) ? 9 : 1), flops);
+    a.chsum_written = 0;
     const int r = tc ? conv_tc(a, s) : (stem ? conv_stem(a, s) : (head ? conv_head(a, s) : conv_simt(a, s)));
     prof_end();
     return r;
@@ -513,9 +518,12 @@ struct Run {
     const double n = (double)B * Z * g.H * g.W * Ctot;
     const double in_b = is_half_dt(g.dt) ? 2 : 4, out_b = (is_half_dt(g.dt) && !g.out_f32) ? 2 : 4;
     const double scale = g.resample == RS_POOL ? 0.25 : (g.resample == RS_UP ? 4.0 : 1.0);
-    prof_begin(4, n * (2 * in_b + out_b * scale));
+    const bool fused = !zp && !g.pre_add && g.chsum[0] && (g.C[1] == 0 || g.chsum[1]);
+    prof_begin(4, n * ((fused ? 1 : 2) * in_b + out_b * scale));
     int r;
-    if (zp) {  // z-slab sharding: statistics span all ranks (fp64 sums all-gathered, summed in rank order)
+    if (fused) {
+      r = gn_forward_chsum(g, s);
+    } else if (zp) {  // z-slab sharding: statistics span all ranks (fp64 sums all-gathered, summed in rank order)
       r = gn_stats_local(g, sums, s);
       if (r == DDPM3D_OK) r = comm_allgather_f64(ctx->slab, sums, gathered, (size_t)B * 64, s);
       if (r == DDPM3D_OK) {
@@ -546,6 +554,7 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   DD_CHECK(L.skip_conv || nsrc == 1, DDPM3D_ERR_ARG, "identity skip over a channel concat is not supported");
   out->C = L.cout; out->H = Ho; out->W = Wo;
   out->p = R.arena.alloc(R.act_bytes(Ho, Wo, L.cout));
+  float* out_cs = R.alloc_chsum(L.cout);
   const size_t mark = R.arena.off;
 
   // in_layers: GN32 -> SiLU (-> h_upd)                                   unet.py:237-244
@@ -553,7 +562,7 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   GnArgs g{};
   g.out_zpad = R.zp;
   g.dt = dt;
-  for (int i = 0; i < nsrc; ++i) { g.src[i] = src[i].p; g.C[i] = src[i].C; }
+  for (int i = 0; i < nsrc; ++i) { g.src[i] = src[i].p; g.C[i] = src[i].C; g.chsum[i] = src[i].chsum; }
   g.H = H; g.W = W;
   g.gamma = L.gn1_g; g.beta = L.gn1_b;
   g.silu = 1;
@@ -569,6 +578,7 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   c.taps = 27;
   c.w = L.c1.w; c.bias = L.c1.bias;
   c.out = h2; c.Ho = Ho; c.Wo = Wo; c.Cout = L.cout;
+  c.chsum_out = R.alloc_chsum(L.cout);
   DD_TRY(R.conv(c));
   // out_layers: GN32 (FiLM | +emb) -> SiLU -> conv                       unet.py:245-255
   void* h3 = R.arena.alloc(R.conv_in_bytes(Ho, Wo, L.cout, ctx->esz));
@@ -576,6 +586,7 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   g2.out_zpad = R.zp;
   g2.dt = dt;
   g2.src[0] = h2; g2.C[0] = L.cout;
+  g2.chsum[0] = c.chsum_written ? c.chsum_out : nullptr;
   g2.H = Ho; g2.W = Wo;
   g2.gamma = L.gn2_g; g2.beta = L.gn2_b;
   if (ctx->cfg.use_scale_shift_norm) { g2.film = R.emb_out ? R.emb_out + L.emb_off : nullptr; g2.film_stride = ctx->emb_rows_total; }
@@ -598,7 +609,9 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
     c2.residual = src[0].p;
     c2.res_mode = L.down ? RES_POOL : (L.up ? RES_UP : RES_SAME);
   }
+  c2.chsum_out = out_cs;
   DD_TRY(R.conv(c2));
+  out->chsum = c2.chsum_written ? out_cs : nullptr;
   R.arena.off = mark;
   return DDPM3D_OK;
 }
@@ -753,6 +766,7 @@ int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, cons
   float* hn = (float*)R.arena.alloc(R.conv_in_bytes(H, W, h.C, sizeof(float)));
   GnArgs g{};
   g.out_zpad = R.zp;
+  g.chsum[0] = h.chsum;
   g.dt = dt; g.src[0] = h.p; g.C[0] = h.C; g.H = H; g.W = W; g.gamma = ctx->out_gn_g; g.beta = ctx->out_gn_b; g.silu = 1;
   g.out = hn; g.out_f32 = 1;
   DD_TRY(R.gn(g));
@@ -1236,6 +1250,7 @@ int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value) {
   if (n == "cuda_graph") ctx->use_graph = value != 0;
   else if (n == "conv_path") { DD_CHECK(value >= 0 && value <= 2, DDPM3D_ERR_ARG, "conv_path must be 0, 1 or 2"); ctx->conv_path = (int)value; }
   else if (n == "profile") ctx->profile = value != 0;
+  else if (n == "fuse_stats") ctx->fuse_stats = value != 0;
   else { set_error("unknown option: " + n); return DDPM3D_ERR_ARG; }
   // cached graphs bake the options in
   if (ctx->device >= 0) {

@@ -32,7 +32,13 @@ struct ConvArgs {
   void* out = nullptr;        // dt, channels-last; or fp32 planar NCDHW when out_planar_f32
   int out_planar_f32 = 0;
   int B = 0, Z = 0, Ho = 0, Wo = 0, Cout = 0;  // output geometry; input H/W = Ho*stride
+  // Optional (tcgen05 path only): per-channel [sum, sum of squares] of the OUTPUT, accumulated from the fp32
+  // accumulators in the epilogue, one partial per CTA: chsum_out[B][CHSUM_SLOTS][Cout][2].  The consuming
+  // GroupNorm then skips its statistics pass over the tensor.  chsum_written is set by the launcher.
+  float* chsum_out = nullptr;
+  int chsum_written = 0;
 };
+constexpr int CHSUM_SLOTS = 148;  // one per persistent CTA (unused slots are zeroed by the launcher)
 
 int conv_simt(const ConvArgs& a, cudaStream_t s);
 // thin ends of the network on the CUDA cores with smem-staged halo bricks (conv_small.cu)
@@ -42,7 +48,7 @@ bool conv_head_eligible(const ConvArgs& a);  // Cout <= 2, fp32, planar output
 int conv_head(const ConvArgs& a, cudaStream_t s);
 // tcgen05 path; returns DDPM3D_ERR_ARG (without launching) when the shape is not eligible.
 bool conv_tc_eligible(const ConvArgs& a);
-int conv_tc(const ConvArgs& a, cudaStream_t s);
+int conv_tc(ConvArgs& a, cudaStream_t s);
 
 // ---- GroupNorm32 + FiLM + SiLU (K4/K5/K6) ------------------------------------------------------
 struct GnArgs {
@@ -66,6 +72,9 @@ struct GnArgs {
   const double* gathered = nullptr;
   int world = 1;
   double inv_count_global = 0.0;
+  // per-source channel sums produced by the preceding convolutions' epilogues (see ConvArgs::chsum_out); when
+  // every source has them the statistics pass is skipped
+  const float* chsum[2] = {nullptr, nullptr};
   // scratch (owned by the caller / workspace)
   float* partials = nullptr;                // [B][n_chunks][32][2]
   float* ab = nullptr;                      // [B][2][Ctot]
@@ -76,6 +85,8 @@ int gn_forward(const GnArgs& a, cudaStream_t s, int* launches);
 // split form for the sharded path: stats -> local fp64 sums [B][32][2] -> (all-gather) -> finalize + apply
 int gn_stats_local(const GnArgs& a, double* sums, cudaStream_t s);
 int gn_finalize_apply(const GnArgs& a, cudaStream_t s);
+// statistics from the producers' channel sums: finalize + apply only (one read + one write of the tensor)
+int gn_forward_chsum(const GnArgs& a, cudaStream_t s);
 
 // plain resample (Upsample(use_conv=True) front half, unet.py:100-105)
 int resample_hw(int dt, const void* in, void* out, int B, int Z, int H, int W, int C, int mode, cudaStream_t s);

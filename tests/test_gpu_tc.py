@@ -81,3 +81,20 @@ def test_unet_on_tensor_cores_matches_simt(golden_dir, name, half):
         assert ("conv_tcgen05" in kinds) == (path == 2)
     # two equally valid bf16 evaluations diverge by the bf16 rounding floor of the network (see test_gpu_model.TOL)
     assert max_rel(outs[2], outs[1]) <= TOL[half]
+
+
+def test_fused_groupnorm_statistics_agree_with_the_separate_pass():
+    """GroupNorm statistics taken from the conv epilogue's fp32 accumulators (per-CTA channel sums) vs the
+    separate statistics pass over the stored 16-bit tensor: same network output up to the rounding floor, and
+    bit-identical from run to run (fixed reduction order)."""
+    case = cases.UNET_CASES["wide"]
+    low, x, _ = synth_inputs(case["shape"], 0)
+    outs = {}
+    for fuse in (1, 0):
+        model, _, _, _ = build(case["flags"], seed=case.get("seed", 0), fp16="fp16")
+        model.set_option("fuse_stats", fuse)
+        a = model(x.to(DEV), torch.tensor(case["t"], device=DEV), low_res=low.to(DEV)).cpu()
+        b = model(x.to(DEV), torch.tensor(case["t"], device=DEV), low_res=low.to(DEV)).cpu()
+        assert torch.equal(a, b)
+        outs[fuse] = a
+    assert max_rel(outs[1], outs[0]) <= 3e-3
