@@ -36,7 +36,8 @@ constexpr int BK = 64;       // channels per k-step (128 bytes of bf16 = one swi
 constexpr int UMMA_K = 16;
 constexpr int NTHREADS = 192;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
-constexpr int CS_SMEM_MAX = 32 * 1024;  // channel-sum accumulators: 4 warps x B x Cout x 2 floats
+constexpr int CS_TR_BYTES = 4 * 32 * 33 * 4;  // transpose scratch of the four epilogue warps
+constexpr int CS_SMEM_MAX = CS_TR_BYTES + 16 * 1024;  // + channel-sum accumulators: 4 warps x B x Cout x 2 floats
 
 struct TcParams {
   int nsrc;
@@ -159,6 +160,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+template <typename T>
+__device__ __forceinline__ void add8r(float* v, const uint4& raw) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a, b;
+    unpack2<T>(w[i], a, b);
+    v[2 * i] += a;
+    v[2 * i + 1] += b;
+  }
+}
 template <typename T>
 __device__ __forceinline__ void add8(float* v, const T* p, float scale) {
   const uint4 raw = *reinterpret_cast<const uint4*>(p);
@@ -290,7 +302,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     // ===================================== epilogue ==========================================
     const int sub = warp & 3;  // TMEM sub-partition this warp may read: lanes 32*sub .. 32*sub+31
     const int row = sub * 32 + lane;
-    float* cs_acc = reinterpret_cast<float*>(smem_raw + p.cs_off);  // [4 warps][B][Cout][2], one slot per warp
+    float* cs_tr = reinterpret_cast<float*>(smem_raw + p.cs_off);  // [4 warps][32][33] transpose scratch
+    float* cs_acc = cs_tr + 4 * 32 * 33;                           // [4 warps][B][Cout][2], one slot per warp
     if (p.chsum)
       for (int i = lane; i < p.B * p.Cout * 2; i += 32) cs_acc[(size_t)sub * p.B * p.Cout * 2 + i] = 0.f;
     int acc = 0;
@@ -318,6 +331,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
         tmem_ld32(t_row + (uint32_t)c, r);
+        // issue the residual / bias loads before waiting for the TMEM load so their latencies overlap
+        uint4 rres[4];
+        const bool res1 = valid && (p.res_mode == RES_SAME || p.res_mode == RES_UP);
+        if (res1) {
+          int64_t rrow = vox;
+          if (p.res_mode == RES_UP) rrow = (((int64_t)b * p.Z + z) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2;
+          const uint4* rp = reinterpret_cast<const uint4*>((const T*)p.res + rrow * p.Cout + n0 + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rres[j] = rp[j];
+        }
         tmem_ld_wait();
         float v[32];
         if (valid) {
@@ -330,10 +353,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
             v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
           }
-          if (p.res_mode == RES_SAME) {
-            const T* rp = (const T*)p.res + vox * p.Cout + n0 + c;
+          if (res1) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) add8<T>(v + 8 * j, rp + 8 * j, 1.0f);
+            for (int j = 0; j < 4; ++j) add8r<T>(v + 8 * j, rres[j]);
           } else if (p.res_mode == RES_POOL) {  // residual = AvgPool(1,2,2) of a (2Ho, 2Wo) tensor
             const int Hr = 2 * p.Ho, Wr = 2 * p.Wo;
             const int64_t r0 = (((int64_t)b * p.Z + z) * Hr + 2 * h) * Wr + 2 * w;
@@ -349,12 +371,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += 0.25f * s[j];
-          } else if (p.res_mode == RES_UP) {  // residual = nearest x2 of a (Ho/2, Wo/2) tensor
-            const int Hr = p.Ho / 2, Wr = p.Wo / 2;
-            const int64_t r0 = (((int64_t)b * p.Z + z) * Hr + h / 2) * Wr + w / 2;
-            const T* rp = (const T*)p.res + r0 * p.Cout + n0 + c;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) add8<T>(v + 8 * j, rp + 8 * j, 1.0f);
           }
           T* op = (T*)p.out + vox * p.Cout + n0 + c;
 #pragma unroll
@@ -369,25 +385,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
         if (p.chsum) {
-          // column sums over the warp's 32 rows by a reduce-scatter butterfly (31 shuffles per quantity):
-          // lane L ends up with channel c + L
-          float q2[32];
+          // column sums over the warp's 32 rows through a padded smem transpose (conflict-free both ways):
+          // lane = row writes its 32 values, lane = channel reads its column and adds in row order
+          float* tr = cs_tr + sub * (32 * 33);
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) q2[j] = v[j] * v[j];
+          for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j];
+          __syncwarp();
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
-          for (int half = 16; half >= 1; half >>= 1) {
-            const bool upper = (lane & half) != 0;
-#pragma unroll
-            for (int j = 0; j < half; ++j) {
-              const float send_s = upper ? v[j] : v[j + half], keep_s = upper ? v[j + half] : v[j];
-              const float send_q = upper ? q2[j] : q2[j + half], keep_q = upper ? q2[j + half] : q2[j];
-              v[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, half);
-              q2[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, half);
-            }
+          for (int rr = 0; rr < 32; rr += 2) {
+            const float x0 = tr[rr * 33 + lane], x1 = tr[(rr + 1) * 33 + lane];
+            s0 += x0; q0 = fmaf(x0, x0, q0);
+            s1 += x1; q1 = fmaf(x1, x1, q1);
           }
           float* acc = cs_acc + (((size_t)sub * p.B + b) * p.Cout + n0 + c + lane) * 2;
-          acc[0] += v[0];
-          acc[1] += q2[0];
+          acc[0] += s0 + s1;
+          acc[1] += q0 + q1;
         }
       }
       }  // MT
@@ -509,7 +523,7 @@ int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, 
   size_t smem = stage_smem;
   if (q.chsum) {
     q.cs_off = (uint32_t)stage_smem;
-    smem += (size_t)4 * q.B * q.Cout * 2 * sizeof(float);
+    smem += CS_TR_BYTES + (size_t)4 * q.B * q.Cout * 2 * sizeof(float);
     if (grid < CHSUM_SLOTS)  // slots of CTAs that do not exist must read as zero
       DD_CUDA(cudaMemsetAsync(q.chsum, 0, (size_t)q.B * CHSUM_SLOTS * q.Cout * 2 * sizeof(float), s));
   }
@@ -538,7 +552,7 @@ int conv_tc(ConvArgs& a, cudaStream_t s) {
   DD_CHECK(conv_tc_eligible(a), DDPM3D_ERR_ARG, "conv_tc: shape not eligible");
   TcParams p{};
   a.chsum_written = 0;
-  if (a.chsum_out && (size_t)4 * a.B * a.Cout * 2 * sizeof(float) <= (size_t)CS_SMEM_MAX && sm_count() <= CHSUM_SLOTS) {
+  if (a.chsum_out && CS_TR_BYTES + (size_t)4 * a.B * a.Cout * 2 * sizeof(float) <= (size_t)CS_SMEM_MAX && sm_count() <= CHSUM_SLOTS) {
     p.chsum = a.chsum_out;
     a.chsum_written = 1;
   }

@@ -9,12 +9,17 @@ from ddpm3d_b200 import script_util as su
 
 dev = torch.device("cuda", 0)
 shape = bench.PATCH
-if len(sys.argv) > 1:
-    z, h, w = (int(v) for v in sys.argv[1].split(","))
+opts = [a for a in sys.argv[1:] if "=" in a]
+pos = [a for a in sys.argv[1:] if "=" not in a]
+if pos:
+    z, h, w = (int(v) for v in pos[0].split(","))
     shape = (1, 1, z, h, w)
 model, diffusion = su.sr_create_model_and_diffusion(**bench.C2_FLAGS)
 model.load_state_dict(bench.synth_weights(model._specs))
 model.to(dev); model.convert_to_fp16(); model.eval()
+for o in opts:
+    k, v = o.split("=")
+    model.set_option(k, int(v))
 g = torch.Generator().manual_seed(0)
 x = torch.randn(shape, generator=g).to(dev); low = torch.rand(shape, generator=g).to(dev)
 t = torch.tensor([500.0], device=dev)
