@@ -56,6 +56,9 @@ struct TcParams {
   const void* res;   // T
   int res_mode;
   void* out;         // T
+  int64_t rows;      // B*Z*Ho*Wo
+  int ksplit;        // split-K factor S (1 = off); work item = tile * S + split
+  float* partial;    // split-K: fp32 partial tiles [S][B*Z*Ho*Wo][Cout] (bias / residual are applied by the reduce kernel)
   float* chsum;      // [B][CHSUM_SLOTS][Cout][2] per-CTA channel sums of the output, or NULL
   uint32_t cs_off;   // byte offset of the channel-sum accumulators in dynamic smem
 };
@@ -230,7 +233,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < p.num_tiles * p.ksplit; item += gridDim.x) {
+        const int tile = item / p.ksplit, ks = item - tile * p.ksplit;
+        const int kbeg = (int)((int64_t)ks * p.nk / p.ksplit), kend = (int)((int64_t)(ks + 1) * p.nk / p.ksplit);
         const int nt = tile % p.nNt;
         int m = tile / p.nNt;
         const int wt = m % p.nWt; m /= p.nWt;
@@ -239,7 +244,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int b = m / p.nZt;
         const int w0 = wt * p.bw * (p.pw ? MT : 1), h0 = ht * p.bh * (p.ph ? MT : 1), z0 = zt * p.bz * (p.pz ? MT : 1);
         const int n0 = nt * BN;
-        for (int kk = 0; kk < p.nk; ++kk) {
+        for (int kk = kbeg; kk < kend; ++kk) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_expect_tx(full_bar(stage), MT * p.a_tx_bytes + B_BYTES);
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
@@ -273,11 +278,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < p.num_tiles * p.ksplit; item += gridDim.x) {
+        const int ks = item % p.ksplit;
+        const int kbeg = (int)((int64_t)ks * p.nk / p.ksplit), kend = (int)((int64_t)(ks + 1) * p.nk / p.ksplit);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
-        for (int kk = 0; kk < p.nk; ++kk) {
+        for (int kk = kbeg; kk < kend; ++kk) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
@@ -288,7 +295,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               // advance 16 elements = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-              umma_bf16(d_tmem + (uint32_t)(j * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kk | k) != 0);
+              umma_bf16(d_tmem + (uint32_t)(j * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, ((kk - kbeg) | k) != 0);
             }
           }
           umma_commit(empty_bar(stage));  // slot is free once these MMAs have read it
@@ -308,7 +315,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       for (int i = lane; i < p.B * p.Cout * 2; i += 32) cs_acc[(size_t)sub * p.B * p.Cout * 2 + i] = 0.f;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < p.num_tiles * p.ksplit; item += gridDim.x) {
+      const int tile = item / p.ksplit, ks = item - tile * p.ksplit;
       const int nt = tile % p.nNt;
       int m = tile / p.nNt;
       const int wt = m % p.nWt; m /= p.nWt;
@@ -333,7 +341,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tmem_ld32(t_row + (uint32_t)c, r);
         // issue the residual / bias loads before waiting for the TMEM load so their latencies overlap
         uint4 rres[4];
-        const bool res1 = valid && (p.res_mode == RES_SAME || p.res_mode == RES_UP);
+        const bool res1 = valid && p.ksplit == 1 && (p.res_mode == RES_SAME || p.res_mode == RES_UP);
         if (res1) {
           int64_t rrow = vox;
           if (p.res_mode == RES_UP) rrow = (((int64_t)b * p.Z + z) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2;
@@ -342,6 +350,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           for (int j = 0; j < 4; ++j) rres[j] = rp[j];
         }
         tmem_ld_wait();
+        if (p.ksplit > 1) {  // split-K: raw fp32 partial sums; bias / residual / rounding happen in the reduce kernel
+          if (valid) {
+            float4* pp = reinterpret_cast<float4*>(p.partial + ((size_t)ks * p.rows + vox) * p.Cout + n0 + c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              pp[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                  __uint_as_float(r[4 * j + 3]));
+          }
+          continue;
+        }
         float v[32];
         if (valid) {
           const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c);
@@ -427,6 +445,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// split-K second pass: out = T(sum_s partial[s] + bias (+ residual)), partials added in split order (deterministic)
+template <typename T>
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, int64_t rows, int Cout,
+                                     const float* __restrict__ bias, const T* __restrict__ res, int res_mode, int Z, int Ho,
+                                     int Wo, T* __restrict__ out) {
+  const int nv = Cout / 8;
+  const int64_t total = rows * nv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t vox = i / nv;
+    const int c = (int)(i - vox * nv) * 8;
+    float v[8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + c), b1 = *reinterpret_cast<const float4*>(bias + c + 4);
+      v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
+    }
+    for (int s = 0; s < S; ++s) {
+      const float4* pp = reinterpret_cast<const float4*>(partial + ((size_t)s * rows + vox) * Cout + c);
+      const float4 a0 = pp[0], a1 = pp[1];
+      v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+    }
+    if (res_mode != RES_NONE) {
+      const int w = (int)(vox % Wo);
+      int64_t t = vox / Wo;
+      const int h = (int)(t % Ho);
+      t /= Ho;  // b*Z + z
+      if (res_mode == RES_SAME) {
+        add8<T>(v, res + vox * Cout + c, 1.0f);
+      } else if (res_mode == RES_POOL) {
+        const int Wr = 2 * Wo;
+        const int64_t r0 = (t * (2 * Ho) + 2 * h) * Wr + 2 * w;
+        float sacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        add8<T>(sacc, res + r0 * Cout + c, 1.0f);
+        add8<T>(sacc, res + (r0 + 1) * Cout + c, 1.0f);
+        add8<T>(sacc, res + (r0 + Wr) * Cout + c, 1.0f);
+        add8<T>(sacc, res + (r0 + Wr + 1) * Cout + c, 1.0f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += 0.25f * sacc[j];
+      } else {
+        const int64_t r0 = (t * (Ho / 2) + h / 2) * (Wo / 2) + w / 2;
+        add8<T>(v, res + r0 * Cout + c, 1.0f);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + vox * Cout + c) =
+        make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
   }
 }
 
@@ -518,7 +583,7 @@ int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, 
     DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, MT, BN, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     configured = true;
   }
-  const int grid = std::min(p.num_tiles, sm_count());
+  const int grid = (int)std::min<int64_t>((int64_t)p.num_tiles * p.ksplit, sm_count());
   TcParams q = p;
   size_t smem = stage_smem;
   if (q.chsum) {
@@ -529,10 +594,81 @@ int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, 
   }
   conv_tc_kernel<T, MT, BN, NSTAGE><<<grid, NTHREADS, smem, s>>>(maps[0], maps[1], maps[2], mapW, q);
   DD_CUDA(cudaGetLastError());
+  if (p.ksplit > 1) {
+    const int64_t total = p.rows * (p.Cout / 8);
+    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), sm_count() * 8);
+    splitk_reduce_kernel<T><<<blocks, 256, 0, s>>>(p.partial, p.ksplit, p.rows, p.Cout, p.bias, (const T*)p.res, p.res_mode, p.Z,
+                                                   p.Ho, p.Wo, (T*)p.out);
+    DD_CUDA(cudaGetLastError());
+  }
   return DDPM3D_OK;
 }
 
 }  // namespace
+
+namespace {
+
+struct TcPlan {
+  int bw, bh, bz, pw = 0, ph = 0, pz = 0, nW, nH, nZ, MT = 1, BN = 128, S = 1;
+};
+
+// Tile configuration and split-K factor from a small cost model (cycles per SM).  Bytes pulled through L2 per
+// MMA bound this kernel, so 256 accumulator columns per k-step (two bricks sharing a 128-channel weight tile, or
+// one brick x 256 channels) run at ~full rate while 128x128 / 128x64 tiles run at ~0.55 / 0.4 of it.  Layers with
+// few tiles split K so that every SM gets work; the fp32 partials cost an extra pass that is charged here.
+TcPlan make_plan(const ConvArgs& a, int nk) {
+  TcPlan best{};
+  choose_brick(a.Z, a.Ho, a.Wo, &best.bw, &best.bh, &best.bz);
+  const int nW0 = (int)ceil_div(a.Wo, best.bw), nH0 = (int)ceil_div(a.Ho, best.bh), nZ0 = (int)ceil_div(a.Z, best.bz);
+  best.nW = nW0; best.nH = nH0; best.nZ = nZ0;
+  const int sms = sm_count();
+  const double rows = (double)a.B * a.Z * a.Ho * a.Wo;
+  double best_cost = 1e30;
+  struct Cfg { int MT, BN; double cyc_per_kstep; };
+  const Cfg cfgs[4] = {{2, 128, 512.0}, {1, 256, 512.0}, {1, 128, 256.0 / 0.55}, {1, 64, 128.0 / 0.40}};
+  for (const Cfg& c : cfgs) {
+    if (a.Cout % c.BN != 0) continue;
+    TcPlan t = best;
+    t.MT = c.MT; t.BN = c.BN; t.pw = t.ph = t.pz = 0;
+    t.nW = nW0; t.nH = nH0; t.nZ = nZ0;
+    if (c.MT == 2) {  // pair bricks along the dimension that wastes the least (an even brick count wastes nothing)
+      const int n[3] = {nH0, nZ0, nW0};
+      int bd = -1;
+      double bw_ = 1e9;
+      for (int d = 0; d < 3; ++d) {
+        if (n[d] < 2) continue;
+        const double waste = (double)(2 * ((n[d] + 1) / 2)) / n[d];
+        if (waste < bw_ - 1e-9) { bw_ = waste; bd = d; }
+      }
+      if (bd < 0 || bw_ > 1.13) continue;
+      if (bd == 0) { t.ph = t.bh; t.nH = (nH0 + 1) / 2; }
+      else if (bd == 1) { t.pz = t.bz; t.nZ = (nZ0 + 1) / 2; }
+      else { t.pw = t.bw; t.nW = (nW0 + 1) / 2; }
+    }
+    const int64_t tiles = (int64_t)a.B * t.nW * t.nH * t.nZ * (a.Cout / c.BN);
+    for (int S : {1, 2, 3, 4, 6, 8}) {
+      if (S > 1 && (nk / S < 12 || !a.splitk_allowed)) continue;
+      const int64_t items = tiles * S;
+      const double waves = (double)ceil_div(items, sms);
+      double cost = waves * ((double)nk / S * c.cyc_per_kstep + 7000.0);
+      if (S > 1) cost += 4000.0 + ((S + 1) * 4.0 + 2.0) * rows * a.Cout / (3.0e12 / 1.8e9) / 1.0;  // reduce pass at ~3 TB/s
+      if (cost < best_cost) { best_cost = cost; best = t; best.S = S; }
+    }
+  }
+  return best;
+}
+
+}  // namespace
+
+size_t conv_tc_scratch_bytes(const ConvArgs& a0) {
+  ConvArgs a = a0;
+  a.splitk_allowed = 1;
+  if (!conv_tc_eligible(a)) return 0;
+  int nk = a.taps * (a.main.C / BK);
+  for (int e = 0; e < a.n_extra; ++e) nk += a.extra[e].C / BK;
+  const TcPlan plan = make_plan(a, nk);
+  return plan.S > 1 ? (size_t)plan.S * a.B * a.Z * a.Ho * a.Wo * a.Cout * sizeof(float) : 0;
+}
 
 bool conv_tc_eligible(const ConvArgs& a) {
   if (!is_half_dt(a.dt) || a.out_planar_f32 || a.stride_hw != 1) return false;
@@ -568,36 +704,22 @@ int conv_tc(ConvArgs& a, cudaStream_t s) {
     p.nk += p.chunks[1 + e];
     Ktot += a.extra[e].C;
   }
-  choose_brick(a.Z, a.Ho, a.Wo, &p.bw, &p.bh, &p.bz);
-  int nW = (int)ceil_div(a.Wo, p.bw), nH = (int)ceil_div(a.Ho, p.bh), nZ = (int)ceil_div(a.Z, p.bz);
-  // Tile shape.  Bytes pulled through L2 per MMA are what bounds this kernel, so prefer 256 accumulator
-  // columns per k-step: either one brick x 256 output channels, or two bricks sharing one 128-channel
-  // weight tile.  Small layers keep single bricks so that every SM still gets a tile.
-  int BN = (a.Cout % 128 == 0) ? 128 : 64;
-  int MT = 1;
-  const int64_t bricks = (int64_t)a.B * nW * nH * nZ;
-  if (a.Cout % 256 == 0 && bricks * (a.Cout / 256) >= sm_count()) {
-    BN = 256;
-  } else if (BN == 128 && bricks / 2 * (a.Cout / 128) >= sm_count()) {
-    // pair bricks along the dimension that wastes the least (an even brick count wastes nothing)
-    const int n[3] = {nH, nZ, nW};
-    int best = -1;
-    double best_w = 1e9;
-    for (int d = 0; d < 3; ++d) {
-      if (n[d] < 2) continue;
-      const double waste = (double)(2 * ((n[d] + 1) / 2)) / n[d];
-      if (waste < best_w - 1e-9) { best_w = waste; best = d; }
-    }
-    if (best >= 0 && best_w <= 1.13) {
-      MT = 2;
-      if (best == 0) { p.ph = p.bh; nH = (nH + 1) / 2; }
-      else if (best == 1) { p.pz = p.bz; nZ = (nZ + 1) / 2; }
-      else { p.pw = p.bw; nW = (nW + 1) / 2; }
-    }
-  }
-  p.nWt = nW; p.nHt = nH; p.nZt = nZ;
+  TcPlan plan = make_plan(a, p.nk);
+  p.bw = plan.bw; p.bh = plan.bh; p.bz = plan.bz;
+  p.pw = plan.pw; p.ph = plan.ph; p.pz = plan.pz;
+  p.nWt = plan.nW; p.nHt = plan.nH; p.nZt = plan.nZ;
+  const int BN = plan.BN, MT = plan.MT;
   p.nNt = a.Cout / BN;
   p.num_tiles = a.B * p.nZt * p.nHt * p.nWt * p.nNt;
+  p.rows = (int64_t)a.B * a.Z * a.Ho * a.Wo;
+  p.ksplit = plan.S;
+  if (plan.S > 1) {
+    DD_CHECK(a.splitk_scratch != nullptr && a.splitk_bytes >= (size_t)plan.S * p.rows * a.Cout * sizeof(float), DDPM3D_ERR_STATE,
+             "conv_tc: split-K scratch missing");
+    p.partial = a.splitk_scratch;
+    p.chsum = nullptr;  // GroupNorm falls back to its own statistics pass for split-K layers
+    a.chsum_written = 0;
+  }
   p.B = a.B; p.Z = a.Z; p.Ho = a.Ho; p.Wo = a.Wo; p.Cout = a.Cout;
   p.a_tx_bytes = (uint32_t)(p.bw * p.bh * p.bz * BK * 2);
   p.bias = a.bias;

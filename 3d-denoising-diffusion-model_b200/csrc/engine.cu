@@ -165,7 +165,9 @@ struct ddpm3d_ctx {
   float* d_img = nullptr;
   size_t img_cap = 0;
   // options
-  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1;
+  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1;
+  float* splitk_buf = nullptr;  // fp32 partial tiles of split-K convolutions (sized by the dry run)
+  size_t splitk_cap = 0, splitk_need = 0;
   cudaStream_t cap_stream = nullptr;
   float* d_freqs = nullptr;  // timestep_embedding frequencies computed by the host exactly like nn.py:113-115
   int n_freqs = 0;
@@ -483,12 +485,19 @@ struct Run {
     a.B = B;
     a.Z = Z;
     if (zp || !ctx->fuse_stats) a.chsum_out = nullptr;  // sharded statistics take the all-gather path
+    if (a.taps == 27) a.in_zpad = zp;
+    a.splitk_allowed = ctx->split_k;
     ++launches;
-    if (arena.dry) return DDPM3D_OK;
+    if (arena.dry) {
+      if (is_half_dt(a.dt) && ctx->conv_path != 1 && a.splitk_allowed)
+        ctx->splitk_need = std::max(ctx->splitk_need, conv_tc_scratch_bytes(a));
+      return DDPM3D_OK;
+    }
+    a.splitk_scratch = ctx->splitk_buf;
+    a.splitk_bytes = ctx->splitk_cap;
     double K = (double)a.taps * a.main.C;
     for (int e = 0; e < a.n_extra; ++e) K += a.extra[e].C;
     const double flops = 2.0 * B * Z * a.Ho * a.Wo * (double)a.Cout * K;
-    if (a.taps == 27) a.in_zpad = zp;
     const bool tc = is_half_dt(a.dt) && ctx->conv_path != 1 && conv_tc_eligible(a);
     const bool stem = !tc && ctx->conv_path != 1 && conv_stem_eligible(a);
     const bool head = !tc && ctx->conv_path != 1 && conv_head_eligible(a);
@@ -800,8 +809,20 @@ int64_t dry_bytes(ddpm3d_ctx* ctx, int B, int Z, int H, int W, int* launches) {
 }
 
 int ensure_workspace(ddpm3d_ctx* ctx, int B, int Z, int H, int W) {
+  ctx->splitk_need = 0;
   const int64_t need = dry_bytes(ctx, B, Z, H, W, nullptr);
   if (need < 0) return DDPM3D_ERR_ARG;
+  if (ctx->splitk_need > ctx->splitk_cap) {
+    for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+    ctx->graphs.clear();
+    ctx->graph_launches.clear();
+    DD_CUDA(cudaDeviceSynchronize());
+    if (ctx->splitk_buf) DD_CUDA(cudaFree(ctx->splitk_buf));
+    ctx->splitk_buf = nullptr;
+    ctx->splitk_cap = 0;
+    DD_CUDA(cudaMalloc((void**)&ctx->splitk_buf, ctx->splitk_need));
+    ctx->splitk_cap = ctx->splitk_need;
+  }
   if ((size_t)need > ctx->ws_cap) {
     // graphs captured on the old workspace are stale
     for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
@@ -968,6 +989,7 @@ void ddpm3d_destroy(ddpm3d_ctx* ctx) {
     if (ctx->d_mo) cudaFree(ctx->d_mo);
     if (ctx->d_img) cudaFree(ctx->d_img);
     if (ctx->d_freqs) cudaFree(ctx->d_freqs);
+    if (ctx->splitk_buf) cudaFree(ctx->splitk_buf);
     comm_destroy(&ctx->slab);
     if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
     for (auto& e : ctx->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -1251,6 +1273,7 @@ int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value) {
   else if (n == "conv_path") { DD_CHECK(value >= 0 && value <= 2, DDPM3D_ERR_ARG, "conv_path must be 0, 1 or 2"); ctx->conv_path = (int)value; }
   else if (n == "profile") ctx->profile = value != 0;
   else if (n == "fuse_stats") ctx->fuse_stats = value != 0;
+  else if (n == "split_k") ctx->split_k = value != 0;
   else { set_error("unknown option: " + n); return DDPM3D_ERR_ARG; }
   // cached graphs bake the options in
   if (ctx->device >= 0) {
@@ -1301,6 +1324,14 @@ int ddpm3d_k_conv3d(int dtype, int path, const void* in, const void* w, const fl
   a.out = out; a.B = B; a.Z = Z; a.Ho = H / stride_hw; a.Wo = W / stride_hw; a.Cout = Cout;
   if (path == 2) {
     DD_CHECK(is_half_dt(dtype) && conv_tc_eligible(a), DDPM3D_ERR_ARG, "k_conv3d: shape not eligible for the tcgen05 path");
+    a.splitk_allowed = 1;
+    const size_t need = conv_tc_scratch_bytes(a);
+    if (need) {
+      void* sc = nullptr;
+      DD_TRY(g_scratch.get(need, &sc));
+      a.splitk_scratch = (float*)sc;
+      a.splitk_bytes = need;
+    }
     return conv_tc(a, (cudaStream_t)stream);
   }
   return conv_simt(a, (cudaStream_t)stream);

@@ -37,6 +37,10 @@ struct ConvArgs {
   // GroupNorm then skips its statistics pass over the tensor.  chsum_written is set by the launcher.
   float* chsum_out = nullptr;
   int chsum_written = 0;
+  // split-K scratch for layers with too few tiles to fill the GPU (fp32 partial tiles); see conv_tc_scratch_bytes
+  float* splitk_scratch = nullptr;
+  size_t splitk_bytes = 0;
+  int splitk_allowed = 0;
 };
 constexpr int CHSUM_SLOTS = 148;  // one per persistent CTA (unused slots are zeroed by the launcher)
 
@@ -49,6 +53,7 @@ int conv_head(const ConvArgs& a, cudaStream_t s);
 // tcgen05 path; returns DDPM3D_ERR_ARG (without launching) when the shape is not eligible.
 bool conv_tc_eligible(const ConvArgs& a);
 int conv_tc(ConvArgs& a, cudaStream_t s);
+size_t conv_tc_scratch_bytes(const ConvArgs& a);  // split-K scratch this launch wants (0 = no split)
 
 // ---- GroupNorm32 + FiLM + SiLU (K4/K5/K6) ------------------------------------------------------
 struct GnArgs {

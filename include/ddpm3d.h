@@ -183,7 +183,9 @@ int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total);
  * "conv_path" (0 = auto, 1 = force the generic CUDA-core kernel everywhere, 2 = same as 0);
  * "profile" (0/1): record a CUDA-event pair around every kernel launch (disables graphs);
  * "fuse_stats" (0/1, default 1): GroupNorm statistics come from per-channel sums accumulated in the producing
- * convolution's epilogue instead of a separate pass over the tensor. */
+ * convolution's epilogue instead of a separate pass over the tensor;
+ * "split_k" (0/1, default 1): convolutions with too few tiles to fill the GPU split K over CTAs (fp32 partials,
+ * deterministic second pass). */
 int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value);
 /* Kernel launches enqueued by this ctx since creation. */
 int64_t ddpm3d_launch_count(const ddpm3d_ctx* ctx);

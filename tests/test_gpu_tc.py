@@ -30,7 +30,9 @@ from test_gpu_model import TOL, build  # noqa: E402
     (128, 128, (1, 24, 96, 96), 27, True),   # two bricks per CTA sharing the weight tile (MT = 2), paired along h
     (256, 256, (1, 48, 24, 24), 27, True),   # BN = 256
     (256, 128, (1, 21, 48, 48), 27, False),  # MT = 2 with an odd brick count (edge brick fully out of bounds)
-    (512, 512, (1, 96, 6, 6), 27, False),    # small-M layer keeps single bricks
+    (512, 512, (1, 96, 6, 6), 27, False),    # small-M layer: split-K (fp32 partials + reduce pass)
+    (384, 384, (1, 96, 12, 12), 27, True),   # split-K with a residual applied in the reduce pass
+    (768, 384, (1, 24, 12, 12), 27, False),  # long K (324 k-steps), few tiles
 ])
 @pytest.mark.parametrize("dt", [N.BF16, N.FP16])
 def test_conv3d_tcgen05(Cin, Cout, shape, taps, res, dt):
