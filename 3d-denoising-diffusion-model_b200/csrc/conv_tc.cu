@@ -56,9 +56,13 @@ struct TcParams {
   const void* res;   // T
   int res_mode;
   void* out;         // T
-  int64_t rows;      // B*Z*Ho*Wo
-  int ksplit;        // split-K factor S (1 = off); work item = tile * S + split
-  float* partial;    // split-K: fp32 partial tiles [S][B*Z*Ho*Wo][Cout] (bias / residual are applied by the reduce kernel)
+  // stream-K (layers with too few tiles to fill the GPU): the num_tiles * nk k-steps are dealt evenly to the CTAs;
+  // a CTA that owns only part of a tile's K range writes its fp32 accumulators to
+  // partial[tile][slot][MT*128][BN] (slot = position among the tile's contributors) and a fix-up kernel adds
+  // the slots in order and applies bias / residual.  Tiles owned by one CTA take the normal epilogue.
+  int sk;
+  int max_slots;
+  float* partial;
   float* chsum;      // [B][CHSUM_SLOTS][Cout][2] per-CTA channel sums of the output, or NULL
   uint32_t cs_off;   // byte offset of the channel-sum accumulators in dynamic smem
 };
@@ -187,6 +191,33 @@ __device__ __forceinline__ void add8(float* v, const T* p, float scale) {
   }
 }
 
+// the sequence of (tile, k-range) segments of one CTA; identical in the three warp roles
+struct WorkIter {
+  int sk, nk, num_tiles, cur;
+  int64_t kpos, kend;
+  __device__ explicit WorkIter(const TcParams& p) : sk(p.sk), nk(p.nk), num_tiles(p.num_tiles), cur(blockIdx.x) {
+    const int64_t T = (int64_t)p.num_tiles * p.nk;
+    kpos = (int64_t)blockIdx.x * T / gridDim.x;
+    kend = (int64_t)(blockIdx.x + 1) * T / gridDim.x;
+  }
+  __device__ bool next(int& tile, int& k0, int& k1) {
+    if (!sk) {
+      if (cur >= num_tiles) return false;
+      tile = cur; k0 = 0; k1 = nk;
+      cur += gridDim.x;
+      return true;
+    }
+    if (kpos >= kend) return false;
+    tile = (int)(kpos / nk);
+    k0 = (int)(kpos - (int64_t)tile * nk);
+    k1 = (int)min((int64_t)nk, k0 + (kend - kpos));
+    kpos += k1 - k0;
+    return true;
+  }
+};
+// first CTA whose k-range touches k-step x (ranges are [c*T/G, (c+1)*T/G))
+__host__ __device__ inline int sk_owner(int64_t x, int64_t T, int G) { return (int)(((x + 1) * G - 1) / T); }
+
 template <typename T, int MT, int BN, int NSTAGE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -233,9 +264,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.num_tiles * p.ksplit; item += gridDim.x) {
-        const int tile = item / p.ksplit, ks = item - tile * p.ksplit;
-        const int kbeg = (int)((int64_t)ks * p.nk / p.ksplit), kend = (int)((int64_t)(ks + 1) * p.nk / p.ksplit);
+      WorkIter it(p);
+      int tile, kbeg, kend;
+      while (it.next(tile, kbeg, kend)) {
         const int nt = tile % p.nNt;
         int m = tile / p.nNt;
         const int wt = m % p.nWt; m /= p.nWt;
@@ -278,9 +309,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < p.num_tiles * p.ksplit; item += gridDim.x) {
-        const int ks = item % p.ksplit;
-        const int kbeg = (int)((int64_t)ks * p.nk / p.ksplit), kend = (int)((int64_t)(ks + 1) * p.nk / p.ksplit);
+      WorkIter it(p);
+      int tile, kbeg, kend;
+      while (it.next(tile, kbeg, kend)) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
@@ -315,8 +346,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       for (int i = lane; i < p.B * p.Cout * 2; i += 32) cs_acc[(size_t)sub * p.B * p.Cout * 2 + i] = 0.f;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < p.num_tiles * p.ksplit; item += gridDim.x) {
-      const int tile = item / p.ksplit, ks = item - tile * p.ksplit;
+    WorkIter it(p);
+    int tile, kbeg, kend;
+    while (it.next(tile, kbeg, kend)) {
+      const bool part = kbeg != 0 || kend != p.nk;  // stream-K: this CTA owns only a piece of the tile's K range
+      int slot = 0;
+      if (part) slot = (int)blockIdx.x - sk_owner((int64_t)tile * p.nk, (int64_t)p.num_tiles * p.nk, (int)gridDim.x);
       const int nt = tile % p.nNt;
       int m = tile / p.nNt;
       const int wt = m % p.nWt; m /= p.nWt;
@@ -341,7 +376,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tmem_ld32(t_row + (uint32_t)c, r);
         // issue the residual / bias loads before waiting for the TMEM load so their latencies overlap
         uint4 rres[4];
-        const bool res1 = valid && p.ksplit == 1 && (p.res_mode == RES_SAME || p.res_mode == RES_UP);
+        const bool res1 = valid && !part && (p.res_mode == RES_SAME || p.res_mode == RES_UP);
         if (res1) {
           int64_t rrow = vox;
           if (p.res_mode == RES_UP) rrow = (((int64_t)b * p.Z + z) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2;
@@ -350,9 +385,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           for (int j = 0; j < 4; ++j) rres[j] = rp[j];
         }
         tmem_ld_wait();
-        if (p.ksplit > 1) {  // split-K: raw fp32 partial sums; bias / residual / rounding happen in the reduce kernel
-          if (valid) {
-            float4* pp = reinterpret_cast<float4*>(p.partial + ((size_t)ks * p.rows + vox) * p.Cout + n0 + c);
+        if (part) {  // raw fp32 partial sums; bias / residual / rounding happen in the fix-up kernel
+          {
+            float4* pp = reinterpret_cast<float4*>(
+                p.partial + ((((size_t)tile * p.max_slots + slot) * MT + mt) * 128 + row) * BN + c);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               pp[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
@@ -448,49 +484,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   }
 }
 
-// split-K second pass: out = T(sum_s partial[s] + bias (+ residual)), partials added in split order (deterministic)
-template <typename T>
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, int64_t rows, int Cout,
-                                     const float* __restrict__ bias, const T* __restrict__ res, int res_mode, int Z, int Ho,
-                                     int Wo, T* __restrict__ out) {
-  const int nv = Cout / 8;
-  const int64_t total = rows * nv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t vox = i / nv;
-    const int c = (int)(i - vox * nv) * 8;
+// stream-K fix-up: for every tile whose K range was shared by several CTAs, add their fp32 partials in slot
+// order (deterministic), apply bias / residual and store.  One block per tile.
+template <typename T, int MT, int BN>
+__global__ void __launch_bounds__(256) sk_fixup_kernel(const TcParams p, int G) {
+  const int tile = blockIdx.x;
+  const int64_t Ttot = (int64_t)p.num_tiles * p.nk;
+  const int c_first = sk_owner((int64_t)tile * p.nk, Ttot, G), c_last = sk_owner((int64_t)(tile + 1) * p.nk - 1, Ttot, G);
+  const int nslots = c_last - c_first + 1;
+  if (nslots <= 1) return;  // the tile was completed by one CTA's normal epilogue
+  const int nt = tile % p.nNt;
+  int m = tile / p.nNt;
+  const int wt = m % p.nWt; m /= p.nWt;
+  const int ht = m % p.nHt; m /= p.nHt;
+  const int zt = m % p.nZt;
+  const int b = m / p.nZt;
+  const int n0 = nt * BN;
+  constexpr int NV = BN / 8;
+  const float* base = p.partial + (size_t)tile * p.max_slots * MT * 128 * BN;
+  for (int i = threadIdx.x; i < MT * 128 * NV; i += blockDim.x) {
+    const int rowt = i / NV, c = (i - rowt * NV) * 8;
+    const int mt = rowt / 128, row = rowt - mt * 128;
+    const int rw = row % p.bw, rh = (row / p.bw) % p.bh, rz = row / (p.bw * p.bh);
+    const int w = wt * p.bw * (p.pw ? MT : 1) + mt * p.pw + rw, h = ht * p.bh * (p.ph ? MT : 1) + mt * p.ph + rh,
+              z = zt * p.bz * (p.pz ? MT : 1) + mt * p.pz + rz;
+    if (!(rz < p.bz && w < p.Wo && h < p.Ho && z < p.Z)) continue;
+    const int64_t vox = (((int64_t)b * p.Z + z) * p.Ho + h) * p.Wo + w;
     float v[8];
     {
-      const float4 b0 = *reinterpret_cast<const float4*>(bias + c), b1 = *reinterpret_cast<const float4*>(bias + c + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n0 + c), b1 = *reinterpret_cast<const float4*>(p.bias + n0 + c + 4);
       v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
     }
-    for (int s = 0; s < S; ++s) {
-      const float4* pp = reinterpret_cast<const float4*>(partial + ((size_t)s * rows + vox) * Cout + c);
+    for (int sidx = 0; sidx < nslots; ++sidx) {
+      const float4* pp = reinterpret_cast<const float4*>(base + ((size_t)sidx * MT * 128 + rowt) * BN + c);
       const float4 a0 = pp[0], a1 = pp[1];
       v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
     }
-    if (res_mode != RES_NONE) {
-      const int w = (int)(vox % Wo);
-      int64_t t = vox / Wo;
-      const int h = (int)(t % Ho);
-      t /= Ho;  // b*Z + z
-      if (res_mode == RES_SAME) {
-        add8<T>(v, res + vox * Cout + c, 1.0f);
-      } else if (res_mode == RES_POOL) {
-        const int Wr = 2 * Wo;
-        const int64_t r0 = (t * (2 * Ho) + 2 * h) * Wr + 2 * w;
-        float sacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        add8<T>(sacc, res + r0 * Cout + c, 1.0f);
-        add8<T>(sacc, res + (r0 + 1) * Cout + c, 1.0f);
-        add8<T>(sacc, res + (r0 + Wr) * Cout + c, 1.0f);
-        add8<T>(sacc, res + (r0 + Wr + 1) * Cout + c, 1.0f);
+    const T* res = (const T*)p.res;
+    if (p.res_mode == RES_SAME) {
+      add8<T>(v, res + vox * p.Cout + n0 + c, 1.0f);
+    } else if (p.res_mode == RES_POOL) {
+      const int Wr = 2 * p.Wo;
+      const int64_t r0 = (((int64_t)b * p.Z + z) * (2 * p.Ho) + 2 * h) * Wr + 2 * w;
+      float sacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      add8<T>(sacc, res + r0 * p.Cout + n0 + c, 1.0f);
+      add8<T>(sacc, res + (r0 + 1) * p.Cout + n0 + c, 1.0f);
+      add8<T>(sacc, res + (r0 + Wr) * p.Cout + n0 + c, 1.0f);
+      add8<T>(sacc, res + (r0 + Wr + 1) * p.Cout + n0 + c, 1.0f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += 0.25f * sacc[j];
-      } else {
-        const int64_t r0 = (t * (Ho / 2) + h / 2) * (Wo / 2) + w / 2;
-        add8<T>(v, res + r0 * Cout + c, 1.0f);
-      }
+      for (int j = 0; j < 8; ++j) v[j] += 0.25f * sacc[j];
+    } else if (p.res_mode == RES_UP) {
+      const int64_t r0 = (((int64_t)b * p.Z + z) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2;
+      add8<T>(v, res + r0 * p.Cout + n0 + c, 1.0f);
     }
-    *reinterpret_cast<uint4*>(out + vox * Cout + c) =
+    *reinterpret_cast<uint4*>((T*)p.out + vox * p.Cout + n0 + c) =
         make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
   }
 }
@@ -583,7 +630,7 @@ int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, 
     DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, MT, BN, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     configured = true;
   }
-  const int grid = (int)std::min<int64_t>((int64_t)p.num_tiles * p.ksplit, sm_count());
+  const int grid = p.sk ? sm_count() : std::min(p.num_tiles, sm_count());
   TcParams q = p;
   size_t smem = stage_smem;
   if (q.chsum) {
@@ -594,11 +641,8 @@ int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, 
   }
   conv_tc_kernel<T, MT, BN, NSTAGE><<<grid, NTHREADS, smem, s>>>(maps[0], maps[1], maps[2], mapW, q);
   DD_CUDA(cudaGetLastError());
-  if (p.ksplit > 1) {
-    const int64_t total = p.rows * (p.Cout / 8);
-    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), sm_count() * 8);
-    splitk_reduce_kernel<T><<<blocks, 256, 0, s>>>(p.partial, p.ksplit, p.rows, p.Cout, p.bias, (const T*)p.res, p.res_mode, p.Z,
-                                                   p.Ho, p.Wo, (T*)p.out);
+  if (p.sk) {
+    sk_fixup_kernel<T, MT, BN><<<p.num_tiles, 256, 0, s>>>(p, grid);
     DD_CUDA(cudaGetLastError());
   }
   return DDPM3D_OK;
@@ -609,7 +653,7 @@ int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, 
 namespace {
 
 struct TcPlan {
-  int bw, bh, bz, pw = 0, ph = 0, pz = 0, nW, nH, nZ, MT = 1, BN = 128, S = 1;
+  int bw, bh, bz, pw = 0, ph = 0, pz = 0, nW, nH, nZ, MT = 1, BN = 128, S = 1 /* 2 = stream-K */, max_slots = 0;
 };
 
 // Tile configuration and split-K factor from a small cost model (cycles per SM).  Bytes pulled through L2 per
@@ -646,13 +690,22 @@ TcPlan make_plan(const ConvArgs& a, int nk) {
       else { t.pw = t.bw; t.nW = (nW0 + 1) / 2; }
     }
     const int64_t tiles = (int64_t)a.B * t.nW * t.nH * t.nZ * (a.Cout / c.BN);
-    for (int S : {1, 2, 3, 4, 6, 8}) {
-      if (S > 1 && (nk / S < 12 || !a.splitk_allowed)) continue;
-      const int64_t items = tiles * S;
-      const double waves = (double)ceil_div(items, sms);
-      double cost = waves * ((double)nk / S * c.cyc_per_kstep + 7000.0);
-      if (S > 1) cost += 4000.0 + ((S + 1) * 4.0 + 2.0) * rows * a.Cout / (3.0e12 / 1.8e9) / 1.0;  // reduce pass at ~3 TB/s
-      if (cost < best_cost) { best_cost = cost; best = t; best.S = S; }
+    // whole tiles, wave-quantised
+    {
+      const double cost = (double)ceil_div(tiles, sms) * ((double)nk * c.cyc_per_kstep + 7000.0);
+      if (cost < best_cost) { best_cost = cost; best = t; best.S = 1; best.max_slots = 0; }
+    }
+    // stream-K: an even share of all k-steps per CTA + the fix-up pass over the shared tiles (~2 per CTA)
+    const int64_t T = tiles * nk;
+    if (a.splitk_allowed && tiles < 4 * (int64_t)sms && T / sms >= 24) {
+      const double share = (double)T / sms;
+      const double tile_bytes = (double)c.MT * 128 * c.BN * 4;
+      const double fix = 5000.0 + 2.0 * sms * tile_bytes * 2.0 / 2200.0;  // written + read, ~4 TB/s at 1.8 GHz
+      const double cost = share * c.cyc_per_kstep + 9000.0 + fix;
+      if (cost < best_cost) {
+        best_cost = cost; best = t; best.S = 2;
+        best.max_slots = (int)(nk / (T / sms)) + 2;
+      }
     }
   }
   return best;
@@ -667,7 +720,9 @@ size_t conv_tc_scratch_bytes(const ConvArgs& a0) {
   int nk = a.taps * (a.main.C / BK);
   for (int e = 0; e < a.n_extra; ++e) nk += a.extra[e].C / BK;
   const TcPlan plan = make_plan(a, nk);
-  return plan.S > 1 ? (size_t)plan.S * a.B * a.Z * a.Ho * a.Wo * a.Cout * sizeof(float) : 0;
+  if (plan.S == 1) return 0;
+  const size_t tiles = (size_t)a.B * plan.nW * plan.nH * plan.nZ * (a.Cout / plan.BN);
+  return tiles * plan.max_slots * plan.MT * 128 * plan.BN * sizeof(float);
 }
 
 bool conv_tc_eligible(const ConvArgs& a) {
@@ -711,11 +766,12 @@ int conv_tc(ConvArgs& a, cudaStream_t s) {
   const int BN = plan.BN, MT = plan.MT;
   p.nNt = a.Cout / BN;
   p.num_tiles = a.B * p.nZt * p.nHt * p.nWt * p.nNt;
-  p.rows = (int64_t)a.B * a.Z * a.Ho * a.Wo;
-  p.ksplit = plan.S;
-  if (plan.S > 1) {
-    DD_CHECK(a.splitk_scratch != nullptr && a.splitk_bytes >= (size_t)plan.S * p.rows * a.Cout * sizeof(float), DDPM3D_ERR_STATE,
-             "conv_tc: split-K scratch missing");
+  p.sk = plan.S > 1;
+  p.max_slots = plan.max_slots;
+  if (p.sk) {
+    DD_CHECK(a.splitk_scratch != nullptr &&
+                 a.splitk_bytes >= (size_t)p.num_tiles * plan.max_slots * MT * 128 * BN * sizeof(float),
+             DDPM3D_ERR_STATE, "conv_tc: stream-K scratch missing");
     p.partial = a.splitk_scratch;
     p.chsum = nullptr;  // GroupNorm falls back to its own statistics pass for split-K layers
     a.chsum_written = 0;
