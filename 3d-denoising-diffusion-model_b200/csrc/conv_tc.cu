@@ -121,6 +121,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// one half of the weight tile, delivered to the same smem offset of every CTA in ctaMask (each destination's
+// mbarrier at the same offset receives the complete_tx)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -152,6 +169,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -192,19 +214,28 @@ __device__ __forceinline__ void add8(float* v, const T* p, float scale) {
 }
 
 // the sequence of (tile, k-range) segments of one CTA; identical in the three warp roles
+// With CL == 2 the two CTAs of a cluster walk the same sequence of super-tiles in lock step: both take the same
+// output-channel tile (so the weight tile is fetched once and multicast) and adjacent M tiles; `tile` may be a
+// dummy (>= num_tiles) for the odd one out, which loads zeros and stores nothing.
 struct WorkIter {
-  int sk, nk, num_tiles, cur;
+  int sk, nk, num_tiles, nNt, cur, step, cl, crank;
   int64_t kpos, kend;
-  __device__ explicit WorkIter(const TcParams& p) : sk(p.sk), nk(p.nk), num_tiles(p.num_tiles), cur(blockIdx.x) {
+  __device__ WorkIter(const TcParams& p, int CL, int rank)
+      : sk(p.sk), nk(p.nk), num_tiles(p.num_tiles), nNt(p.nNt), cur(blockIdx.x / CL), step(gridDim.x / CL), cl(CL), crank(rank) {
     const int64_t T = (int64_t)p.num_tiles * p.nk;
     kpos = (int64_t)blockIdx.x * T / gridDim.x;
     kend = (int64_t)(blockIdx.x + 1) * T / gridDim.x;
   }
   __device__ bool next(int& tile, int& k0, int& k1) {
     if (!sk) {
-      if (cur >= num_tiles) return false;
-      tile = cur; k0 = 0; k1 = nk;
-      cur += gridDim.x;
+      const int numM = num_tiles / nNt;
+      const int n_super = ((numM + cl - 1) / cl) * nNt;
+      if (cur >= n_super) return false;
+      const int mp = cur / nNt, nt = cur - mp * nNt;
+      const int m = mp * cl + crank;
+      tile = m < numM ? m * nNt + nt : num_tiles + nt;  // dummy keeps the right n-tile for the weight multicast
+      k0 = 0; k1 = nk;
+      cur += step;
       return true;
     }
     if (kpos >= kend) return false;
@@ -218,7 +249,7 @@ struct WorkIter {
 // first CTA whose k-range touches k-step x (ranges are [c*T/G, (c+1)*T/G))
 __host__ __device__ inline int sk_owner(int64_t x, int64_t T, int G) { return (int)(((x + 1) * G - 1) / T); }
 
-template <typename T, int MT, int BN, int NSTAGE>
+template <typename T, int MT, int BN, int NSTAGE, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
@@ -244,7 +275,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     prefetch_tmap(&mapW);
     if (p.nsrc > 1) prefetch_tmap(&mapA1);
     if (p.nsrc > 2) prefetch_tmap(&mapA2);
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    // a stage is refilled by this CTA's producer AND (weight half) by the peer's: it is free only when the MMA
+    // warps of all CL CTAs have consumed it
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     fence_barrier_init();
   }
@@ -258,13 +291,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before any multicast can signal them
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      WorkIter it(p);
+      WorkIter it(p, CL, crank);
       int tile, kbeg, kend;
       while (it.next(tile, kbeg, kend)) {
         const int nt = tile % p.nNt;
@@ -272,7 +307,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int wt = m % p.nWt; m /= p.nWt;
         const int ht = m % p.nHt; m /= p.nHt;
         const int zt = m % p.nZt;
-        const int b = m / p.nZt;
+        const int b = m / p.nZt;  // == p.B for a dummy tile: every box is out of bounds and arrives as zeros
         const int w0 = wt * p.bw * (p.pw ? MT : 1), h0 = ht * p.bh * (p.ph ? MT : 1), z0 = zt * p.bz * (p.pz ? MT : 1);
         const int n0 = nt * BN;
         for (int kk = kbeg; kk < kend; ++kk) {
@@ -296,7 +331,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           for (int j = 0; j < MT; ++j)
             tma_load_5d(a_dst + j * A_BYTES, map, full_bar(stage), c0, w0 + j * p.pw + dw, h0 + j * p.ph + dh,
                         z0 + j * p.pz + dz, b);
-          tma_load_2d(b_dst, &mapW, full_bar(stage), kk * BK, n0);
+          if (CL == 1) {
+            tma_load_2d(b_dst, &mapW, full_bar(stage), kk * BK, n0);
+          } else {  // this CTA fetches its half of the weight tile for the whole cluster
+            constexpr int HALF = BN / CL;
+            tma_load_2d_mc(b_dst + crank * HALF * BK * 2, &mapW, full_bar(stage), kk * BK, n0 + crank * HALF,
+                           (uint16_t)((1u << CL) - 1));
+          }
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
@@ -309,7 +350,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      WorkIter it(p);
+      WorkIter it(p, CL, crank);
       int tile, kbeg, kend;
       while (it.next(tile, kbeg, kend)) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
@@ -329,7 +370,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               umma_bf16(d_tmem + (uint32_t)(j * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, ((kk - kbeg) | k) != 0);
             }
           }
-          umma_commit(empty_bar(stage));  // slot is free once these MMAs have read it
+          // slot is free once these MMAs have read it (told to every CTA whose producer writes into it)
+          if (CL == 1) umma_commit(empty_bar(stage));
+          else umma_commit_mc(empty_bar(stage), (uint16_t)((1u << CL) - 1));
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull_bar(acc));  // accumulator complete
@@ -346,7 +389,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       for (int i = lane; i < p.B * p.Cout * 2; i += 32) cs_acc[(size_t)sub * p.B * p.Cout * 2 + i] = 0.f;
     int acc = 0;
     uint32_t acc_phase = 0;
-    WorkIter it(p);
+    WorkIter it(p, CL, crank);
     int tile, kbeg, kend;
     while (it.next(tile, kbeg, kend)) {
       const bool part = kbeg != 0 || kend != p.nk;  // stream-K: this CTA owns only a piece of the tile's K range
@@ -367,7 +410,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       for (int mt = 0; mt < MT; ++mt) {
       const int w = wt * p.bw * (p.pw ? MT : 1) + mt * p.pw + rw, h = ht * p.bh * (p.ph ? MT : 1) + mt * p.ph + rh,
                 z = zt * p.bz * (p.pz ? MT : 1) + mt * p.pz + rz;
-      const bool valid = rz < p.bz && w < p.Wo && h < p.Ho && z < p.Z;
+      const bool valid = tile < p.num_tiles && rz < p.bz && w < p.Wo && h < p.Ho && z < p.Z;
       const int64_t vox = (((int64_t)b * p.Z + z) * p.Ho + h) * p.Wo + w;
       const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * ACC_COLS + mt * BN);
 #pragma unroll 1
@@ -453,7 +496,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             s0 += x0; q0 = fmaf(x0, x0, q0);
             s1 += x1; q1 = fmaf(x1, x1, q1);
           }
-          float* acc = cs_acc + (((size_t)sub * p.B + b) * p.Cout + n0 + c + lane) * 2;
+          float* acc = cs_acc + (((size_t)sub * p.B + (b < p.B ? b : 0)) * p.Cout + n0 + c + lane) * 2;
           acc[0] += s0 + s1;
           acc[1] += q0 + q1;
         }
@@ -478,6 +521,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   // ---- teardown ---------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer may still multicast into this CTA's smem / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
@@ -620,17 +664,24 @@ int sm_count() {
   return n;
 }
 
-template <typename T, int MT, int BN, int NSTAGE>
-int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s) {
+template <typename T, int MT, int BN, int NSTAGE, int CL>
+int launch_cl(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s) {
   constexpr size_t stage_smem = (size_t)NSTAGE * (MT * A_BYTES + BN * BK * 2) + 1024;
   constexpr size_t smem_max = stage_smem + CS_SMEM_MAX;
   static_assert(smem_max <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, MT, BN, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, MT, BN, NSTAGE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     configured = true;
   }
-  const int grid = p.sk ? sm_count() : std::min(p.num_tiles, sm_count());
+  int grid;
+  if (p.sk) {
+    grid = sm_count();
+  } else {
+    const int numM = p.num_tiles / p.nNt;
+    const int n_super = (int)ceil_div(numM, CL) * p.nNt;
+    grid = std::min(n_super * CL, (sm_count() / CL) * CL);
+  }
   TcParams q = p;
   size_t smem = stage_smem;
   if (q.chsum) {
@@ -639,13 +690,31 @@ int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, 
     if (grid < CHSUM_SLOTS)  // slots of CTAs that do not exist must read as zero
       DD_CUDA(cudaMemsetAsync(q.chsum, 0, (size_t)q.B * CHSUM_SLOTS * q.Cout * 2 * sizeof(float), s));
   }
-  conv_tc_kernel<T, MT, BN, NSTAGE><<<grid, NTHREADS, smem, s>>>(maps[0], maps[1], maps[2], mapW, q);
-  DD_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<T, MT, BN, NSTAGE, CL>, maps[0], maps[1], maps[2], mapW, q));
   if (p.sk) {
     sk_fixup_kernel<T, MT, BN><<<p.num_tiles, 256, 0, s>>>(p, grid);
     DD_CUDA(cudaGetLastError());
   }
   return DDPM3D_OK;
+}
+
+// stream-K ranges differ per CTA, so those launches cannot share weight tiles (CL = 1)
+template <typename T, int MT, int BN, int NSTAGE>
+int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s, int cl) {
+  if (cl == 2) return launch_cl<T, MT, BN, NSTAGE, 2>(maps, mapW, p, s);
+  return launch_cl<T, MT, BN, NSTAGE, 1>(maps, mapW, p, s);
 }
 
 }  // namespace
@@ -791,17 +860,18 @@ int conv_tc(ConvArgs& a, cudaStream_t s) {
   for (int e = 0; e < a.n_extra; ++e)
     DD_TRY(make_act_map(&maps[1 + e], tdt, a.extra[e].ptr, a.B, a.Z, a.Ho, a.Wo, a.extra[e].C, p.bw, p.bh, p.bz));
   CUtensorMap mapW;
-  DD_TRY(make_w_map(&mapW, tdt, a.w, a.Cout, Ktot, BN));
+  const int cl = (!p.sk && a.cluster_allowed && p.num_tiles / p.nNt >= 2 * sm_count()) ? 2 : 1;
+  DD_TRY(make_w_map(&mapW, tdt, a.w, a.Cout, Ktot, BN / cl));
   if (a.dt == DDPM3D_BF16) {
-    if (MT == 2) return launch<bf16, 2, 128, 4>(maps, mapW, p, s);
-    if (BN == 256) return launch<bf16, 1, 256, 4>(maps, mapW, p, s);
-    if (BN == 128) return launch<bf16, 1, 128, 6>(maps, mapW, p, s);
-    return launch<bf16, 1, 64, 8>(maps, mapW, p, s);
+    if (MT == 2) return launch<bf16, 2, 128, 4>(maps, mapW, p, s, cl);
+    if (BN == 256) return launch<bf16, 1, 256, 4>(maps, mapW, p, s, cl);
+    if (BN == 128) return launch<bf16, 1, 128, 6>(maps, mapW, p, s, cl);
+    return launch<bf16, 1, 64, 8>(maps, mapW, p, s, cl);
   }
-  if (MT == 2) return launch<f16, 2, 128, 4>(maps, mapW, p, s);
-  if (BN == 256) return launch<f16, 1, 256, 4>(maps, mapW, p, s);
-  if (BN == 128) return launch<f16, 1, 128, 6>(maps, mapW, p, s);
-  return launch<f16, 1, 64, 8>(maps, mapW, p, s);
+  if (MT == 2) return launch<f16, 2, 128, 4>(maps, mapW, p, s, cl);
+  if (BN == 256) return launch<f16, 1, 256, 4>(maps, mapW, p, s, cl);
+  if (BN == 128) return launch<f16, 1, 128, 6>(maps, mapW, p, s, cl);
+  return launch<f16, 1, 64, 8>(maps, mapW, p, s, cl);
 }
 
 }  // namespace ddpm3d

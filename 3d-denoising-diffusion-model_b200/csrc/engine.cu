@@ -165,7 +165,7 @@ struct ddpm3d_ctx {
   float* d_img = nullptr;
   size_t img_cap = 0;
   // options
-  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1;
+  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 1;
   float* splitk_buf = nullptr;  // fp32 partial tiles of split-K convolutions (sized by the dry run)
   size_t splitk_cap = 0, splitk_need = 0;
   cudaStream_t cap_stream = nullptr;
@@ -487,6 +487,7 @@ struct Run {
     if (zp || !ctx->fuse_stats) a.chsum_out = nullptr;  // sharded statistics take the all-gather path
     if (a.taps == 27) a.in_zpad = zp;
     a.splitk_allowed = ctx->split_k;
+    a.cluster_allowed = ctx->cluster;
     ++launches;
     if (arena.dry) {
       if (is_half_dt(a.dt) && ctx->conv_path != 1 && a.splitk_allowed)
@@ -1274,6 +1275,7 @@ int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value) {
   else if (n == "profile") ctx->profile = value != 0;
   else if (n == "fuse_stats") ctx->fuse_stats = value != 0;
   else if (n == "split_k") ctx->split_k = value != 0;
+  else if (n == "cluster") ctx->cluster = value != 0;
   else { set_error("unknown option: " + n); return DDPM3D_ERR_ARG; }
   // cached graphs bake the options in
   if (ctx->device >= 0) {
