@@ -518,6 +518,41 @@ int gn_forward_chsum(const GnArgs& a, cudaStream_t s) {
   return gn_apply_any(a, s);
 }
 
+// z-slab sharding with fused statistics: this rank's fp64 group sums [B][32][2] from the conv epilogues' channel sums
+__global__ void __launch_bounds__(128) gn_chsum_local_kernel(const float* __restrict__ cs0, const float* __restrict__ cs1, int C0,
+                                                             int C1, int P, double* __restrict__ sums) {
+  __shared__ double sh[2][128];
+  const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int Ctot = C0 + C1, gpc = Ctot / 32;
+  const int n = P * gpc;
+  double s = 0.0, q = 0.0;
+  for (int i = tid; i < n; i += 128) {
+    const int slot = i / gpc, c = g * gpc + i % gpc;
+    const float* src = c < C0 ? cs0 + (((int64_t)b * P + slot) * C0 + c) * 2 : cs1 + (((int64_t)b * P + slot) * C1 + (c - C0)) * 2;
+    s += (double)src[0];
+    q += (double)src[1];
+  }
+  sh[0][tid] = s;
+  sh[1][tid] = q;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (tid < o) { sh[0][tid] += sh[0][tid + o]; sh[1][tid] += sh[1][tid + o]; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    sums[((int64_t)b * 32 + g) * 2] = sh[0][0];
+    sums[((int64_t)b * 32 + g) * 2 + 1] = sh[1][0];
+  }
+}
+
+int gn_chsum_local(const GnArgs& a, double* sums, cudaStream_t s) {
+  DD_TRY(gn_check(a));
+  DD_CHECK(a.chsum[0] && (a.C[1] == 0 || a.chsum[1]), DDPM3D_ERR_STATE, "groupnorm: channel sums missing");
+  gn_chsum_local_kernel<<<dim3(32, a.B), 128, 0, s>>>(a.chsum[0], a.chsum[1], a.C[0], a.C[1], CHSUM_SLOTS, sums);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
 int gn_stats_local(const GnArgs& a, double* sums, cudaStream_t s) {
   DD_TRY(gn_check(a));
   DD_TRY(gn_stats_any(a, s));

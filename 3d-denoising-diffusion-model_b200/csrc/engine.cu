@@ -165,7 +165,7 @@ struct ddpm3d_ctx {
   float* d_img = nullptr;
   size_t img_cap = 0;
   // options
-  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 1;
+  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0;
   float* splitk_buf = nullptr;  // fp32 partial tiles of split-K convolutions (sized by the dry run)
   size_t splitk_cap = 0, splitk_need = 0;
   cudaStream_t cap_stream = nullptr;
@@ -484,7 +484,7 @@ struct Run {
   int conv(ConvArgs& a) {
     a.B = B;
     a.Z = Z;
-    if (zp || !ctx->fuse_stats) a.chsum_out = nullptr;  // sharded statistics take the all-gather path
+    if (!ctx->fuse_stats) a.chsum_out = nullptr;
     if (a.taps == 27) a.in_zpad = zp;
     a.splitk_allowed = ctx->split_k;
     a.cluster_allowed = ctx->cluster;
@@ -528,13 +528,14 @@ struct Run {
     const double n = (double)B * Z * g.H * g.W * Ctot;
     const double in_b = is_half_dt(g.dt) ? 2 : 4, out_b = (is_half_dt(g.dt) && !g.out_f32) ? 2 : 4;
     const double scale = g.resample == RS_POOL ? 0.25 : (g.resample == RS_UP ? 4.0 : 1.0);
-    const bool fused = !zp && !g.pre_add && g.chsum[0] && (g.C[1] == 0 || g.chsum[1]);
-    prof_begin(4, n * ((fused ? 1 : 2) * in_b + out_b * scale));
+    const bool have_cs = !g.pre_add && g.chsum[0] && (g.C[1] == 0 || g.chsum[1]);
+    const bool fused = !zp && have_cs;
+    prof_begin(4, n * ((have_cs ? 1 : 2) * in_b + out_b * scale));
     int r;
     if (fused) {
       r = gn_forward_chsum(g, s);
     } else if (zp) {  // z-slab sharding: statistics span all ranks (fp64 sums all-gathered, summed in rank order)
-      r = gn_stats_local(g, sums, s);
+      r = have_cs ? gn_chsum_local(g, sums, s) : gn_stats_local(g, sums, s);
       if (r == DDPM3D_OK) r = comm_allgather_f64(ctx->slab, sums, gathered, (size_t)B * 64, s);
       if (r == DDPM3D_OK) {
         g.gathered = gathered;

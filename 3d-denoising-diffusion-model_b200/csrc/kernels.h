@@ -90,6 +90,7 @@ int gn_chunks(int64_t rows_per_batch);      // number of stats chunks per batch 
 int gn_forward(const GnArgs& a, cudaStream_t s, int* launches);
 // split form for the sharded path: stats -> local fp64 sums [B][32][2] -> (all-gather) -> finalize + apply
 int gn_stats_local(const GnArgs& a, double* sums, cudaStream_t s);
+int gn_chsum_local(const GnArgs& a, double* sums, cudaStream_t s);  // same, from the producers' channel sums
 int gn_finalize_apply(const GnArgs& a, cudaStream_t s);
 // statistics from the producers' channel sums: finalize + apply only (one read + one write of the tensor)
 int gn_forward_chsum(const GnArgs& a, cudaStream_t s);
