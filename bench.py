@@ -184,6 +184,8 @@ def run_c4(args, rank, world, dev):
     model.to(dev)
     model.convert_to_fp16()
     model.eval()
+    for o in args.opt:
+        model.set_option(o.split("=")[0], int(o.split("=")[1]))
     bounds = slab.slab_bounds(Z, world)
     z0, z1 = bounds[rank], bounds[rank + 1]
     if world > 1:
@@ -257,6 +259,7 @@ def main():
     ap.add_argument("--conv-path", type=int, default=0, help="0 auto, 1 force SIMT, 2 force tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shape", default="", help="override Z,H,W (debug only; invalidates the metric)")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (ddpm3d_set_option), repeatable")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
                     help="c2 (default, the driver's metric): one 96^3 patch per GPU; c4: ONE 640x192x192 volume "
                          "sharded as z-slabs over the GPUs (strong scaling; extra measurement, BASELINE config 4)")
@@ -295,6 +298,8 @@ def main():
     model.eval()
     if args.conv_path:
         model.set_option("conv_path", args.conv_path)
+    for o in args.opt:
+        model.set_option(o.split("=")[0], int(o.split("=")[1]))
 
     # independent patches per rank (scripts/test.py:235-246): weak scaling, no data-path collective
     g = torch.Generator().manual_seed(1234 + rank)
