@@ -546,7 +546,10 @@ __global__ void __launch_bounds__(256) sk_fixup_kernel(const TcParams p, int G) 
   const int n0 = nt * BN;
   constexpr int NV = BN / 8;
   const float* base = p.partial + (size_t)tile * p.max_slots * MT * 128 * BN;
-  for (int i = threadIdx.x; i < MT * 128 * NV; i += blockDim.x) {
+  // blockIdx.y splits the tile's rows so that a few dozen shared tiles still fill the GPU
+  const int per = (MT * 128 * NV + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int i_end = min(MT * 128 * NV, ((int)blockIdx.y + 1) * per);
+  for (int i = (int)blockIdx.y * per + threadIdx.x; i < i_end; i += blockDim.x) {
     const int rowt = i / NV, c = (i - rowt * NV) * 8;
     const int mt = rowt / 128, row = rowt - mt * 128;
     const int rw = row % p.bw, rh = (row / p.bw) % p.bh, rz = row / (p.bw * p.bh);
@@ -704,7 +707,7 @@ int launch_cl(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& 
   cfg.numAttrs = 1;
   DD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<T, MT, BN, NSTAGE, CL>, maps[0], maps[1], maps[2], mapW, q));
   if (p.sk) {
-    sk_fixup_kernel<T, MT, BN><<<p.num_tiles, 256, 0, s>>>(p, grid);
+    sk_fixup_kernel<T, MT, BN><<<dim3(p.num_tiles, 8), 256, 0, s>>>(p, grid);
     DD_CUDA(cudaGetLastError());
   }
   return DDPM3D_OK;
