@@ -60,6 +60,7 @@ SIGNATURES = {
     "ddpm3d_set_sampler": (_I, [_P, _I, C.c_float]),
     "ddpm3d_p_sample_update": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, C.c_int64, _P]),
     "ddpm3d_p_sample": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P]),
+    "ddpm3d_p_sample_t": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
     "ddpm3d_sample_loop": (_I, [_P, _P, _P, _P, _P, C.c_uint64, _I, _I, _P, _I, _I, _I, _I, _P]),
     "ddpm3d_comm_unique_id": (_I, [_P]),
     "ddpm3d_set_comm": (_I, [_P, _P, _I, _I]),

@@ -893,6 +893,24 @@ int step_set_k(int32_t* counter, float* t_model, const ddpm3d_step_scalars* tabl
   return DDPM3D_OK;
 }
 
+// per-sample step indices given as a device tensor (the public p_sample(model, x, t) signature): no host read-back
+__global__ void step_from_tensor_kernel(const int64_t* __restrict__ t, int32_t* __restrict__ t_index, float* __restrict__ t_model,
+                                        const ddpm3d_step_scalars* __restrict__ table, int B, int T) {
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int64_t i = t[b];
+    i = i < 0 ? 0 : (i >= T ? T - 1 : i);
+    t_index[b] = (int32_t)i;
+    t_model[b] = table[i].model_t;
+  }
+}
+
+int step_from_tensor_k(const int64_t* t, int32_t* t_index, float* t_model, const ddpm3d_step_scalars* table, int B, int T,
+                       cudaStream_t s) {
+  step_from_tensor_kernel<<<1, 32, 0, s>>>(t, t_index, t_model, table, B, T);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
 int step_advance_k(int32_t* counter, float* t_model, const ddpm3d_step_scalars* table, int B, cudaStream_t s) {
   step_advance_kernel<<<1, 32, 0, s>>>(counter, t_model, table, B);
   DD_CUDA(cudaGetLastError());

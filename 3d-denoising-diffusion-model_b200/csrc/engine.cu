@@ -158,6 +158,7 @@ struct ddpm3d_ctx {
   int ddim = 0;
   float eta = 0.f;
   float* d_tmodel = nullptr;
+  int32_t* d_tindex = nullptr;
   int32_t* d_counter = nullptr;
   int loop_B = 0;
   float* d_mo = nullptr;
@@ -905,7 +906,9 @@ int ensure_loop_buffers(ddpm3d_ctx* ctx, int B, int64_t n_vox) {
   if (B > ctx->loop_B) {
     DD_CUDA(cudaDeviceSynchronize());
     if (ctx->d_tmodel) cudaFree(ctx->d_tmodel);
+    if (ctx->d_tindex) cudaFree(ctx->d_tindex);
     DD_CUDA(cudaMalloc((void**)&ctx->d_tmodel, (size_t)B * sizeof(float)));
+    DD_CUDA(cudaMalloc((void**)&ctx->d_tindex, (size_t)B * sizeof(int32_t)));
     ctx->loop_B = B;
   }
   if (!ctx->d_counter) DD_CUDA(cudaMalloc((void**)&ctx->d_counter, 4 * sizeof(int32_t)));
@@ -987,6 +990,7 @@ void ddpm3d_destroy(ddpm3d_ctx* ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->d_table) cudaFree(ctx->d_table);
     if (ctx->d_tmodel) cudaFree(ctx->d_tmodel);
+    if (ctx->d_tindex) cudaFree(ctx->d_tindex);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->d_mo) cudaFree(ctx->d_mo);
     if (ctx->d_img) cudaFree(ctx->d_img);
@@ -1196,6 +1200,37 @@ int ddpm3d_p_sample(ddpm3d_ctx* ctx, const float* x, const float* low_res, const
     a.B = B; a.C = 1; a.n = n; a.T = ctx->T;
     DD_TRY(p_sample_update_k(a, cs));
     *nl += 1;
+    return (int)DDPM3D_OK;
+  });
+}
+
+int ddpm3d_p_sample_t(ddpm3d_ctx* ctx, const float* x, const float* low_res, const int64_t* y, const float* noise,
+                      const int64_t* t, int clip_denoised, float* sample, float* pred_xstart, int B, int Z, int H, int W,
+                      void* stream) {
+  DD_CHECK(ctx && x && low_res && noise && sample && t, DDPM3D_ERR_ARG, "p_sample_t: null argument");
+  DD_TRY(check_geometry(ctx, B, Z, H, W));
+  DD_TRY(check_sampler_shapes(ctx));
+  DD_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = (int64_t)Z * H * W;
+  DD_TRY(ensure_workspace(ctx, B, Z, H, W));
+  DD_TRY(ensure_loop_buffers(ctx, B, n));
+  cudaStream_t s = (cudaStream_t)stream;
+  GraphKey key{};
+  key.kind = 3; key.B = B; key.Z = Z; key.H = H; key.W = W;
+  key.p[0] = x; key.p[1] = low_res; key.p[2] = y; key.p[3] = noise; key.p[4] = sample; key.p[5] = pred_xstart; key.p[6] = s;
+  key.p[7] = t;
+  key.i[0] = clip_denoised;
+  return run_graphed(ctx, key, s, [&](cudaStream_t cs, int* nl) {
+    DD_TRY(step_from_tensor_k(t, ctx->d_tindex, ctx->d_tmodel, ctx->d_table, B, ctx->T, cs));
+    DD_TRY(forward_launch(ctx, x, low_res, ctx->d_tmodel, y, ctx->d_mo, B, Z, H, W, cs, nl));
+    UpdateArgs a{};
+    a.x = x; a.model_out = ctx->d_mo; a.noise = noise; a.t_index = ctx->d_tindex; a.table = ctx->d_table;
+    a.mean_type = ctx->mean_type; a.var_type = ctx->var_type; a.clip = clip_denoised;
+    a.ddim = ctx->ddim; a.eta = ctx->eta;
+    a.sample = sample; a.pred_xstart = pred_xstart;
+    a.B = B; a.C = 1; a.n = n; a.T = ctx->T;
+    DD_TRY(p_sample_update_k(a, cs));
+    *nl += 2;
     return (int)DDPM3D_OK;
   });
 }

@@ -140,6 +140,8 @@ struct UpdateArgs {
 };
 int p_sample_update_k(const UpdateArgs& a, cudaStream_t s);
 int step_set_k(int32_t* step_counter, float* t_model, const ddpm3d_step_scalars* table, int B, int index, int exec, cudaStream_t s);
+int step_from_tensor_k(const int64_t* t, int32_t* t_index, float* t_model, const ddpm3d_step_scalars* table, int B, int T,
+                       cudaStream_t s);
 int step_advance_k(int32_t* step_counter, float* t_model, const ddpm3d_step_scalars* table, int B, cudaStream_t s);
 
 // ---- attention core (K12) --------------------------------------------------------------------

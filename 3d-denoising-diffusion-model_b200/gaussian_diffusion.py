@@ -237,6 +237,12 @@ class GaussianDiffusion:
         x = x.contiguous().float()
         if noise is None:
             noise = torch.randn_like(x)
+        from .unet import UNetModel_noatt
+        if isinstance(model, UNetModel_noatt) and x.shape[1] == 1:
+            # native model: UNet + update fused in one graph-cached library call, t stays on the device
+            model._bind_schedule(self)
+            self._set_sampler(model._ctx, False, 0.0)
+            return model._p_sample(self, x, noise.contiguous().float(), t, model_kwargs, clip_denoised, clone=True)
         model_output = model(x, self._map_timesteps(t), **model_kwargs)
         out = self._posterior(model, model_output, x, t, noise, clip_denoised)
         return {"sample": out["sample"], "pred_xstart": out["pred_xstart"]}

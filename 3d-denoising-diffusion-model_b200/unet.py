@@ -386,7 +386,8 @@ class UNetModel_noatt:
 
     # ---- fused sampler entry points used by GaussianDiffusion ---------------------------------------
     def _p_sample(self, diffusion, x, noise, step_index, model_kwargs, clip_denoised, clone=False):
-        """UNet + posterior update for one step in a single (graph-cached) library call."""
+        """UNet + posterior update for one step in a single (graph-cached) library call.  `step_index` is a
+        Python int (same step for the whole batch) or a device int64 tensor (B,) as in the public p_sample."""
         import torch
         self._bind_schedule(diffusion)
         low = model_kwargs.get("low_res")
@@ -401,9 +402,20 @@ class UNetModel_noatt:
         x0 = self._ps_buf[2]
         self._keep = (low, yy, noise)
         with torch.cuda.device(self._device):
-            N.check(N.lib().ddpm3d_p_sample(self._ctx, N.ptr(x), N.ptr(low), N.ptr(yy), N.ptr(noise), int(step_index),
-                                            int(bool(clip_denoised)), N.ptr(sample), N.ptr(x0), B, Z, H, W,
-                                            N.current_stream_ptr(self._device)))
+            if torch.is_tensor(step_index):
+                # stable address for the graph cache: the indices are copied into a persistent device buffer
+                if getattr(self, "_t_buf", None) is None or self._t_buf.shape[0] != B or self._t_buf.device != x.device:
+                    self._t_buf = torch.zeros(B, dtype=torch.int64, device=self._device)
+                self._t_buf.copy_(step_index.to(self._device, torch.int64), non_blocking=True)
+                tt = self._t_buf
+                self._keep = (low, yy, noise, tt)
+                N.check(N.lib().ddpm3d_p_sample_t(self._ctx, N.ptr(x), N.ptr(low), N.ptr(yy), N.ptr(noise), N.ptr(tt),
+                                                  int(bool(clip_denoised)), N.ptr(sample), N.ptr(x0), B, Z, H, W,
+                                                  N.current_stream_ptr(self._device)))
+            else:
+                N.check(N.lib().ddpm3d_p_sample(self._ctx, N.ptr(x), N.ptr(low), N.ptr(yy), N.ptr(noise), int(step_index),
+                                                int(bool(clip_denoised)), N.ptr(sample), N.ptr(x0), B, Z, H, W,
+                                                N.current_stream_ptr(self._device)))
         if clone:
             return {"sample": sample.clone(), "pred_xstart": x0.clone()}
         return {"sample": sample, "pred_xstart": x0}

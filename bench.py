@@ -338,11 +338,13 @@ def main():
     nz = torch.empty(shape, device=dev)
     t_top = diffusion.num_timesteps - 1
 
-    def e2e_step(i):
+    t_dev = [torch.tensor([t_top - (i % (t_top + 1))], device=dev) for i in range(max(K, Wm))]
+
+    def e2e_step(i):  # the public call: diffusion.p_sample(model, x, t, model_kwargs=..., noise=...)
         x = xT_h.to(dev, non_blocking=True)
         lr = low_h.to(dev, non_blocking=True)
         nz.normal_()
-        o = model._p_sample(diffusion, x, nz, t_top - i, {"low_res": lr}, True)
+        o = diffusion.p_sample(model, x, t_dev[i], clip_denoised=True, model_kwargs={"low_res": lr}, noise=nz)
         out_h.copy_(o["sample"], non_blocking=True)
 
     for i in range(Wm):

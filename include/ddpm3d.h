@@ -158,6 +158,12 @@ int ddpm3d_p_sample(ddpm3d_ctx* ctx, const float* x, const float* low_res, const
                     int step_index, int clip_denoised, float* sample, float* pred_xstart,
                     int B, int Z, int H, int W, void* stream);
 
+/* Same with the step indices as the device int64 tensor `t` (B) of the public signature p_sample(model, x, t, ...),
+ * possibly different per sample: nothing is read back to the host. */
+int ddpm3d_p_sample_t(ddpm3d_ctx* ctx, const float* x, const float* low_res, const int64_t* y, const float* noise,
+                      const int64_t* t, int clip_denoised, float* sample, float* pred_xstart, int B, int Z, int H, int W,
+                      void* stream);
+
 /* p_sample_loop (gaussian_diffusion.py:441-485): runs steps i = T-1 ... T-n_steps (n_steps <= 0: all T)
  * entirely on the device.  noise: device fp32 [n_steps][B*Z*H*W] consumed in execution order
  * (replaces th.randn_like, :430), or NULL to draw it in-kernel from Philox4x32-10 with `seed`.
