@@ -720,7 +720,73 @@ int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, 
   return launch_cl<T, MT, BN, NSTAGE, 1>(maps, mapW, p, s);
 }
 
+// ---- probe (test-only): does a SWIZZLE_128B K-major operand descriptor work when its start address is an
+// arbitrary multiple of 128 bytes (a row shift inside the 8-row swizzle atom)?  D = A[shift : shift+128] * I.
+__global__ void __launch_bounds__(128) probe_rowshift_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                             const __grid_constant__ CUtensorMap mapI, int rows, int shift,
+                                                             int mode, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_smem = base, i_smem = base + (uint32_t)rows * 128u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_load = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+  if (threadIdx.x == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(64u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar_load, (uint32_t)(rows * 128 + 64 * 128));
+    tma_load_2d(a_smem, &mapA, bar_load, 0, 0);
+    tma_load_2d(i_smem, &mapI, bar_load, 0, 0);
+    mbar_wait(bar_load, 0);
+    tc_fence_after();
+    const uint32_t start = a_smem + (uint32_t)shift * 128u;
+    uint64_t adesc = make_sw128_desc(start);
+    if (mode == 1) adesc |= (uint64_t)((start >> 7) & 7u) << 49;  // matrix base offset
+    const uint64_t bdesc = make_sw128_desc(i_smem);
+    const uint32_t idesc = make_idesc(128, 64, true);
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0);
+    umma_commit(bar_mma);
+    mbar_wait(bar_mma, 0);
+  }
+  __syncthreads();
+  tc_fence_after();
+  for (int c = 0; c < 64; c += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 64 + c + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u) : "memory");
+}
+
 }  // namespace
+
+int probe_rowshift(const void* a, int rows, const void* ident, int shift, int mode, float* out, cudaStream_t s) {
+  DD_CHECK(rows >= 136 && rows <= 1024 && rows % 8 == 0 && shift >= 0 && shift + 128 <= rows, DDPM3D_ERR_ARG, "probe: bad geometry");
+  CUtensorMap mapA, mapI;
+  DD_TRY(make_w_map(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a, rows > 256 ? 256 : rows, 64, rows > 256 ? 256 : rows));
+  DD_CHECK(rows <= 256, DDPM3D_ERR_ARG, "probe: at most 256 rows (one TMA box)");
+  DD_TRY(make_w_map(&mapI, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, ident, 64, 64, 64));
+  const size_t smem = (size_t)rows * 128 + 64 * 128 + 1024;
+  DD_CUDA(cudaFuncSetAttribute(probe_rowshift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_rowshift_kernel<<<1, 128, smem, s>>>(mapA, mapI, rows, shift, mode, out);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
 
 namespace {
 

@@ -1375,6 +1375,11 @@ int ddpm3d_k_conv3d(int dtype, int path, const void* in, const void* w, const fl
   return conv_simt(a, (cudaStream_t)stream);
 }
 
+int ddpm3d_k_probe_rowshift(const void* a, int rows, const void* ident, int shift, int mode, float* out, void* stream) {
+  DD_CHECK(a && ident && out, DDPM3D_ERR_ARG, "k_probe_rowshift: null argument");
+  return probe_rowshift(a, rows, ident, shift, mode, out, (cudaStream_t)stream);
+}
+
 int ddpm3d_k_groupnorm(int dtype, const void* in, const float* gamma, const float* beta, const float* film, int silu,
                        int resample, void* out, int B, int Z, int H, int W, int C, void* stream) {
   DD_CHECK(in && gamma && beta && out, DDPM3D_ERR_ARG, "k_groupnorm: null argument");

@@ -54,7 +54,9 @@ int conv_head(const ConvArgs& a, cudaStream_t s);
 // tcgen05 path; returns DDPM3D_ERR_ARG (without launching) when the shape is not eligible.
 bool conv_tc_eligible(const ConvArgs& a);
 int conv_tc(ConvArgs& a, cudaStream_t s);
-size_t conv_tc_scratch_bytes(const ConvArgs& a);  // split-K scratch this launch wants (0 = no split)
+size_t conv_tc_scratch_bytes(const ConvArgs& a);
+// test-only probe of row-shifted SWIZZLE_128B operand descriptors (see conv_tc.cu)
+int probe_rowshift(const void* a, int rows, const void* ident, int shift, int mode, float* out, cudaStream_t s);  // split-K scratch this launch wants (0 = no split)
 
 // ---- GroupNorm32 + FiLM + SiLU (K4/K5/K6) ------------------------------------------------------
 struct GnArgs {

@@ -212,6 +212,11 @@ int ddpm3d_profile_read(ddpm3d_ctx* ctx, ddpm3d_prof_record* out, int cap);
 int ddpm3d_k_conv3d(int dtype, int path, const void* in, const void* w, const float* bias, const void* residual,
                     void* out, int B, int Z, int H, int W, int Cin, int Cout, int taps, int stride_hw, void* stream);
 
+/* Hardware probe used by the tests / design work: D = A[shift : shift+128, :] * I on tcgen05 with the A operand
+ * descriptor starting `shift` rows into a [rows][64] bf16 SWIZZLE_128B tile (mode 0: base-offset field 0, mode 1:
+ * base-offset = (start >> 7) & 7).  a: device bf16 [rows][64], ident: device bf16 64x64 identity, out: fp32 [128][64]. */
+int ddpm3d_k_probe_rowshift(const void* a, int rows, const void* ident, int shift, int mode, float* out, void* stream);
+
 /* GroupNorm32(32,C) (+ optional per-(b,c) FiLM scale/shift, unet.py:248-252) (+ optional SiLU)
  * (+ optional AvgPool (1,2,2) / nearest x2 on (H,W) of the result, unet.py:81-140):
  * resample 0 none, 1 pool, 2 upsample.  gamma/beta fp32 [C]; film fp32 [B][2C] (scale then shift) or NULL. */
