@@ -528,6 +528,292 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   }
 }
 
+// =================================================================================================
+// Strip variant for the large 3x3x3 layers: the A operand is staged ONCE per (dz, 64-channel chunk) and reused
+// by the 9 in-plane taps.
+//
+// A z-plane band of width Wb is viewed as a padded, flattened sequence q = h * Wp + w' (Wp = Wb + 2, w' = 0 and
+// Wp-1 are the conv's zero padding / the neighbouring band's voxels).  A CTA tile is NB*128 consecutive q.  One
+// 5-D TMA box {64 ch, Wp, nh, 1, 1} starting at (w0 - 1, h_s) lands in smem as nh*Wp rows of 128 bytes -- exactly
+// that padded-flattened order -- and tap (dh, dw) of brick j is simply the 128 rows starting
+// (q0 + 128 j - h_s Wp) + dh Wp + dw rows into the strip.  tcgen05 applies the 128-byte swizzle to absolute smem
+// address bits, so an operand descriptor may start at any 128-byte row (probe_rowshift_kernel verifies this on the
+// hardware).  Per 9 taps the SM now pulls one 75 KB strip + 9 x 16 KB weight tiles through L2 instead of 9 x 48 KB.
+// The ~2/Wp pad columns are computed and discarded.
+constexpr int STRIP_THREADS = 224;  // warp 0 strip producer, 1 MMA, 2-5 epilogue, 6 weight producer
+
+struct StripParams {
+  int B, Z, H, W, Cout;
+  int Wb, Wp, nbands, nh, tiles_per_band, nNt, num_tiles, zoff;
+  int nsrc, chunks[3], n_macro_main, n_macro, Cin;
+  uint32_t strip_bytes, strip_stride;  // bytes delivered per strip / smem distance between the two strip buffers
+  const float* bias;
+  const void* res;   // RES_SAME residual or NULL
+  void* out;
+  float* chsum;
+  uint32_t cs_off;
+};
+
+template <typename T, int NB, int NW>
+__global__ void __launch_bounds__(STRIP_THREADS, 1)
+conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW, const StripParams p) {
+  constexpr int BN = 128;
+  constexpr int W_BYTES = BN * BK * 2;
+  constexpr int ACC_COLS = NB * BN;
+  constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static_assert(TMEM_COLS == 512 || TMEM_COLS == 256, "TMEM allocation must be a power of two <= 512");
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * 2 + 2 * NW + 4];
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = smem_base + 2 * p.strip_stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto sfull = [&](int i) { return bar0 + 8u * i; };
+  auto sempty = [&](int i) { return bar0 + 8u * (2 + i); };
+  auto wfull = [&](int i) { return bar0 + 8u * (4 + i); };
+  auto wempty = [&](int i) { return bar0 + 8u * (4 + NW + i); };
+  auto tfull = [&](int i) { return bar0 + 8u * (4 + 2 * NW + i); };
+  auto tempty = [&](int i) { return bar0 + 8u * (6 + 2 * NW + i); };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA0);
+    prefetch_tmap(&mapW);
+    if (p.nsrc > 1) prefetch_tmap(&mapA1);
+    if (p.nsrc > 2) prefetch_tmap(&mapA2);
+    for (int i = 0; i < 2; ++i) { mbar_init(sfull(i), 1); mbar_init(sempty(i), 1); mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
+    for (int i = 0; i < NW; ++i) { mbar_init(wfull(i), 1); mbar_init(wempty(i), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  // tile -> (b, z, band, q0, n0)
+  auto decode = [&](int tile, int& b, int& z, int& w0, int& q0, int& n0) {
+    const int nt = tile % p.nNt;
+    int m = tile / p.nNt;
+    const int tq = m % p.tiles_per_band; m /= p.tiles_per_band;
+    const int band = m % p.nbands; m /= p.nbands;
+    z = m % p.Z;
+    b = m / p.Z;
+    w0 = band * p.Wb;
+    q0 = tq * (128 * NB);
+    n0 = nt * BN;
+  };
+  // first strip row (may be negative: rows above the plane arrive as zeros)
+  auto strip_h0 = [&](int q0) {
+    const int x = q0 - p.Wp - 1 + 4 * p.Wp;  // shift into the non-negative range for the division
+    return x / p.Wp - 4;
+  };
+
+  if (warp == 0) {
+    // ===================================== strip producer =====================================
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t sph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int b, z, w0, q0, n0;
+        decode(tile, b, z, w0, q0, n0);
+        const int h_s = strip_h0(q0);
+        for (int m = 0; m < p.n_macro; ++m) {
+          mbar_wait(sempty(sb), sph ^ 1);
+          mbar_expect_tx(sfull(sb), p.strip_bytes);
+          const uint32_t dst = smem_base + sb * p.strip_stride;
+          if (m < p.n_macro_main) {
+            const int dz = m / p.chunks[0], ch = m - dz * p.chunks[0];
+            tma_load_5d(dst, &mapA0, sfull(sb), ch * BK, w0 - 1, h_s, z + dz - 1 + p.zoff, b);
+          } else {
+            const int e = m - p.n_macro_main;
+            if (e < p.chunks[1]) tma_load_5d(dst, &mapA1, sfull(sb), e * BK, w0 - 1, h_s, z, b);
+            else tma_load_5d(dst, &mapA2, sfull(sb), (e - p.chunks[1]) * BK, w0 - 1, h_s, z, b);
+          }
+          if (++sb == 2) { sb = 0; sph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===================================== weight producer ====================================
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.nNt) * BN;
+        for (int m = 0; m < p.n_macro; ++m) {
+          int ntaps, kcol;
+          if (m < p.n_macro_main) {
+            const int dz = m / p.chunks[0], ch = m - dz * p.chunks[0];
+            ntaps = 9;
+            kcol = dz * 9 * p.Cin + ch * BK;  // + t * Cin per in-plane tap
+          } else {
+            ntaps = 1;
+            kcol = 27 * p.Cin + (m - p.n_macro_main) * BK;
+          }
+          for (int t = 0; t < ntaps; ++t) {
+            mbar_wait(wempty(ws), wph ^ 1);
+            mbar_expect_tx(wfull(ws), W_BYTES);
+            tma_load_2d(w_base + ws * W_BYTES, &mapW, wfull(ws), kcol + t * p.Cin, n0);
+            if (++ws == NW) { ws = 0; wph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, sizeof(T) == 2 && !std::is_same<T, f16>::value);
+      int sb = 0, ws = 0, acc = 0;
+      uint32_t sph = 0, wph = 0, aph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int b, z, w0, q0, n0;
+        decode(tile, b, z, w0, q0, n0);
+        const int offbase = q0 - strip_h0(q0) * p.Wp;  // strip row of the tile's first output position (centre tap)
+        mbar_wait(tempty(acc), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+        bool first = true;
+        for (int m = 0; m < p.n_macro; ++m) {
+          mbar_wait(sfull(sb), sph);
+          tc_fence_after();
+          const uint32_t strip = smem_base + sb * p.strip_stride;
+          const int ntaps = m < p.n_macro_main ? 9 : 1;
+          for (int t = 0; t < ntaps; ++t) {
+            const int dh = ntaps == 9 ? t / 3 - 1 : 0, dw = ntaps == 9 ? t % 3 - 1 : 0;
+            mbar_wait(wfull(ws), wph);
+            tc_fence_after();
+            const uint64_t bdesc = make_sw128_desc(w_base + ws * W_BYTES);
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              const uint64_t adesc = make_sw128_desc(strip + (uint32_t)(offbase + j * 128 + dh * p.Wp + dw) * 128u);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_bf16(d_tmem + (uint32_t)(j * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                          (first && k == 0) ? 0u : 1u);
+            }
+            first = false;
+            umma_commit(wempty(ws));
+            if (++ws == NW) { ws = 0; wph ^= 1; }
+          }
+          umma_commit(sempty(sb));
+          if (++sb == 2) { sb = 0; sph ^= 1; }
+        }
+        umma_commit(tfull(acc));
+        if (++acc == 2) { acc = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue ===========================================
+    const int sub = warp & 3;
+    const int row = sub * 32 + lane;
+    float* cs_tr = reinterpret_cast<float*>(smem_raw + p.cs_off);
+    float* cs_acc = cs_tr + 4 * 32 * 33;
+    if (p.chsum)
+      for (int i = lane; i < p.B * p.Cout * 2; i += 32) cs_acc[(size_t)sub * p.B * p.Cout * 2 + i] = 0.f;
+    int acc = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int b, z, w0, q0, n0;
+      decode(tile, b, z, w0, q0, n0);
+      mbar_wait(tfull(acc), aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < NB; ++j) {
+        const int q = q0 + j * 128 + row;
+        const int hq = q / p.Wp, wq = q - hq * p.Wp;
+        const int w = w0 + wq - 1;
+        const bool valid = wq >= 1 && wq <= p.Wb && hq < p.H && w < p.W;
+        const int64_t vox = (((int64_t)b * p.Z + z) * p.H + hq) * p.W + w;
+        const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * ACC_COLS + j * BN);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_row + (uint32_t)c, r);
+          uint4 rres[4];
+          const bool res1 = valid && p.res != nullptr;
+          if (res1) {
+            const uint4* rp = reinterpret_cast<const uint4*>((const T*)p.res + vox * p.Cout + n0 + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rres[i] = rp[i];
+          }
+          tmem_ld_wait();
+          float v[32];
+          if (valid) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = __ldg(bp + i);
+              v[4 * i] = __uint_as_float(r[4 * i]) + b4.x;
+              v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
+              v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z;
+              v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
+            }
+            if (res1) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) add8r<T>(v + 8 * i, rres[i]);
+            }
+            T* op = (T*)p.out + vox * p.Cout + n0 + c;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq) w4[qq] = pack2<T>(v[8 * i + 2 * qq], v[8 * i + 2 * qq + 1]);
+              *reinterpret_cast<uint4*>(op + 8 * i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          if (p.chsum) {
+            float* tr = cs_tr + sub * (32 * 33);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = v[i];
+            __syncwarp();
+            float s0 = 0.f, s1 = 0.f, q0s = 0.f, q1s = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; rr += 2) {
+              const float x0 = tr[rr * 33 + lane], x1 = tr[(rr + 1) * 33 + lane];
+              s0 += x0; q0s = fmaf(x0, x0, q0s);
+              s1 += x1; q1s = fmaf(x1, x1, q1s);
+            }
+            float* a2 = cs_acc + (((size_t)sub * p.B + b) * p.Cout + n0 + c + lane) * 2;
+            a2[0] += s0 + s1;
+            a2[1] += q0s + q1s;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(acc));
+      if (++acc == 2) { acc = 0; aph ^= 1; }
+    }
+    if (p.chsum) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = (warp - 2) * 32 + lane, n = p.B * p.Cout * 2;
+      for (int i = et; i < n; i += 128) {
+        const float t = ((cs_acc[i] + cs_acc[n + i]) + cs_acc[2 * n + i]) + cs_acc[3 * n + i];
+        const int bb = i / (p.Cout * 2), rem = i - bb * p.Cout * 2;
+        p.chsum[((size_t)bb * CHSUM_SLOTS + blockIdx.x) * p.Cout * 2 + rem] = t;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+
 // stream-K fix-up: for every tile whose K range was shared by several CTAs, add their fp32 partials in slot
 // order (deterministic), apply bias / residual and store.  One block per tile.
 template <typename T, int MT, int BN>
@@ -851,10 +1137,108 @@ TcPlan make_plan(const ConvArgs& a, int nk) {
 
 }  // namespace
 
+namespace {
+
+struct StripPlan {
+  int Wb, Wp, nbands, nh, tiles_per_band, nNt, num_tiles, NW;
+  uint32_t strip_bytes, strip_stride;
+  size_t smem;
+};
+
+bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
+  if (!a.strip_allowed || !is_half_dt(a.dt) || a.taps != 27 || a.stride_hw != 1 || a.out_planar_f32) return false;
+  if (a.Cout % 128 != 0 || a.main.C % BK != 0) return false;
+  for (int e = 0; e < a.n_extra; ++e)
+    if (a.extra[e].C % BK != 0) return false;
+  if (a.residual && a.res_mode != RES_SAME) return false;
+  StripPlan t{};
+  t.Wb = 0;
+  for (int d = std::min(a.Wo, 96); d >= 24; --d)
+    if (a.Wo % d == 0) { t.Wb = d; break; }
+  if (!t.Wb) return false;
+  constexpr int NB = 2;
+  t.Wp = t.Wb + 2;
+  t.nbands = a.Wo / t.Wb;
+  t.nh = 3 + (int)ceil_div(128 * NB + 1, t.Wp);
+  if (t.nh > 256) return false;
+  t.tiles_per_band = (int)ceil_div((int64_t)a.Ho * t.Wp, 128 * NB);
+  t.nNt = a.Cout / 128;
+  const int64_t tiles = (int64_t)a.B * a.Z * t.nbands * t.tiles_per_band * t.nNt;
+  if (tiles < 2 * (int64_t)sm_count() || tiles >= ((int64_t)1 << 31)) return false;
+  t.num_tiles = (int)tiles;
+  t.strip_bytes = (uint32_t)(t.nh * t.Wp * 128);
+  t.strip_stride = (t.strip_bytes + 1023u) & ~1023u;
+  const size_t cs = want_chsum ? CS_TR_BYTES + (size_t)4 * a.B * a.Cout * 2 * sizeof(float) : 0;
+  for (int nw : {4, 3}) {
+    t.NW = nw;
+    t.smem = (size_t)2 * t.strip_stride + (size_t)nw * 128 * BK * 2 + 1024 + cs;
+    if (t.smem + 256 <= 227 * 1024) { *out = t; return true; }
+  }
+  return false;
+}
+
+template <typename T, int NW>
+int launch_strip(const CUtensorMap* maps, const CUtensorMap& mapW, const StripParams& p, const StripPlan& plan, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_strip_kernel<T, 2, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    configured = true;
+  }
+  const int grid = std::min(p.num_tiles, sm_count());
+  if (p.chsum && grid < CHSUM_SLOTS)
+    DD_CUDA(cudaMemsetAsync(p.chsum, 0, (size_t)p.B * CHSUM_SLOTS * p.Cout * 2 * sizeof(float), s));
+  conv_tc_strip_kernel<T, 2, NW><<<grid, STRIP_THREADS, plan.smem, s>>>(maps[0], maps[1], maps[2], mapW, p);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
+int conv_tc_strip(ConvArgs& a, const StripPlan& plan, bool chsum, cudaStream_t s) {
+  StripParams p{};
+  p.B = a.B; p.Z = a.Z; p.H = a.Ho; p.W = a.Wo; p.Cout = a.Cout;
+  p.Wb = plan.Wb; p.Wp = plan.Wp; p.nbands = plan.nbands; p.nh = plan.nh; p.tiles_per_band = plan.tiles_per_band;
+  p.nNt = plan.nNt; p.num_tiles = plan.num_tiles; p.zoff = a.in_zpad;
+  p.nsrc = 1 + a.n_extra;
+  p.chunks[0] = a.main.C / BK;
+  p.Cin = a.main.C;
+  p.n_macro_main = 3 * p.chunks[0];
+  p.n_macro = p.n_macro_main;
+  int Ktot = 27 * a.main.C;
+  for (int e = 0; e < a.n_extra; ++e) {
+    p.chunks[1 + e] = a.extra[e].C / BK;
+    p.n_macro += p.chunks[1 + e];
+    Ktot += a.extra[e].C;
+  }
+  p.strip_bytes = plan.strip_bytes;
+  p.strip_stride = plan.strip_stride;
+  p.bias = a.bias;
+  p.res = a.residual;
+  p.out = a.out;
+  p.chsum = chsum ? a.chsum_out : nullptr;
+  p.cs_off = (uint32_t)((size_t)2 * plan.strip_stride + (size_t)plan.NW * 128 * BK * 2 + 1024);
+  a.chsum_written = chsum ? 1 : 0;
+  const CUtensorMapDataType tdt = a.dt == DDPM3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap maps[3];
+  DD_TRY(make_act_map(&maps[0], tdt, a.main.ptr, a.B, a.Z + 2 * a.in_zpad, a.Ho, a.Wo, a.main.C, plan.Wp, plan.nh, 1));
+  maps[1] = maps[0];
+  maps[2] = maps[0];
+  for (int e = 0; e < a.n_extra; ++e)
+    DD_TRY(make_act_map(&maps[1 + e], tdt, a.extra[e].ptr, a.B, a.Z, a.Ho, a.Wo, a.extra[e].C, plan.Wp, plan.nh, 1));
+  CUtensorMap mapW;
+  DD_TRY(make_w_map(&mapW, tdt, a.w, a.Cout, Ktot, 128));
+  if (a.dt == DDPM3D_BF16) return plan.NW == 4 ? launch_strip<bf16, 4>(maps, mapW, p, plan, s) : launch_strip<bf16, 3>(maps, mapW, p, plan, s);
+  return plan.NW == 4 ? launch_strip<f16, 4>(maps, mapW, p, plan, s) : launch_strip<f16, 3>(maps, mapW, p, plan, s);
+}
+
+}  // namespace
+
 size_t conv_tc_scratch_bytes(const ConvArgs& a0) {
   ConvArgs a = a0;
   a.splitk_allowed = 1;
   if (!conv_tc_eligible(a)) return 0;
+  {
+    StripPlan sp;
+    if (strip_plan(a, false, &sp)) return 0;
+  }
   int nk = a.taps * (a.main.C / BK);
   for (int e = 0; e < a.n_extra; ++e) nk += a.extra[e].C / BK;
   const TcPlan plan = make_plan(a, nk);
@@ -879,6 +1263,13 @@ bool conv_tc_eligible(const ConvArgs& a) {
 
 int conv_tc(ConvArgs& a, cudaStream_t s) {
   DD_CHECK(conv_tc_eligible(a), DDPM3D_ERR_ARG, "conv_tc: shape not eligible");
+  {
+    const bool want_cs = a.chsum_out && CS_TR_BYTES + (size_t)4 * a.B * a.Cout * 2 * sizeof(float) <= (size_t)CS_SMEM_MAX &&
+                         sm_count() <= CHSUM_SLOTS;
+    StripPlan sp;
+    if (strip_plan(a, want_cs, &sp)) return conv_tc_strip(a, sp, want_cs, s);
+    if (want_cs && strip_plan(a, false, &sp)) return conv_tc_strip(a, sp, false, s);
+  }
   TcParams p{};
   a.chsum_written = 0;
   if (a.chsum_out && CS_TR_BYTES + (size_t)4 * a.B * a.Cout * 2 * sizeof(float) <= (size_t)CS_SMEM_MAX && sm_count() <= CHSUM_SLOTS) {

@@ -166,7 +166,7 @@ struct ddpm3d_ctx {
   float* d_img = nullptr;
   size_t img_cap = 0;
   // options
-  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0;
+  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 1;
   float* splitk_buf = nullptr;  // fp32 partial tiles of split-K convolutions (sized by the dry run)
   size_t splitk_cap = 0, splitk_need = 0;
   cudaStream_t cap_stream = nullptr;
@@ -489,6 +489,7 @@ struct Run {
     if (a.taps == 27) a.in_zpad = zp;
     a.splitk_allowed = ctx->split_k;
     a.cluster_allowed = ctx->cluster;
+    a.strip_allowed = ctx->strip;
     ++launches;
     if (arena.dry) {
       if (is_half_dt(a.dt) && ctx->conv_path != 1 && a.splitk_allowed)
@@ -1312,6 +1313,7 @@ int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value) {
   else if (n == "fuse_stats") ctx->fuse_stats = value != 0;
   else if (n == "split_k") ctx->split_k = value != 0;
   else if (n == "cluster") ctx->cluster = value != 0;
+  else if (n == "strip") ctx->strip = value != 0;
   else { set_error("unknown option: " + n); return DDPM3D_ERR_ARG; }
   // cached graphs bake the options in
   if (ctx->device >= 0) {

@@ -33,6 +33,12 @@ from test_gpu_model import TOL, build  # noqa: E402
     (512, 512, (1, 96, 6, 6), 27, False),    # small-M layer: split-K (fp32 partials + reduce pass)
     (384, 384, (1, 96, 12, 12), 27, True),   # split-K with a residual applied in the reduce pass
     (768, 384, (1, 24, 12, 12), 27, False),  # long K (324 k-steps), few tiles
+    # strip variant (A staged once per (dz, chunk), 9 taps through row-shifted descriptors): >= 296 tiles
+    (128, 128, (2, 16, 96, 96), 27, True),   # batch 2, residual
+    (64, 128, (1, 40, 48, 48), 27, False),   # 48-wide band (pitch 50)
+    (128, 256, (1, 32, 48, 48), 27, True),   # two output-channel tiles
+    (64, 128, (1, 4, 192, 192), 27, False),  # two 96-wide bands per plane (halo column shared between bands)
+    (64, 128, (1, 12, 80, 80), 27, True),    # band width that is not a power of two
 ])
 @pytest.mark.parametrize("dt", [N.BF16, N.FP16])
 def test_conv3d_tcgen05(Cin, Cout, shape, taps, res, dt):
