@@ -9,6 +9,7 @@ from ddpm3d_b200 import script_util as su
 
 opt = sys.argv[1]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+fixed = [a.split("=") for a in sys.argv[3:]]
 dev = torch.device("cuda", 0)
 model, diffusion = su.sr_create_model_and_diffusion(**bench.C2_FLAGS)
 model.load_state_dict(bench.synth_weights(model._specs))
@@ -16,6 +17,8 @@ model.to(dev); model.convert_to_fp16(); model.eval()
 g = torch.Generator().manual_seed(0)
 x = torch.randn(bench.PATCH, generator=g).to(dev); low = torch.rand(bench.PATCH, generator=g).to(dev)
 t = torch.tensor([500.0], device=dev)
+for k_, v_ in fixed:
+    model.set_option(k_, int(v_))
 for _ in range(3):
     model(x, t, low_res=low)
 res = {0: collections.defaultdict(float), 1: collections.defaultdict(float)}
