@@ -713,8 +713,8 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     // ===================================== epilogue ===========================================
     const int sub = warp & 3;
     const int row = sub * 32 + lane;
-    float* cs_tr = reinterpret_cast<float*>(smem_raw + p.cs_off);
-    float* cs_acc = cs_tr + 4 * 32 * 33;
+    float* cs_tr = reinterpret_cast<float*>(smem_raw + p.cs_off);  // [2][32][33]
+    float* cs_acc = cs_tr + 2 * 32 * 33;
     if (p.chsum)
       for (int i = lane; i < p.B * p.Cout * 2; i += 32) cs_acc[(size_t)sub * p.B * p.Cout * 2 + i] = 0.f;
     int acc = 0;
@@ -772,17 +772,23 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
           if (p.chsum) {
-            float* tr = cs_tr + sub * (32 * 33);
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = v[i];
-            __syncwarp();
+            // two transpose buffers for the four epilogue warps (smem is full): the warps of a pair take turns
+            float* tr = cs_tr + (sub >> 1) * (32 * 33);
             float s0 = 0.f, s1 = 0.f, q0s = 0.f, q1s = 0.f;
 #pragma unroll
-            for (int rr = 0; rr < 32; rr += 2) {
-              const float x0 = tr[rr * 33 + lane], x1 = tr[(rr + 1) * 33 + lane];
-              s0 += x0; q0s = fmaf(x0, x0, q0s);
-              s1 += x1; q1s = fmaf(x1, x1, q1s);
+            for (int turn = 0; turn < 2; ++turn) {
+              if ((sub & 1) == turn) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = v[i];
+                __syncwarp();
+#pragma unroll
+                for (int rr = 0; rr < 32; rr += 2) {
+                  const float x0 = tr[rr * 33 + lane], x1 = tr[(rr + 1) * 33 + lane];
+                  s0 += x0; q0s = fmaf(x0, x0, q0s);
+                  s1 += x1; q1s = fmaf(x1, x1, q1s);
+                }
+              }
+              asm volatile("bar.sync %0, 64;" ::"r"(2 + (sub >> 1)) : "memory");
             }
             float* a2 = cs_acc + (((size_t)sub * p.B + b) * p.Cout + n0 + c + lane) * 2;
             a2[0] += s0 + s1;
@@ -1168,7 +1174,7 @@ bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
   t.num_tiles = (int)tiles;
   t.strip_bytes = (uint32_t)(t.nh * t.Wp * 128);
   t.strip_stride = (t.strip_bytes + 1023u) & ~1023u;
-  const size_t cs = want_chsum ? CS_TR_BYTES + (size_t)4 * a.B * a.Cout * 2 * sizeof(float) : 0;
+  const size_t cs = want_chsum ? CS_TR_BYTES / 2 + (size_t)4 * a.B * a.Cout * 2 * sizeof(float) : 0;
   for (int nw : {4, 3}) {
     t.NW = nw;
     t.smem = (size_t)2 * t.strip_stride + (size_t)nw * 128 * BK * 2 + 1024 + cs;
