@@ -41,7 +41,7 @@ struct ConvArgs {
   float* splitk_scratch = nullptr;
   size_t splitk_bytes = 0;
   int splitk_allowed = 0;
-  int strip_allowed = 1;    // strip variant: A staged once per (dz, chunk), 9 in-plane taps by row-shifted descriptors
+  int strip_allowed = 1;    // (unit-test entry point default; the engine passes its `strip` option) strip variant: A staged once per (dz, chunk), 9 in-plane taps by row-shifted descriptors
   int cluster_allowed = 1;  // 2-CTA clusters sharing the weight tile by TMA multicast (big layers)
 };
 constexpr int CHSUM_SLOTS = 148;  // one per persistent CTA (unused slots are zeroed by the launcher)

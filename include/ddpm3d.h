@@ -190,8 +190,12 @@ int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total);
  * "profile" (0/1): record a CUDA-event pair around every kernel launch (disables graphs);
  * "fuse_stats" (0/1, default 1): GroupNorm statistics come from per-channel sums accumulated in the producing
  * convolution's epilogue instead of a separate pass over the tensor;
- * "split_k" (0/1, default 1): convolutions with too few tiles to fill the GPU split K over CTAs (fp32 partials,
- * deterministic second pass). */
+ * "split_k" (0/1, default 1): convolutions with too few tiles to fill the GPU deal their k-steps evenly to the CTAs
+ * (stream-K: fp32 partials, deterministic fix-up pass);
+ * "strip" (0/1, default 0): large 3x3x3 layers stage the A operand once per (dz, channel chunk) and address the 9
+ * in-plane taps through row-shifted descriptors (half the L2 traffic; 6-14 % faster stand-alone, neutral inside the
+ * power-capped network step);
+ * "cluster" (0/1, default 0): 2-CTA clusters multicast the weight tile (neutral). */
 int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value);
 /* Kernel launches enqueued by this ctx since creation. */
 int64_t ddpm3d_launch_count(const ddpm3d_ctx* ctx);
