@@ -29,7 +29,7 @@ struct SimtParams {
   int res_mode;
   void* out;
   int planar;
-  int B, Z, Ho, Wo, Hin, Win, Cout, Ktot;
+  int B, Z, Ho, Wo, Hin, Win, Cout, Ktot, wld;
   int zp;  // halo planes of source 0
   int64_t M;
 };
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(SimtParams p) {
   // ---- B loader: thread -> (n, 4-wide k quarter) ------------------------------------------------
   const int b_n = tid / 4, b_kq = tid % 4;
   const bool b_ok = (n0 + b_n) < p.Cout;
-  const T* wrow = (const T*)p.w + (int64_t)(n0 + b_n) * p.Ktot;
+  const T* wrow = (const T*)p.w + (int64_t)(n0 + b_n) * p.wld;
 
   float ra[8], rb[4];
 
@@ -297,7 +297,8 @@ int conv_simt(const ConvArgs& a, cudaStream_t s) {
     vec = vec && (a.extra[e].C % 8 == 0);
   }
   p.Ktot = p.kbeg[p.nsrc];
-  vec = vec && (p.Ktot % 4 == 0);
+  p.wld = a.w_ld ? a.w_ld : p.Ktot;
+  vec = vec && (p.Ktot % 4 == 0) && (p.wld % 4 == 0);
   p.taps = a.taps;
   p.stride = a.stride_hw;
   p.zp = a.in_zpad;

@@ -669,7 +669,7 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
   } else if (warp == 1) {
     // ===================================== MMA issuer =========================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, sizeof(T) == 2 && !std::is_same<T, f16>::value);
+      constexpr uint32_t idesc = make_idesc(128, 128 * NB, sizeof(T) == 2 && !std::is_same<T, f16>::value);
       int sb = 0, ws = 0, acc = 0;
       uint32_t sph = 0, wph = 0, aph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -689,15 +689,15 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
             const int dh = ntaps == 9 ? t / 3 - 1 : 0, dw = ntaps == 9 ? t % 3 - 1 : 0;
             mbar_wait(wfull(ws), wph);
             tc_fence_after();
-            const uint64_t bdesc = make_sw128_desc(w_base + ws * W_BYTES);
+            // Operands are swapped with respect to the brick kernel: M = 128 output channels (the weight tile),
+            // N = 256 voxels (256 consecutive strip rows).  One N=256 instruction reads 4 KB + 8 KB of smem per
+            // 128 tensor cycles instead of 2 x (4 + 4) KB -- shared-memory read bandwidth (128 B/clk, shared with the
+            // TMA fills) is what holds the M=128, N=128 form at ~65 % tensor-pipe utilisation.
+            const uint64_t wdesc = make_sw128_desc(w_base + ws * W_BYTES);
+            const uint64_t sdesc = make_sw128_desc(strip + (uint32_t)(offbase + dh * p.Wp + dw) * 128u);
 #pragma unroll
-            for (int j = 0; j < NB; ++j) {
-              const uint64_t adesc = make_sw128_desc(strip + (uint32_t)(offbase + j * 128 + dh * p.Wp + dw) * 128u);
-#pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k)
-                umma_bf16(d_tmem + (uint32_t)(j * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                          (first && k == 0) ? 0u : 1u);
-            }
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16(d_tmem, wdesc + (uint64_t)(2 * k), sdesc + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
             first = false;
             umma_commit(wempty(ws));
             if (++ws == NW) { ws = 0; wph ^= 1; }
@@ -711,90 +711,74 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     }
   } else {
     // ===================================== epilogue ===========================================
+    // D is [lane = output channel][column = voxel of the tile].  A warp owns 32 channels (its TMEM sub-partition);
+    // per 32-voxel chunk it adds bias, accumulates the GroupNorm channel sums (a thread owns a channel: no
+    // cross-lane reduction), transposes through padded smem and stores 32 channels x 2 bytes per voxel.
     const int sub = warp & 3;
-    const int row = sub * 32 + lane;
-    float* cs_tr = reinterpret_cast<float*>(smem_raw + p.cs_off);  // [2][32][33]
-    float* cs_acc = cs_tr + 2 * 32 * 33;
-    if (p.chsum)
-      for (int i = lane; i < p.B * p.Cout * 2; i += 32) cs_acc[(size_t)sub * p.B * p.Cout * 2 + i] = 0.f;
+    float* cs_tr = reinterpret_cast<float*>(smem_raw + p.cs_off);  // [2][32][33]: the warps of a pair take turns
+    float* cs_acc = cs_tr + 2 * 32 * 33;                           // [B][Cout][2]
+    float* tr = cs_tr + (sub >> 1) * (32 * 33);
+    if (p.chsum) {
+      for (int i = (warp - 2) * 32 + lane; i < p.B * p.Cout * 2; i += 128) cs_acc[i] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     int acc = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int b, z, w0, q0, n0;
       decode(tile, b, z, w0, q0, n0);
+      const int co = n0 + sub * 32 + lane;
+      const float bias_co = __ldg(p.bias + co);
+      float ts = 0.f, tq = 0.f;
       mbar_wait(tfull(acc), aph);
       tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * ACC_COLS);
 #pragma unroll 1
-      for (int j = 0; j < NB; ++j) {
-        const int q = q0 + j * 128 + row;
+      for (int vc = 0; vc < NB * 4; ++vc) {
+        uint32_t r[32];
+        tmem_ld32(t_row + (uint32_t)(vc * 32), r);
+        // the voxel this thread will store after the transpose
+        const int q = q0 + vc * 32 + lane;
         const int hq = q / p.Wp, wq = q - hq * p.Wp;
         const int w = w0 + wq - 1;
         const bool valid = wq >= 1 && wq <= p.Wb && hq < p.H && w < p.W;
         const int64_t vox = (((int64_t)b * p.Z + z) * p.H + hq) * p.W + w;
-        const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * ACC_COLS + j * BN);
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_row + (uint32_t)c, r);
-          uint4 rres[4];
-          const bool res1 = valid && p.res != nullptr;
-          if (res1) {
-            const uint4* rp = reinterpret_cast<const uint4*>((const T*)p.res + vox * p.Cout + n0 + c);
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        tmem_ld_wait();
+        float x[32];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) rres[i] = rp[i];
+        for (int j = 0; j < 32; ++j) {
+          x[j] = ((vmask >> j) & 1u) ? __uint_as_float(r[j]) + bias_co : 0.f;
+          ts += x[j];
+          tq = fmaf(x[j], x[j], tq);
+        }
+        float v[32];
+#pragma unroll
+        for (int turn = 0; turn < 2; ++turn) {
+          if ((sub & 1) == turn) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tr[j * 33 + lane] = x[j];  // [voxel][channel]
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = tr[lane * 33 + c];
           }
-          tmem_ld_wait();
-          float v[32];
-          if (valid) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c);
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + (sub >> 1)) : "memory");
+        }
+        if (valid) {
+          T* op = (T*)p.out + vox * p.Cout + n0 + sub * 32;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b4 = __ldg(bp + i);
-              v[4 * i] = __uint_as_float(r[4 * i]) + b4.x;
-              v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
-              v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z;
-              v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
-            }
-            if (res1) {
+          for (int i = 0; i < 4; ++i) {
+            uint32_t w4[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) add8r<T>(v + 8 * i, rres[i]);
-            }
-            T* op = (T*)p.out + vox * p.Cout + n0 + c;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint32_t w4[4];
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq) w4[qq] = pack2<T>(v[8 * i + 2 * qq], v[8 * i + 2 * qq + 1]);
-              *reinterpret_cast<uint4*>(op + 8 * i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
-          }
-          if (p.chsum) {
-            // two transpose buffers for the four epilogue warps (smem is full): the warps of a pair take turns
-            float* tr = cs_tr + (sub >> 1) * (32 * 33);
-            float s0 = 0.f, s1 = 0.f, q0s = 0.f, q1s = 0.f;
-#pragma unroll
-            for (int turn = 0; turn < 2; ++turn) {
-              if ((sub & 1) == turn) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = v[i];
-                __syncwarp();
-#pragma unroll
-                for (int rr = 0; rr < 32; rr += 2) {
-                  const float x0 = tr[rr * 33 + lane], x1 = tr[(rr + 1) * 33 + lane];
-                  s0 += x0; q0s = fmaf(x0, x0, q0s);
-                  s1 += x1; q1s = fmaf(x1, x1, q1s);
-                }
-              }
-              asm volatile("bar.sync %0, 64;" ::"r"(2 + (sub >> 1)) : "memory");
-            }
-            float* a2 = cs_acc + (((size_t)sub * p.B + b) * p.Cout + n0 + c + lane) * 2;
-            a2[0] += s0 + s1;
-            a2[1] += q0s + q1s;
+            for (int qq = 0; qq < 4; ++qq) w4[qq] = pack2<T>(v[8 * i + 2 * qq], v[8 * i + 2 * qq + 1]);
+            *reinterpret_cast<uint4*>(op + 8 * i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
         }
+      }
+      if (p.chsum) {  // this thread is the only one of the CTA that owns channel `co`
+        float* a2 = cs_acc + ((size_t)b * p.Cout + co) * 2;
+        a2[0] += ts;
+        a2[1] += tq;
       }
       tc_fence_before();
       __syncwarp();
@@ -803,11 +787,10 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     }
     if (p.chsum) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int et = (warp - 2) * 32 + lane, n = p.B * p.Cout * 2;
-      for (int i = et; i < n; i += 128) {
-        const float t = ((cs_acc[i] + cs_acc[n + i]) + cs_acc[2 * n + i]) + cs_acc[3 * n + i];
+      const int n = p.B * p.Cout * 2;
+      for (int i = (warp - 2) * 32 + lane; i < n; i += 128) {
         const int bb = i / (p.Cout * 2), rem = i - bb * p.Cout * 2;
-        p.chsum[((size_t)bb * CHSUM_SLOTS + blockIdx.x) * p.Cout * 2 + rem] = t;
+        p.chsum[((size_t)bb * CHSUM_SLOTS + blockIdx.x) * p.Cout * 2 + rem] = cs_acc[i];
       }
     }
   }
@@ -1156,7 +1139,7 @@ bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
   if (a.Cout % 128 != 0 || a.main.C % BK != 0) return false;
   for (int e = 0; e < a.n_extra; ++e)
     if (a.extra[e].C % BK != 0) return false;
-  if (a.residual && a.res_mode != RES_SAME) return false;
+  if (a.residual) return false;  // identity skips arrive as a unit-weight 1x1x1 source (fold_identity)
   StripPlan t{};
   t.Wb = 0;
   for (int d = std::min(a.Wo, 96); d >= 24; --d)
@@ -1174,7 +1157,7 @@ bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
   t.num_tiles = (int)tiles;
   t.strip_bytes = (uint32_t)(t.nh * t.Wp * 128);
   t.strip_stride = (t.strip_bytes + 1023u) & ~1023u;
-  const size_t cs = want_chsum ? CS_TR_BYTES / 2 + (size_t)4 * a.B * a.Cout * 2 * sizeof(float) : 0;
+  const size_t cs = CS_TR_BYTES / 2 + (want_chsum ? (size_t)a.B * a.Cout * 2 * sizeof(float) : 0);  // the transpose scratch is always needed
   for (int nw : {4, 3}) {
     t.NW = nw;
     t.smem = (size_t)2 * t.strip_stride + (size_t)nw * 128 * BK * 2 + 1024 + cs;
@@ -1230,7 +1213,7 @@ int conv_tc_strip(ConvArgs& a, const StripPlan& plan, bool chsum, cudaStream_t s
   for (int e = 0; e < a.n_extra; ++e)
     DD_TRY(make_act_map(&maps[1 + e], tdt, a.extra[e].ptr, a.B, a.Z, a.Ho, a.Wo, a.extra[e].C, plan.Wp, plan.nh, 1));
   CUtensorMap mapW;
-  DD_TRY(make_w_map(&mapW, tdt, a.w, a.Cout, Ktot, 128));
+  DD_TRY(make_w_map(&mapW, tdt, a.w, a.Cout, a.w_ld ? a.w_ld : Ktot, 128));
   if (a.dt == DDPM3D_BF16) return plan.NW == 4 ? launch_strip<bf16, 4>(maps, mapW, p, plan, s) : launch_strip<bf16, 3>(maps, mapW, p, plan, s);
   return plan.NW == 4 ? launch_strip<f16, 4>(maps, mapW, p, plan, s) : launch_strip<f16, 3>(maps, mapW, p, plan, s);
 }
@@ -1327,7 +1310,7 @@ int conv_tc(ConvArgs& a, cudaStream_t s) {
     DD_TRY(make_act_map(&maps[1 + e], tdt, a.extra[e].ptr, a.B, a.Z, a.Ho, a.Wo, a.extra[e].C, p.bw, p.bh, p.bz));
   CUtensorMap mapW;
   const int cl = (!p.sk && a.cluster_allowed && p.num_tiles / p.nNt >= 2 * sm_count()) ? 2 : 1;
-  DD_TRY(make_w_map(&mapW, tdt, a.w, a.Cout, Ktot, BN / cl));
+  DD_TRY(make_w_map(&mapW, tdt, a.w, a.Cout, a.w_ld ? a.w_ld : Ktot, BN / cl));
   if (a.dt == DDPM3D_BF16) {
     if (MT == 2) return launch<bf16, 2, 128, 4>(maps, mapW, p, s, cl);
     if (BN == 256) return launch<bf16, 1, 256, 4>(maps, mapW, p, s, cl);

@@ -166,7 +166,7 @@ struct ddpm3d_ctx {
   float* d_img = nullptr;
   size_t img_cap = 0;
   // options
-  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 0;
+  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 0, fold_identity = 0;
   float* splitk_buf = nullptr;  // fp32 partial tiles of split-K convolutions (sized by the dry run)
   size_t splitk_cap = 0, splitk_need = 0;
   cudaStream_t cap_stream = nullptr;
@@ -362,7 +362,7 @@ int upload_f32(ddpm3d_ctx* ctx, const std::string& key, float** out) {
 
 // [Cout][Cin][taps] (reference) -> [Cout][taps*Cin (+ Cskip)], element type dt; bias (+ skip bias) fp32
 int pack_conv(ddpm3d_ctx* ctx, int dt, const std::string& wkey, const std::string& bkey, int taps,
-              const std::string* skip_w, const std::string* skip_b, DevConv* out) {
+              const std::string* skip_w, const std::string* skip_b, DevConv* out, bool append_identity = false) {
   const Param* w = find(ctx, wkey);
   const Param* b = find(ctx, bkey);
   DD_CHECK(w && w->loaded, DDPM3D_ERR_MISSING, "missing state_dict tensor: " + wkey);
@@ -378,8 +378,11 @@ int pack_conv(ddpm3d_ctx* ctx, int dt, const std::string& wkey, const std::strin
     DD_CHECK(sb && sb->loaded, DDPM3D_ERR_MISSING, "missing state_dict tensor: " + *skip_b);
     Cs = sw->shape[1];
   }
+  // append_identity: skip_connection = Identity written as a 1x1x1 conv with unit weights, so that the residual
+  // can be folded into the accumulation like a real skip conv (x * 1.0 is exact in the fp32 accumulator)
+  if (append_identity) Cs = Cout;
   const int64_t Ktot = taps * Cin + Cs;
-  std::vector<float> packed((size_t)(Cout * Ktot));
+  std::vector<float> packed((size_t)(Cout * Ktot), 0.f);
   for (int64_t co = 0; co < Cout; ++co) {
     float* row = packed.data() + co * Ktot;
     const float* src = w->host.data() + co * Cin * taps;
@@ -387,6 +390,8 @@ int pack_conv(ddpm3d_ctx* ctx, int dt, const std::string& wkey, const std::strin
       for (int t = 0; t < taps; ++t) row[(int64_t)t * Cin + ci] = src[ci * taps + t];
     if (sw)
       for (int64_t ci = 0; ci < Cs; ++ci) row[taps * Cin + ci] = sw->host[co * Cs + ci];
+    else if (append_identity)
+      row[taps * Cin + co] = 1.0f;
   }
   std::vector<float> bias(b->host);
   if (sb)
@@ -419,7 +424,10 @@ int finalize_layer(ddpm3d_ctx* ctx, Layer& L, std::vector<float>& emb_w, std::ve
       const std::string sw = p + ".skip_connection.weight", sb = p + ".skip_connection.bias";
       DD_TRY(pack_conv(ctx, dt, p + ".out_layers.3.weight", p + ".out_layers.3.bias", 27, &sw, &sb, &L.c2));
     } else {
-      DD_TRY(pack_conv(ctx, dt, p + ".out_layers.3.weight", p + ".out_layers.3.bias", 27, nullptr, nullptr, &L.c2));
+      // identity skip: the unit block is appended (w_ld grows by Cout); it is only read when the residual is
+      // folded into the accumulation (fold_identity), otherwise the epilogue adds x and the block is skipped
+      const bool ident = !L.up && !L.down && L.cin == L.cout;
+      DD_TRY(pack_conv(ctx, dt, p + ".out_layers.3.weight", p + ".out_layers.3.bias", 27, nullptr, nullptr, &L.c2, ident));
     }
     const Param* ew = find(ctx, p + ".emb_layers.1.weight");
     const Param* eb = find(ctx, p + ".emb_layers.1.bias");
@@ -618,9 +626,13 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   if (L.skip_conv) {  // skip_connection (1x1x1) folded into the same accumulation, reading the concat halves in place
     c2.n_extra = nsrc;
     for (int i = 0; i < nsrc; ++i) c2.extra[i] = {src[i].p, src[i].C};
+  } else if (!L.up && !L.down && ctx->fold_identity && is_half_dt(dt)) {
+    c2.n_extra = 1;  // Identity skip as a unit-weight 1x1x1 source: no residual traffic in the epilogue
+    c2.extra[0] = {src[0].p, src[0].C};
   } else {
     c2.residual = src[0].p;
     c2.res_mode = L.down ? RES_POOL : (L.up ? RES_UP : RES_SAME);
+    if (!L.up && !L.down) c2.w_ld = 27 * L.cout + L.cout;  // skip the appended unit block
   }
   c2.chsum_out = out_cs;
   DD_TRY(R.conv(c2));
@@ -1314,6 +1326,7 @@ int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value) {
   else if (n == "split_k") ctx->split_k = value != 0;
   else if (n == "cluster") ctx->cluster = value != 0;
   else if (n == "strip") ctx->strip = value != 0;
+  else if (n == "fold_identity") ctx->fold_identity = value != 0;
   else { set_error("unknown option: " + n); return DDPM3D_ERR_ARG; }
   // cached graphs bake the options in
   if (ctx->device >= 0) {

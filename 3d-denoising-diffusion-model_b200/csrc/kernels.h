@@ -25,7 +25,8 @@ struct ConvArgs {
   int stride_hw = 1;          // Downsample(use_conv=True): (1,2,2)  (unet.py:129-133)
   ConvSrc extra[2];           // 1x1x1 sources appended along K (skip_connection folded in; K11 concat elision)
   int n_extra = 0;
-  const void* w = nullptr;    // [Cout][Ktot], Ktot = taps*main.C + sum(extra.C); k = tap*C + ci
+  const void* w = nullptr;    // [Cout][w_ld], first Ktot = taps*main.C + sum(extra.C) columns used; k = tap*C + ci
+  int w_ld = 0;               // row pitch of w in elements (0 = Ktot)
   const float* bias = nullptr;  // [Cout] (already includes the folded skip bias)
   const void* residual = nullptr;  // element type dt
   int res_mode = RES_NONE;

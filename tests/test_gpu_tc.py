@@ -106,3 +106,31 @@ def test_fused_groupnorm_statistics_agree_with_the_separate_pass():
         assert torch.equal(a, b)
         outs[fuse] = a
     assert max_rel(outs[1], outs[0]) <= 3e-3
+
+
+@pytest.mark.parametrize("opts", [dict(strip=1, fold_identity=1), dict(fold_identity=1), dict(strip=1), dict(cluster=1)])
+def test_c2_architecture_with_kernel_options(opts):
+    """The optional kernel variants (strip staging with swapped MMA operands, identity skips folded into the
+    accumulation as unit-weight 1x1x1 sources, weight multicast in 2-CTA clusters) on the shipped network:
+    same parity bound against the CPU oracle as the default path."""
+    from oracle.unet import unet_forward
+    from oracle.weights import synth_state_dict
+    from ddpm3d_b200 import script_util as su
+    flags = cases.sr_flags(use_fp16=True)
+    cfg = cases.cfg_from_flags(flags)
+    sd = synth_state_dict(cfg, seed=4)
+    model, _ = su.sr_create_model_and_diffusion(**flags)
+    model.load_state_dict(sd)
+    model.to(DEV)
+    model.convert_to_fp16()
+    model.eval()
+    for k, v in opts.items():
+        model.set_option(k, v)
+    shape = (1, 1, 8, 96, 96)
+    low, x, _ = synth_inputs(shape, 0)
+    t = torch.tensor([777])
+    want = unet_forward(cfg, sd, x, t, low)
+    out = model(x.to(DEV), t.to(DEV), low_res=low.to(DEV)).cpu()
+    err = max_rel(out, want)
+    print(f"C2 architecture, options {opts}: eps max-rel {err:.3e}")
+    assert err <= TOL[True], err
