@@ -548,9 +548,10 @@ struct StripParams {
   int nsrc, chunks[3], n_macro_main, n_macro, Cin;
   uint32_t strip_bytes, strip_stride;  // bytes delivered per strip / smem distance between the two strip buffers
   const float* bias;
-  const void* res;   // RES_SAME residual or NULL
+  const void* res;   // residual (applied after the transpose, voxel-major) or NULL
+  int res_mode;
   void* out;
-  float* chsum;
+  float* chsum;      // only without a residual (the sums are taken channel-major, before the transpose)
   uint32_t cs_off;
 };
 
@@ -765,7 +766,33 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
           asm volatile("bar.sync %0, 64;" ::"r"(2 + (sub >> 1)) : "memory");
         }
         if (valid) {
-          T* op = (T*)p.out + vox * p.Cout + n0 + sub * 32;
+          const int cb = n0 + sub * 32;
+          if (p.res_mode == RES_SAME) {
+            const T* rp = (const T*)p.res + vox * p.Cout + cb;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) add8<T>(v + 8 * i, rp + 8 * i, 1.0f);
+          } else if (p.res_mode == RES_POOL) {  // residual = AvgPool(1,2,2) of a (2H, 2W) tensor
+            const int Wr = 2 * p.W;
+            const int64_t r0 = (((int64_t)b * p.Z + z) * (2 * p.H) + 2 * hq) * Wr + 2 * w;
+            float sacc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sacc[i] = 0.f;
+            const int64_t offs[4] = {r0, r0 + 1, r0 + Wr, r0 + Wr + 1};
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+              const T* rp = (const T*)p.res + offs[qd] * p.Cout + cb;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) add8<T>(sacc + 8 * i, rp + 8 * i, 1.0f);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += 0.25f * sacc[i];
+          } else if (p.res_mode == RES_UP) {  // residual = nearest x2 of a (H/2, W/2) tensor
+            const int64_t r0 = (((int64_t)b * p.Z + z) * (p.H / 2) + hq / 2) * (p.W / 2) + w / 2;
+            const T* rp = (const T*)p.res + r0 * p.Cout + cb;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) add8<T>(v + 8 * i, rp + 8 * i, 1.0f);
+          }
+          T* op = (T*)p.out + vox * p.Cout + cb;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint32_t w4[4];
@@ -1139,7 +1166,7 @@ bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
   if (a.Cout % 128 != 0 || a.main.C % BK != 0) return false;
   for (int e = 0; e < a.n_extra; ++e)
     if (a.extra[e].C % BK != 0) return false;
-  if (a.residual) return false;  // identity skips arrive as a unit-weight 1x1x1 source (fold_identity)
+  if (a.residual && a.res_mode == RES_UP && (a.Ho % 2 || a.Wo % 2)) return false;
   StripPlan t{};
   t.Wb = 0;
   for (int d = std::min(a.Wo, 96); d >= 24; --d)
@@ -1151,6 +1178,7 @@ bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
   t.nh = 3 + (int)ceil_div(128 * NB + 1, t.Wp);
   if (t.nh > 256) return false;
   t.tiles_per_band = (int)ceil_div((int64_t)a.Ho * t.Wp, 128 * NB);
+  if ((double)a.Ho * t.Wb < 0.88 * t.tiles_per_band * 128 * NB) return false;  // pad columns + ragged last tile
   t.nNt = a.Cout / 128;
   const int64_t tiles = (int64_t)a.B * a.Z * t.nbands * t.tiles_per_band * t.nNt;
   if (tiles < 2 * (int64_t)sm_count() || tiles >= ((int64_t)1 << 31)) return false;
@@ -1201,7 +1229,9 @@ int conv_tc_strip(ConvArgs& a, const StripPlan& plan, bool chsum, cudaStream_t s
   p.strip_stride = plan.strip_stride;
   p.bias = a.bias;
   p.res = a.residual;
+  p.res_mode = a.residual ? a.res_mode : RES_NONE;
   p.out = a.out;
+  if (a.residual) chsum = false;
   p.chsum = chsum ? a.chsum_out : nullptr;
   p.cs_off = (uint32_t)((size_t)2 * plan.strip_stride + (size_t)plan.NW * 128 * BK * 2 + 1024);
   a.chsum_written = chsum ? 1 : 0;

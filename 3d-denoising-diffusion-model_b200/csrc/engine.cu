@@ -166,7 +166,7 @@ struct ddpm3d_ctx {
   float* d_img = nullptr;
   size_t img_cap = 0;
   // options
-  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 0, fold_identity = 0;
+  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 1, fold_identity = 1;
   float* splitk_buf = nullptr;  // fp32 partial tiles of split-K convolutions (sized by the dry run)
   size_t splitk_cap = 0, splitk_need = 0;
   cudaStream_t cap_stream = nullptr;
