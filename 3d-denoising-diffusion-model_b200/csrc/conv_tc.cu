@@ -545,6 +545,7 @@ constexpr int STRIP_THREADS = 224;  // warp 0 strip producer, 1 MMA, 2-5 epilogu
 struct StripParams {
   int B, Z, H, W, Cout;
   int Wb, Wp, nbands, nh, tiles_per_band, nNt, num_tiles, zoff;
+  int NV;            // voxels (padded-flattened positions) per tile = the MMA N: a multiple of 16, <= 256
   int nsrc, chunks[3], n_macro_main, n_macro, Cin;
   uint32_t strip_bytes, strip_stride;  // bytes delivered per strip / smem distance between the two strip buffers
   const float* bias;
@@ -607,7 +608,7 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     z = m % p.Z;
     b = m / p.Z;
     w0 = band * p.Wb;
-    q0 = tq * (128 * NB);
+    q0 = tq * p.NV;
     n0 = nt * BN;
   };
   // first strip row (may be negative: rows above the plane arrive as zeros)
@@ -670,7 +671,7 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
   } else if (warp == 1) {
     // ===================================== MMA issuer =========================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, 128 * NB, sizeof(T) == 2 && !std::is_same<T, f16>::value);
+      const uint32_t idesc = make_idesc(128, p.NV, sizeof(T) == 2 && !std::is_same<T, f16>::value);
       int sb = 0, ws = 0, acc = 0;
       uint32_t sph = 0, wph = 0, aph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -735,14 +736,14 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * ACC_COLS);
 #pragma unroll 1
-      for (int vc = 0; vc < NB * 4; ++vc) {
+      for (int vc = 0; vc * 32 < p.NV; ++vc) {
         uint32_t r[32];
         tmem_ld32(t_row + (uint32_t)(vc * 32), r);
         // the voxel this thread will store after the transpose
         const int q = q0 + vc * 32 + lane;
         const int hq = q / p.Wp, wq = q - hq * p.Wp;
         const int w = w0 + wq - 1;
-        const bool valid = wq >= 1 && wq <= p.Wb && hq < p.H && w < p.W;
+        const bool valid = vc * 32 + lane < p.NV && wq >= 1 && wq <= p.Wb && hq < p.H && w < p.W;
         const int64_t vox = (((int64_t)b * p.Z + z) * p.H + hq) * p.W + w;
         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
         tmem_ld_wait();
@@ -1156,7 +1157,7 @@ TcPlan make_plan(const ConvArgs& a, int nk) {
 namespace {
 
 struct StripPlan {
-  int Wb, Wp, nbands, nh, tiles_per_band, nNt, num_tiles, NW;
+  int Wb, Wp, nbands, nh, tiles_per_band, nNt, num_tiles, NW, NV;
   uint32_t strip_bytes, strip_stride;
   size_t smem;
 };
@@ -1172,13 +1173,18 @@ bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
   for (int d = std::min(a.Wo, 96); d >= 24; --d)
     if (a.Wo % d == 0) { t.Wb = d; break; }
   if (!t.Wb) return false;
-  constexpr int NB = 2;
   t.Wp = t.Wb + 2;
   t.nbands = a.Wo / t.Wb;
-  t.nh = 3 + (int)ceil_div(128 * NB + 1, t.Wp);
+  // tile length NV (= MMA N): the multiple of 16 in [192, 256] that wastes the least of the padded plane
+  double best_eff = 0.0;
+  for (int nv = 256; nv >= 192; nv -= 16) {
+    const int tpb = (int)ceil_div((int64_t)a.Ho * t.Wp, nv);
+    const double eff = (double)a.Ho * t.Wb / ((double)tpb * nv) * (nv >= 224 ? 1.0 : 0.97);
+    if (eff > best_eff + 0.015) { best_eff = eff; t.NV = nv; t.tiles_per_band = tpb; }  // prefer the longest tile
+  }
+  if (best_eff < 0.88) return false;  // pad columns + ragged last tile
+  t.nh = 3 + (int)ceil_div(t.NV + 1, t.Wp);
   if (t.nh > 256) return false;
-  t.tiles_per_band = (int)ceil_div((int64_t)a.Ho * t.Wp, 128 * NB);
-  if ((double)a.Ho * t.Wb < 0.88 * t.tiles_per_band * 128 * NB) return false;  // pad columns + ragged last tile
   t.nNt = a.Cout / 128;
   const int64_t tiles = (int64_t)a.B * a.Z * t.nbands * t.tiles_per_band * t.nNt;
   if (tiles < 2 * (int64_t)sm_count() || tiles >= ((int64_t)1 << 31)) return false;
@@ -1214,6 +1220,7 @@ int conv_tc_strip(ConvArgs& a, const StripPlan& plan, bool chsum, cudaStream_t s
   p.B = a.B; p.Z = a.Z; p.H = a.Ho; p.W = a.Wo; p.Cout = a.Cout;
   p.Wb = plan.Wb; p.Wp = plan.Wp; p.nbands = plan.nbands; p.nh = plan.nh; p.tiles_per_band = plan.tiles_per_band;
   p.nNt = plan.nNt; p.num_tiles = plan.num_tiles; p.zoff = a.in_zpad;
+  p.NV = plan.NV;
   p.nsrc = 1 + a.n_extra;
   p.chunks[0] = a.main.C / BK;
   p.Cin = a.main.C;
