@@ -386,8 +386,15 @@ def main():
         dom = "conv_tcgen05" if breakdown.get("conv_tcgen05", {}).get("ms", 0) > 0 else "conv_simt"
         d = breakdown[dom]
         achieved = d["work"] / (d["ms"] * 1e-3) / 1e12
+        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (96^3 128->128 convolution, 782.8 GFLOP,
+        # algorithmic 226 MB in + 226 MB out + 0.9 MB weights) from the ncu --set full capture in
+        # profiles/r1k_conv_tc_ncu_full.txt; only meaningful for the default shape
+        traffic = 227427584 + 183572480 if (dom == "conv_tcgen05" and shape == PATCH) else None
         roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": None, "peak_source": which,
+                    "frac": achieved / peak_tf, "traffic": traffic,
+                    "traffic_note": "DRAM bytes of the dominant launch (96^3 128->128 conv) from profiles/r1k_conv_tc_ncu_full.txt; "
+                                    "achieved/frac are over all 70 conv launches of the step",
+                    "peak_source": which,
                     "share_of_step": d["ms"] / sum(b["ms"] for b in breakdown.values()),
                     "launches_per_step": d["launches"]}
         hbm = peaks.get("hbm_gbs", 6650.0)
