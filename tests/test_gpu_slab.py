@@ -26,10 +26,12 @@ def _worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     res = {}
     try:
-        for mode, shape, tol in ((False, (1, 1, 10, 16, 16), 2e-5), (False, (2, 1, 9, 16, 32), 2e-5),
-                                 (True, (1, 1, 12, 32, 32), 3e-2)):
-            over = dict(large_size=16, small_size=16, num_channels=64, num_res_blocks=2, num_head_channels=64,
-                        timestep_respacing="10", use_fp16=bool(mode))
+        # the last case is the shipped network on 96x96 planes: 8 planes per rank make 296 strip tiles, so the
+        # halo planes are read by the strip kernel's row-shifted descriptors (the C4 bench configuration)
+        for mode, shape, tol, ch in ((False, (1, 1, 10, 16, 16), 2e-5, 64), (False, (2, 1, 9, 16, 32), 2e-5, 64),
+                                     (True, (1, 1, 12, 32, 32), 3e-2, 64), (True, (1, 1, 16, 96, 96), 3e-2, 128)):
+            over = dict(large_size=16, small_size=16, num_channels=ch, num_res_blocks=2, num_head_channels=64,
+                        timestep_respacing="10" if ch == 64 else "3", use_fp16=bool(mode))
             flags = cases.sr_flags(**over)
             cfg = cases.cfg_from_flags(flags)
             sd = synth_state_dict(cfg, seed=11)
@@ -85,4 +87,6 @@ def test_slab_sharding_matches_single_gpu():
             assert e1 <= tol, (key, e1)
             # fp32: only the GroupNorm summation order differs; bf16: two roundings-equivalent evaluations
             # of a 10-step loop (the C1 bf16-vs-fp32 loop NRMSE is 8e-3, tests/test_gpu_model.py)
+            if "96, 96" in key:
+                continue  # 3-step loop of the big case: only the forward parity is asserted
             assert e2 <= (1e-4 if tol < 1e-3 else 5e-2), (key, e2)
