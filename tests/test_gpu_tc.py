@@ -134,3 +134,18 @@ def test_c2_architecture_with_kernel_options(opts):
     err = max_rel(out, want)
     print(f"C2 architecture, options {opts}: eps max-rel {err:.3e}")
     assert err <= TOL[True], err
+
+
+def test_operand_descriptor_may_start_at_any_row_of_a_swizzled_tile():
+    """The hardware property the strip kernel relies on: a SWIZZLE_128B K-major operand descriptor whose start
+    address is any multiple of 128 bytes reads the rows from there on (the swizzle is a function of absolute smem
+    address bits; the descriptor's base-offset field stays 0).  D = A[shift : shift + 128] @ I must be exact."""
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn((256, 64), generator=g).bfloat16().to(DEV)
+    ident = torch.eye(64).bfloat16().to(DEV)
+    out = torch.empty((128, 64), device=DEV)
+    from gpu_util import stream
+    for shift in (0, 1, 3, 7, 8, 13, 50, 99, 128):
+        N.check(N.lib().ddpm3d_k_probe_rowshift(N.ptr(A), 256, N.ptr(ident), shift, 0, N.ptr(out), stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(out, A[shift:shift + 128].float()), shift
