@@ -1,9 +1,8 @@
 // QKV attention core (unet.py:328-393) on channels-last tokens, online softmax in fp32.
 //
 // Attention is OFF at the shipped flags (attention_resolutions=1000 -> ds=0 never matches and the
-// middle-block attention is commented out, unet.py:876-882), so this first version is a simple
-// CUDA-core flash-style kernel that exists for drop-in completeness and parity; the tcgen05
-// version is a later-round item.
+// middle-block attention is commented out, unet.py:876-882).  This CUDA-core flash-style kernel serves fp32
+// mode and head widths other than 64; 16-bit models with 64-wide heads run attention_tc.cu (tcgen05).
 #include "kernels.h"
 
 namespace ddpm3d {
@@ -79,8 +78,11 @@ int launch(const void* qkv, void* out, int B, int T_tok, int C, int heads, int n
 
 }  // namespace
 
-int attention_k(int dt, const void* qkv, void* out, int B, int T_tok, int C, int heads, int new_order, cudaStream_t s) {
+int attention_k(int dt, const void* qkv, void* out, int B, int T_tok, int C, int heads, int new_order, void* scratch,
+                size_t scratch_bytes, cudaStream_t s) {
   DD_CHECK(heads > 0 && C % heads == 0, DDPM3D_ERR_ARG, "attention: C must be divisible by heads");
+  const size_t need = attention_tc_scratch_bytes(dt, B, T_tok, C, heads);
+  if (need > 0 && scratch && scratch_bytes >= need) return attention_tc(dt, qkv, out, B, T_tok, C, heads, new_order, scratch, s);
   if (dt == DDPM3D_BF16) return launch<bf16>(qkv, out, B, T_tok, C, heads, new_order, s);
   if (dt == DDPM3D_FP16) return launch<f16>(qkv, out, B, T_tok, C, heads, new_order, s);
   return launch<float>(qkv, out, B, T_tok, C, heads, new_order, s);

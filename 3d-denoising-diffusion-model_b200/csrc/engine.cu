@@ -658,11 +658,14 @@ int run_attn(Run& R, const Layer& L, const Act& x, Act* out) {
   c.dt = dt; c.main = {n, C}; c.taps = 1; c.w = L.c1.w; c.bias = L.c1.bias; c.out = qkv; c.Ho = H; c.Wo = W; c.Cout = 3 * C;
   DD_TRY(R.conv(c));
   void* a = R.arena.alloc(R.act_bytes(H, W, C));
-  ++R.launches;
+  const size_t at_bytes = ctx->conv_path == 1 ? 0 : attention_tc_scratch_bytes(dt, R.B, R.Z * H * W, C, L.heads);
+  void* at_scratch = at_bytes ? R.arena.alloc(at_bytes) : nullptr;
+  R.launches += at_bytes ? 2 : 1;
   if (!R.arena.dry) {
     const double T = (double)R.Z * H * W;
     R.prof_begin(7, 4.0 * R.B * T * T * C);
-    const int r = attention_k(dt, qkv, a, R.B, R.Z * H * W, C, L.heads, ctx->cfg.use_new_attention_order, R.s);
+    const int r = attention_k(dt, qkv, a, R.B, R.Z * H * W, C, L.heads, ctx->cfg.use_new_attention_order, at_scratch, at_bytes,
+                              R.s);
     R.prof_end();
     DD_TRY(r);
   }
@@ -1418,7 +1421,12 @@ int ddpm3d_k_timestep_embedding(const float* t, const float* freqs, float* out, 
 
 int ddpm3d_k_attention(int dtype, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, void* stream) {
   DD_CHECK(qkv && out, DDPM3D_ERR_ARG, "k_attention: null argument");
-  return attention_k(dtype, qkv, out, B, T, C, heads, new_order, (cudaStream_t)stream);
+  const int path = new_order >> 8;  // bits 8..: 1 forces the CUDA-core kernel (unit tests cross-check the two)
+  new_order &= 0xff;
+  const size_t need = path == 1 ? 0 : attention_tc_scratch_bytes(dtype, B, T, C, heads);
+  void* sc = nullptr;
+  if (need) DD_TRY(g_scratch.get(need, &sc));
+  return attention_k(dtype, qkv, out, B, T, C, heads, new_order, sc, need, (cudaStream_t)stream);
 }
 
 }  // extern "C"

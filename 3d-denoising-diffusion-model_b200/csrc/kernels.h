@@ -149,6 +149,11 @@ int step_from_tensor_k(const int64_t* t, int32_t* t_index, float* t_model, const
 int step_advance_k(int32_t* step_counter, float* t_model, const ddpm3d_step_scalars* table, int B, cudaStream_t s);
 
 // ---- attention core (K12) --------------------------------------------------------------------
-int attention_k(int dt, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, cudaStream_t s);
+// scratch (optional): attention_tc_scratch_bytes() bytes for the tensor-core path (64-wide heads, 16-bit types);
+// without it, or for other head widths / fp32, the CUDA-core kernel runs
+int attention_k(int dt, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, void* scratch,
+                size_t scratch_bytes, cudaStream_t s);
+size_t attention_tc_scratch_bytes(int dt, int B, int T, int C, int heads);
+int attention_tc(int dt, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, void* scratch, cudaStream_t s);
 
 }  // namespace ddpm3d

@@ -231,7 +231,8 @@ int ddpm3d_k_groupnorm(int dtype, const void* in, const float* gamma, const floa
  * [dim/2] host-computed table (see ddpm3d_set_timestep_freqs) or NULL to evaluate exp() on the device. */
 int ddpm3d_k_timestep_embedding(const float* t, const float* freqs, float* out, int B, int dim, void* stream);
 
-/* QKVAttentionLegacy / QKVAttention core (unet.py:328-393): qkv [B][T][3C] channels-last -> out [B][T][C]. */
+/* QKVAttentionLegacy / QKVAttention core (unet.py:328-393): qkv [B][T][3C] channels-last -> out [B][T][C].
+ * 16-bit types with 64-wide heads run the fused tcgen05 kernel; new_order | 0x100 forces the CUDA-core kernel. */
 int ddpm3d_k_attention(int dtype, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, void* stream);
 
 /* ---- the steps either side of the loop (scripts/test.py) and the ensemble reduction ----------------

@@ -131,7 +131,11 @@ def test_p_sample_update_matches_reference(golden_dir, i):
 
 
 @pytest.mark.parametrize("dt", [N.FP32, N.BF16, N.FP16])
-@pytest.mark.parametrize("B,T,C,heads,new_order", [(1, 64, 64, 4, 0), (2, 100, 32, 1, 1), (1, 300, 128, 2, 0)])
+@pytest.mark.parametrize("B,T,C,heads,new_order", [
+    (1, 64, 64, 4, 0), (2, 100, 32, 1, 1), (1, 300, 128, 2, 0),
+    # 64-wide heads: the fused tcgen05 kernel for 16-bit types (T = 300 exercises the key / query tail masks)
+    (2, 256, 64, 1, 1), (1, 1000, 192, 3, 0), (1, 3456, 512, 8, 0),
+])
 def test_attention_core(dt, B, T, C, heads, new_order):
     """QKVAttentionLegacy / QKVAttention (unet.py:328-393)."""
     g = torch.Generator().manual_seed(T + C)
@@ -152,6 +156,12 @@ def test_attention_core(dt, B, T, C, heads, new_order):
                                        B, T, C, heads, new_order, stream()))
     torch.cuda.synchronize()
     tol = ROUND_TOL[dt]
+    if dt != N.FP32 and C // heads == 64:
+        tol *= 3  # tensor-core path: P is rounded to 16 bits before the PV product (like the reference's fp16 einsum)
+        simt = torch.empty_like(out)
+        N.check(N.lib().ddpm3d_k_attention(dt, N.ptr(qd), N.ptr(simt), B, T, C, heads, new_order | 0x100, stream()))
+        torch.cuda.synchronize()
+        assert max_rel(out.float().cpu(), simt.float().cpu()) <= tol
     assert max_rel(out.float().permute(0, 2, 1).cpu(), ref) <= tol
 
 
