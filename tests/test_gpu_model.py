@@ -183,3 +183,21 @@ def test_c2_architecture_matches_oracle(fp16):
     err = max_rel(out, want)
     print(f"C2 architecture, mode {fp16}: eps max-rel {err:.3e}")
     assert err <= TOL[fp16], err
+
+
+@pytest.mark.parametrize("fp16", [True, "fp16"])
+def test_unet_with_tensor_core_attention_matches_oracle(fp16):
+    """attention_resolutions on, 64-wide heads: the AttentionBlocks (unet.py:259-305) run GroupNorm -> 1x1x1 qkv conv
+    (tcgen05) -> fused tcgen05 attention -> 1x1x1 proj conv + residual; compared with the CPU oracle."""
+    over = dict(large_size=16, small_size=16, num_channels=64, num_res_blocks=1, num_head_channels=64,
+                attention_resolutions="8,4", timestep_respacing="10")
+    model, _, cfg, sd = build(over, seed=6, fp16=fp16)
+    shape = (1, 1, 8, 32, 32)  # attention at 16x16 and 8x8 planes: T = 2048 and 512 tokens
+    low, x, _ = synth_inputs(shape, 0)
+    t = torch.tensor([321])
+    want = unet_forward(cfg, sd, x, t, low)
+    model.set_option("profile", 1)
+    out = model(x.to(DEV), t.to(DEV), low_res=low.to(DEV)).cpu()
+    kinds = [k for k, _, _ in model.profile_read()]
+    assert kinds.count("attention") == 4  # ds = 2, 4 on the way down and up
+    assert max_rel(out, want) <= TOL[fp16]
