@@ -199,5 +199,5 @@ def test_unet_with_tensor_core_attention_matches_oracle(fp16):
     model.set_option("profile", 1)
     out = model(x.to(DEV), t.to(DEV), low_res=low.to(DEV)).cpu()
     kinds = [k for k, _, _ in model.profile_read()]
-    assert kinds.count("attention") == 4  # ds = 2, 4 on the way down and up
+    assert kinds.count("attention") == 6  # ds = 2 and 4: one block each on the way down, two each on the way up
     assert max_rel(out, want) <= TOL[fp16]
