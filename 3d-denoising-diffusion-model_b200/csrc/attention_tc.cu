@@ -252,10 +252,9 @@ int launch_attention(const void* qkv, void* out, void* scratch, const AttnParams
   DD_TRY(make_w_map(&mapQKV, tdt, qkv, p.B * p.T, 3 * p.C, 128));
   DD_TRY(make_w_map(&mapVt, tdt, scratch, p.B * p.H * CH, p.Tp, 64));
   const size_t smem = (size_t)5 * TILE_BYTES + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;
+  if (first_use_on_device(&configured)) {
     DD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   const int nq = (int)ceil_div(p.T, QT);
   attention_tc_kernel<T><<<p.B * p.H * nq, AT_THREADS, smem, s>>>(mapQKV, mapVt, p);

@@ -46,6 +46,16 @@ __host__ __device__ inline bool is_half_dt(int dt) { return dt == DDPM3D_BF16 ||
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute is per device: a launcher keeps one `uint64_t` mask and asks once per device
+inline bool first_use_on_device(uint64_t* mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+
 // ---- scalar conversions ------------------------------------------------------------------
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }

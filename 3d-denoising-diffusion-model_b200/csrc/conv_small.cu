@@ -207,11 +207,10 @@ int conv_head(const ConvArgs& a, cudaStream_t s) {
   const int nWt = (int)ceil_div(a.Wo, HW_), nHt = (int)ceil_div(a.Ho, HH_), nZt = (int)ceil_div(a.Z, HZ_);
   const int grid = a.B * nZt * nHt * nWt;
   const size_t smem = (size_t)2 * HIZ * HIH * HIW * sizeof(float4) + (size_t)27 * a.Cout * HCC * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;
+  if (first_use_on_device(&configured)) {
     DD_CUDA(cudaFuncSetAttribute(head_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     DD_CUDA(cudaFuncSetAttribute(head_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    configured = true;
   }
   if (a.Cout == 1)
     head_conv_kernel<1><<<grid, HEAD_THREADS, smem, s>>>((const float*)a.main.ptr, (const float*)a.w, a.bias, (float*)a.out,
@@ -233,12 +232,11 @@ int conv_stem(const ConvArgs& a, cudaStream_t s) {
   const int nWt = (int)ceil_div(a.Wo, SW_), nHt = (int)ceil_div(a.Ho, SH_), nZt = (int)ceil_div(a.Z, SZ_);
   const int grid = a.B * nZt * nHt * nWt;
   const size_t smem = (size_t)(54 + 1) * a.Cout * sizeof(float) + (size_t)SIZ * SIH * SIW * sizeof(float2);
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;
+  if (first_use_on_device(&configured)) {
     DD_CUDA(cudaFuncSetAttribute(stem_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     DD_CUDA(cudaFuncSetAttribute(stem_conv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     DD_CUDA(cudaFuncSetAttribute(stem_conv_kernel<f16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = true;
   }
   if (a.dt == DDPM3D_BF16)
     stem_conv_kernel<bf16><<<grid, STEM_THREADS, smem, s>>>((const bf16*)a.main.ptr, (const bf16*)a.w, a.bias, (bf16*)a.out,

@@ -804,10 +804,9 @@ int launch_cl(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& 
   constexpr size_t stage_smem = (size_t)NSTAGE * (MT * A_BYTES + BN * BK * 2) + 1024;
   constexpr size_t smem_max = stage_smem + CS_SMEM_MAX;
   static_assert(smem_max <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;
+  if (first_use_on_device(&configured)) {
     DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, MT, BN, NSTAGE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    configured = true;
   }
   int grid;
   if (p.sk) {
@@ -1031,10 +1030,9 @@ bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
 
 template <typename T, int NW>
 int launch_strip(const CUtensorMap* maps, const CUtensorMap& mapW, const StripParams& p, const StripPlan& plan, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;
+  if (first_use_on_device(&configured)) {
     DD_CUDA(cudaFuncSetAttribute(conv_tc_strip_kernel<T, 2, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
-    configured = true;
   }
   const int grid = std::min(p.num_tiles, sm_count());
   if (p.chsum && grid < CHSUM_SLOTS)

@@ -148,7 +148,7 @@ struct ddpm3d_ctx {
   float *emb_w_all = nullptr, *emb_b_all = nullptr;
   int emb_rows_total = 0;
   float *out_gn_g = nullptr, *out_gn_b = nullptr;
-  DevConv in_conv_unused, out_conv;  // out.2 (fp32 always)
+  DevConv out_conv;  // out.2 (fp32 always)
   // workspace
   char* ws = nullptr;
   size_t ws_cap = 0;
