@@ -39,8 +39,6 @@ def log(msg):
 
 def main():
     args = create_argparser().parse_args()
-    if args.use_ddim:
-        raise NotImplementedError("the DDIM sampler is a next-row item (SURVEY.md section 8f, N3)")
     dist_util.setup_dist()
     log("creating model...")
     model, diffusion = sr_create_model_and_diffusion(**args_to_dict(args, sr_model_and_diffusion_defaults().keys()))
@@ -55,9 +53,16 @@ def main():
     vol = io_formats.read_volume(args.base_samples)
     log(f"Using original data without normalization - min: {vol.min():.4f}, max: {vol.max():.4f}, std: {vol.std():.4f}")
     t0 = time.time()
+    sample_fn = None
+    if args.use_ddim:  # scripts/test_backup.py:63-71: same network, DDIM update with eta
+        def sample_fn(low_res):
+            shape = tuple(low_res.shape)
+            noise = th.randn(*shape, device=low_res.device)
+            return diffusion.ddim_sample_loop(model, shape, noise, clip_denoised=args.clip_denoised,
+                                              model_kwargs={"low_res": low_res}, eta=args.eta, rng=args.rng)
     with th.no_grad():
-        arr = volume.denoise_volume(model, diffusion, vol, resolution=args.large_size,
-                                    clip_denoised=args.clip_denoised, seed=10, log=log, rng=args.rng)
+        arr = volume.denoise_volume(model, diffusion, vol, resolution=args.large_size, clip_denoised=args.clip_denoised,
+                                    seed=10, log=log, sample_fn=sample_fn, **({} if args.use_ddim else {"rng": args.rng}))
     th.cuda.synchronize()
     log(f"sampling + blending took {time.time() - t0:.1f} s")
     if dist_util.get_rank() == 0:

@@ -77,3 +77,33 @@ def test_denoise_volume_flow_and_ensemble():
     low = volume.extract_patch(vd, origins[0], 16)
     mean, var, n = ensemble.ensemble_sample(model, diffusion, low, seeds=[10, 11, 12, 13])
     assert n == 4 and mean.shape == low.shape and float(var.min()) >= 0 and float(var.max()) > 0
+
+
+def test_ddim_loop_and_script_flags():
+    """ddim_sample_loop (gaussian_diffusion.py:625-707) through the native path: eta = 0 is deterministic given x_T
+    (no noise consumed matters), equals stepping ddim_sample by hand, and differs from the ancestral sampler."""
+    flags = cases.sr_flags(large_size=16, small_size=16, num_channels=32, num_res_blocks=1, num_head_channels=16,
+                           timestep_respacing="ddim5", use_fp16=False)
+    cfg = cases.cfg_from_flags(flags)
+    model, diffusion = su.sr_create_model_and_diffusion(**flags)
+    model.load_state_dict(synth_state_dict(cfg, seed=3))
+    model.to(DEV).eval()
+    shape = (1, 1, 4, 16, 16)
+    g = torch.Generator().manual_seed(1)
+    x_T = torch.randn(shape, generator=g).to(DEV)
+    low = torch.rand(shape, generator=g).to(DEV)
+    kw = {"low_res": low}
+    a = diffusion.ddim_sample_loop(model, shape, noise=x_T, model_kwargs=kw, eta=0.0)
+    b = diffusion.ddim_sample_loop(model, shape, noise=x_T, model_kwargs=kw, eta=0.0)
+    assert torch.equal(a, b) and torch.isfinite(a).all()
+    img = x_T
+    for i in range(diffusion.num_timesteps - 1, -1, -1):
+        img = diffusion.ddim_sample(model, img, torch.tensor([i], device=DEV), model_kwargs=kw, eta=0.0)["sample"]
+    assert torch.allclose(img, a, rtol=0, atol=1e-6)
+    torch.manual_seed(0)
+    c = diffusion.p_sample_loop(model, shape, noise=x_T, model_kwargs=kw)
+    assert not torch.equal(a, c)
+    # the ancestral sampler is unaffected by a previous DDIM call on the same context
+    torch.manual_seed(0)
+    d = diffusion.p_sample_loop(model, shape, noise=x_T, model_kwargs=kw)
+    assert torch.equal(c, d)
