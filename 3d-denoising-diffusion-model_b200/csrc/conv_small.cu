@@ -7,7 +7,10 @@
 //
 // Both stage a haloed input brick in shared memory (zero padding applied while staging) so every
 // input voxel is fetched from L2/HBM once per CTA and reused by the 27 taps from smem.
+#include <type_traits>
+
 #include "kernels.h"
+#include "tc_ptx.cuh"
 
 namespace ddpm3d {
 
@@ -195,6 +198,157 @@ stem_conv_kernel(const T* __restrict__ in, const T* __restrict__ w, const float*
   }
 }
 
+
+// =================================================================================================
+// stem on the tensor cores (16-bit modes): the 27 taps x 2 channels of a voxel are ONE 128-byte swizzle row
+// (K = 54, zero-padded to 64), so a tile of 128 voxels is a single M128 x N(Cout) x K64 tcgen05 accumulation.
+// The im2col rows cannot come from TMA (a row gathers 27 scattered 4-byte voxels), so each thread gathers its
+// voxel's row from L2 (the packed input is 4 bytes per voxel, L2-resident) and writes it in the SWIZZLE_128B
+// layout by hand.  Thread i owns A row i and TMEM lane i.  The kernel is bound by writing the output once;
+// several CTAs per SM overlap gather / MMA / store phases.
+// =================================================================================================
+constexpr int STEM_TC_THREADS = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(STEM_TC_THREADS)
+stem_tc_kernel(const uint32_t* __restrict__ in, const T* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
+               int Z, int H, int W, int Cout, int zp, uint32_t tmem_cols, int64_t total, int ntiles) {
+  extern __shared__ uint8_t stem_smem_raw[];
+  __shared__ uint64_t bar_storage;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_bias[256];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t raw = smem_u32(stem_smem_raw);
+  const uint32_t a_smem = (raw + 1023u) & ~1023u;     // [128 rows][128 B]
+  const uint32_t w_smem = a_smem + 128 * 128;         // [Cout rows][128 B]
+  uint8_t* a_ptr = stem_smem_raw + (a_smem - raw);
+  uint8_t* w_ptr = a_ptr + 128 * 128;
+  const uint32_t bar = smem_u32(&bar_storage);
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // weights [Cout][54] -> K-major swizzled rows of 64 (k = tap * 2 + ci; 54..63 zero)
+  for (int i = tid; i < Cout * 8; i += STEM_TC_THREADS) {
+    const int n = i >> 3, c = i & 7;
+    uint32_t v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = c * 8 + 2 * q;  // 54 is even: a pair is either fully inside or fully outside
+      v[q] = k < 54 ? *reinterpret_cast<const uint32_t*>(w + (int64_t)n * 54 + k) : 0u;
+    }
+    *reinterpret_cast<uint4*>(w_ptr + n * 128 + ((c ^ (n & 7)) << 4)) = make_uint4(v[0], v[1], v[2], v[3]);
+  }
+  for (int i = tid; i < Cout; i += STEM_TC_THREADS) s_bias[i] = bias[i];
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = make_idesc(128, Cout, sizeof(T) == 2 && std::is_same<T, bf16>::value);
+  const uint64_t adesc = make_sw128_desc(a_smem), wdesc = make_sw128_desc(w_smem);
+  const int Zp = Z + 2 * zp;
+  uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t m = (int64_t)tile * 128 + tid;
+    const bool live = m < total;
+    int x = 0, y = 0, z = 0, b = 0;
+    if (live) {
+      int64_t r = m;
+      x = (int)(r % W); r /= W;
+      y = (int)(r % H); r /= H;
+      z = (int)(r % Z);
+      b = (int)(r / Z);
+    }
+    uint32_t row[32];
+#pragma unroll
+    for (int tap = 0; tap < 27; ++tap) {
+      const int gz = z + tap / 9 - 1, gy = y + (tap / 3) % 3 - 1, gx = x + tap % 3 - 1;
+      const bool ok = live && gz >= -zp && gz < Z + zp && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+      row[tap] = ok ? __ldg(in + (((int64_t)b * Zp + gz + zp) * H + gy) * W + gx) : 0u;
+    }
+#pragma unroll
+    for (int tap = 27; tap < 32; ++tap) row[tap] = 0u;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      *reinterpret_cast<uint4*>(a_ptr + tid * 128 + ((c ^ (tid & 7)) << 4)) =
+          make_uint4(row[4 * c], row[4 * c + 1], row[4 * c + 2], row[4 * c + 3]);
+    fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async proxy
+    tc_fence_before();     // (also orders the previous tile's tcgen05.ld before this tile's MMA)
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(tmem, adesc + 2 * k, wdesc + 2 * k, idesc, k > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    T* op = out + m * Cout;
+    for (int c0 = 0; c0 < Cout; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int cc = 8 * j + 2 * q;
+            w4[q] = pack2<T>(__uint_as_float(r[cc]) + s_bias[c0 + cc], __uint_as_float(r[cc + 1]) + s_bias[c0 + cc + 1]);
+          }
+          *reinterpret_cast<uint4*>(op + c0 + 8 * j) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+  }
+}
+
+bool stem_tc_eligible(const ConvArgs& a) {
+  return is_half_dt(a.dt) && a.stem_tc_allowed && a.Cout % 32 == 0 && a.Cout <= 256 &&
+         (reinterpret_cast<uintptr_t>(a.main.ptr) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 3) == 0;
+}
+
+template <typename T>
+int stem_tc_launch(const ConvArgs& a, cudaStream_t s) {
+  const int64_t total = (int64_t)a.B * a.Z * a.Ho * a.Wo;
+  const int64_t ntiles = ceil_div(total, 128);
+  DD_CHECK(ntiles < ((int64_t)1 << 31), DDPM3D_ERR_ARG, "conv_stem: too many voxels");
+  uint32_t cols = 32;
+  while ((int)cols < a.Cout) cols *= 2;
+  const int per_sm = std::max(1, std::min(6, 512 / (int)cols));   // TMEM columns bound the co-resident CTAs
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sms * per_sm);
+  const size_t smem = 1024 + 128 * 128 + (size_t)a.Cout * 128;
+  static uint64_t configured = 0;
+  if (first_use_on_device(&configured)) {
+    DD_CUDA(cudaFuncSetAttribute(stem_tc_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    DD_CUDA(cudaFuncSetAttribute(stem_tc_kernel<f16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  }
+  stem_tc_kernel<T><<<grid, STEM_TC_THREADS, smem, s>>>((const uint32_t*)a.main.ptr, (const T*)a.w, a.bias, (T*)a.out, a.Z, a.Ho,
+                                                        a.Wo, a.Cout, a.in_zpad, cols, total, (int)ntiles);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
 }  // namespace
 
 bool conv_head_eligible(const ConvArgs& a) {
@@ -229,6 +383,7 @@ bool conv_stem_eligible(const ConvArgs& a) {
 
 int conv_stem(const ConvArgs& a, cudaStream_t s) {
   DD_CHECK(conv_stem_eligible(a), DDPM3D_ERR_ARG, "conv_stem: shape not eligible");
+  if (stem_tc_eligible(a)) return a.dt == DDPM3D_BF16 ? stem_tc_launch<bf16>(a, s) : stem_tc_launch<f16>(a, s);
   const int nWt = (int)ceil_div(a.Wo, SW_), nHt = (int)ceil_div(a.Ho, SH_), nZt = (int)ceil_div(a.Z, SZ_);
   const int grid = a.B * nZt * nHt * nWt;
   const size_t smem = (size_t)(54 + 1) * a.Cout * sizeof(float) + (size_t)SIZ * SIH * SIW * sizeof(float2);

@@ -166,7 +166,7 @@ struct ddpm3d_ctx {
   float* d_img = nullptr;
   size_t img_cap = 0;
   // options
-  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 1, fold_identity = 1;
+  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 1, fold_identity = 1, stem_tc = 1;
   float* splitk_buf = nullptr;  // fp32 partial tiles of split-K convolutions (sized by the dry run)
   size_t splitk_cap = 0, splitk_need = 0;
   cudaStream_t cap_stream = nullptr;
@@ -498,6 +498,7 @@ struct Run {
     a.splitk_allowed = ctx->split_k;
     a.cluster_allowed = ctx->cluster;
     a.strip_allowed = ctx->strip;
+    a.stem_tc_allowed = ctx->stem_tc;
     ++launches;
     if (arena.dry) {
       if (is_half_dt(a.dt) && ctx->conv_path != 1 && a.splitk_allowed)
@@ -1330,6 +1331,7 @@ int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value) {
   else if (n == "cluster") ctx->cluster = value != 0;
   else if (n == "strip") ctx->strip = value != 0;
   else if (n == "fold_identity") ctx->fold_identity = value != 0;
+  else if (n == "stem_tc") ctx->stem_tc = value != 0;
   else { set_error("unknown option: " + n); return DDPM3D_ERR_ARG; }
   // cached graphs bake the options in
   if (ctx->device >= 0) {
@@ -1389,6 +1391,11 @@ int ddpm3d_k_conv3d(int dtype, int path, const void* in, const void* w, const fl
       a.splitk_bytes = need;
     }
     return conv_tc(a, (cudaStream_t)stream);
+  }
+  if (path == 3 || path == 4) {  // the Cin == 2 stem: 3 = tensor-core tile per 128 voxels (16-bit), 4 = CUDA cores
+    DD_CHECK(conv_stem_eligible(a), DDPM3D_ERR_ARG, "k_conv3d: shape not eligible for the stem kernels");
+    a.stem_tc_allowed = path == 3;
+    return conv_stem(a, (cudaStream_t)stream);
   }
   return conv_simt(a, (cudaStream_t)stream);
 }

@@ -195,7 +195,9 @@ int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total);
  * "strip" (0/1, default 0): large 3x3x3 layers stage the A operand once per (dz, channel chunk) and address the 9
  * in-plane taps through row-shifted descriptors (half the L2 traffic; 6-14 % faster stand-alone, neutral inside the
  * power-capped network step);
- * "cluster" (0/1, default 0): 2-CTA clusters multicast the weight tile (neutral). */
+ * "cluster" (0/1, default 0): 2-CTA clusters multicast the weight tile (neutral);
+ * "fold_identity" (0/1, default 1): identity skips enter the second conv of a ResBlock as a unit-weight 1x1x1 source;
+ * "stem_tc" (0/1, default 1): the Cin == 2 stem runs as one tcgen05 tile per 128 voxels in the 16-bit modes. */
 int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value);
 /* Kernel launches enqueued by this ctx since creation. */
 int64_t ddpm3d_launch_count(const ddpm3d_ctx* ctx);
@@ -212,7 +214,8 @@ int ddpm3d_profile_read(ddpm3d_ctx* ctx, ddpm3d_prof_record* out, int cap);
 /* 3x3x3 (taps=27) or 1x1x1 (taps=1) "same" convolution, stride (1,s,s) (nn.py:22-32; call sites
  * unet.py:185,211,219,222).  w: [Cout][taps*Cin] with k = tap*Cin + ci, tap = (dz*3+dh)*3+dw;
  * bias fp32 [Cout]; residual (optional, [B][Z][Ho][Wo][Cout]) is added in the epilogue.
- * path: 1 SIMT, 2 tcgen05 (bf16 / fp16, Cin%64==0, Cout%64==0, s==1). */
+ * path: 1 SIMT, 2 tcgen05 (bf16 / fp16, Cin%64==0, Cout%64==0, s==1), 3 / 4 the Cin==2 stem kernels
+ * (3: tcgen05 tile per 128 voxels in the 16-bit modes, 4: CUDA cores). */
 int ddpm3d_k_conv3d(int dtype, int path, const void* in, const void* w, const float* bias, const void* residual,
                     void* out, int B, int Z, int H, int W, int Cin, int Cout, int taps, int stride_hw, void* stream);
 

@@ -108,7 +108,7 @@ def test_fused_groupnorm_statistics_agree_with_the_separate_pass():
     assert max_rel(outs[1], outs[0]) <= 3e-3
 
 
-@pytest.mark.parametrize("opts", [dict(strip=1, fold_identity=1), dict(fold_identity=1), dict(strip=1), dict(cluster=1)])
+@pytest.mark.parametrize("opts", [dict(strip=1, fold_identity=1), dict(fold_identity=1), dict(strip=1), dict(cluster=1), dict(stem_tc=0)])
 def test_c2_architecture_with_kernel_options(opts):
     """The optional kernel variants (strip staging with swapped MMA operands, identity skips folded into the
     accumulation as unit-weight 1x1x1 sources, weight multicast in 2-CTA clusters) on the shipped network:
@@ -149,3 +149,25 @@ def test_operand_descriptor_may_start_at_any_row_of_a_swizzled_tile():
         N.check(N.lib().ddpm3d_k_probe_rowshift(N.ptr(A), 256, N.ptr(ident), shift, 0, N.ptr(out), stream()))
         torch.cuda.synchronize()
         assert torch.equal(out, A[shift:shift + 128].float()), shift
+
+
+@pytest.mark.parametrize("dt", [N.BF16, N.FP16])
+@pytest.mark.parametrize("Cout,shape", [(32, (1, 4, 8, 8)), (128, (2, 3, 10, 7)), (256, (1, 2, 16, 16)), (96, (1, 5, 9, 11)),
+                                        (128, (1, 6, 24, 24))])
+def test_stem_tensor_core_tile(dt, Cout, shape):
+    """input_blocks.0.0 (unet.py:809-811): Conv3d(2 -> C) as one M128 x C x K64 tcgen05 tile per 128 voxels (hand-swizzled
+    im2col rows) vs F.conv3d fp32 and vs the CUDA-core stem kernel; ragged last tile, B > 1, every TMEM width."""
+    B, Z, H, W = shape
+    tdt = TDT[dt]
+    g = torch.Generator().manual_seed(Cout + Z)
+    x = torch.randn((B, 2, Z, H, W), generator=g).to(tdt).float()
+    w = (torch.randn((Cout, 2, 3, 3, 3), generator=g) / np.sqrt(54)).to(tdt).float()
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv3d(x, w, b, padding=1)
+    args = (to_cl(x, tdt), pack_weight(w, tdt), b.to(DEV), None, B, Z, H, W, 2, Cout)
+    tc = conv3d(dt, 3, *args)
+    cc = conv3d(dt, 4, *args)
+    assert max_rel(from_cl(tc), ref) <= ROUND_TOL[dt]
+    assert max_rel(from_cl(cc), ref) <= ROUND_TOL[dt]
+    # same products, fp32 accumulation in a different order, one rounding each: at most an ulp apart
+    assert max_rel(from_cl(tc), from_cl(cc)) <= ROUND_TOL[dt]
