@@ -23,6 +23,7 @@ class Config(C.Structure):
         ("num_head_channels", C.c_int32), ("num_heads_upsample", C.c_int32),
         ("use_scale_shift_norm", C.c_int32), ("resblock_updown", C.c_int32),
         ("use_new_attention_order", C.c_int32), ("precision", C.c_int32),
+        ("dims", C.c_int32), ("middle_attention", C.c_int32), ("unconditional", C.c_int32),
     ]
 
 

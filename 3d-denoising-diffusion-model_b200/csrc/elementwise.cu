@@ -34,6 +34,36 @@ int pack_input(int dt, const float* x, const float* low, void* out, int B, int Z
   return DDPM3D_OK;
 }
 
+// general form: x and (optionally) low_res with Cx channels each, planar (B, Cx, Z, H, W) -> channels-last
+// (B, Z, H, W, Cx [+ Cx]); used by the 2-D / multi-channel model classes (unet.py:396-716, 1650-1673)
+template <typename T>
+__global__ void pack_planar_kernel(const float* __restrict__ x, const float* __restrict__ low, int Cx, T* __restrict__ out,
+                                   int64_t n, int64_t per_b, int64_t pad_vox) {
+  const int Ctot = low ? 2 * Cx : Cx;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const int64_t b = i / per_b, sp = i - b * per_b;
+    const int64_t o = (i + (2 * b + 1) * pad_vox) * Ctot;
+    for (int c = 0; c < Cx; ++c) {
+      out[o + c] = from_f32<T>(x[(b * Cx + c) * per_b + sp]);
+      if (low) out[o + Cx + c] = from_f32<T>(low[(b * Cx + c) * per_b + sp]);
+    }
+  }
+}
+
+int pack_input_planar(int dt, const float* x, const float* low, int Cx, void* out, int B, int Z, int64_t plane, int out_zpad,
+                      cudaStream_t s) {
+  const int64_t n = (int64_t)B * Z * plane, per_b = (int64_t)Z * plane, pad_vox = (int64_t)out_zpad * plane;
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>(ceil_div(n, threads), 148 * 16);
+  if (dt == DDPM3D_BF16) pack_planar_kernel<bf16><<<blocks, threads, 0, s>>>(x, low, Cx, (bf16*)out, n, per_b, pad_vox);
+  else if (dt == DDPM3D_FP16) pack_planar_kernel<f16><<<blocks, threads, 0, s>>>(x, low, Cx, (f16*)out, n, per_b, pad_vox);
+  else pack_planar_kernel<float><<<blocks, threads, 0, s>>>(x, low, Cx, (float*)out, n, per_b, pad_vox);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
 // =================================================================================================
 // GroupNorm32 (nn.py:17-19,93-100): statistics in fp32 over (C/32, Z, H, W) per batch element.
 // Pass 1 (stats): per-chunk partial [sum, sumsq] per group, fixed summation order (deterministic).

@@ -133,6 +133,12 @@ using namespace ddpm3d;
 
 struct ddpm3d_ctx {
   ddpm3d_config cfg{};
+  int stem_cin() const { return cfg.in_channels * (cfg.unconditional ? 1 : 2); }
+  bool two_d() const { return cfg.dims == 2; }
+  // conv weight shape in the state_dict: [Cout][Cin][k][k][k] (dims 3) or [Cout][Cin][k][k] (dims 2)
+  std::vector<int64_t> wshape(int64_t co, int64_t ci, int64_t k) const {
+    return two_d() ? std::vector<int64_t>{co, ci, k, k} : std::vector<int64_t>{co, ci, k, k, k};
+  }
   std::vector<Param> params;
   std::unordered_map<std::string, int> index;
   std::vector<std::vector<Layer>> input_blocks, output_blocks;
@@ -225,22 +231,22 @@ void add_layer_params(ddpm3d_ctx* ctx, const Layer& L) {
   const std::string& p = L.prefix;
   const int64_t ted = ctx->ted;
   if (L.kind == L_CONV || L.kind == L_UPCONV) {
-    add_param(ctx, p + ".weight", {L.cout, L.cin, 3, 3, 3});
+    add_param(ctx, p + ".weight", ctx->wshape(L.cout, L.cin, 3));
     add_param(ctx, p + ".bias", {L.cout});
   } else if (L.kind == L_RES) {
     const int64_t e = ctx->cfg.use_scale_shift_norm ? 2 * L.cout : L.cout;
     add_param(ctx, p + ".in_layers.0.weight", {L.cin});
     add_param(ctx, p + ".in_layers.0.bias", {L.cin});
-    add_param(ctx, p + ".in_layers.2.weight", {L.cout, L.cin, 3, 3, 3});
+    add_param(ctx, p + ".in_layers.2.weight", ctx->wshape(L.cout, L.cin, 3));
     add_param(ctx, p + ".in_layers.2.bias", {L.cout});
     add_param(ctx, p + ".emb_layers.1.weight", {e, ted});
     add_param(ctx, p + ".emb_layers.1.bias", {e});
     add_param(ctx, p + ".out_layers.0.weight", {L.cout});
     add_param(ctx, p + ".out_layers.0.bias", {L.cout});
-    add_param(ctx, p + ".out_layers.3.weight", {L.cout, L.cout, 3, 3, 3});
+    add_param(ctx, p + ".out_layers.3.weight", ctx->wshape(L.cout, L.cout, 3));
     add_param(ctx, p + ".out_layers.3.bias", {L.cout});
     if (L.skip_conv) {
-      add_param(ctx, p + ".skip_connection.weight", {L.cout, L.cin, 1, 1, 1});
+      add_param(ctx, p + ".skip_connection.weight", ctx->wshape(L.cout, L.cin, 1));
       add_param(ctx, p + ".skip_connection.bias", {L.cout});
     }
   } else {  // attention (unet.py:259-305)
@@ -259,14 +265,15 @@ int build_topology(ddpm3d_ctx* ctx) {
   DD_CHECK(c.model_channels > 0 && c.model_channels % 32 == 0, DDPM3D_ERR_ARG,
            "config: model_channels must be a positive multiple of 32 (GroupNorm32)");
   DD_CHECK(c.num_res_blocks >= 1, DDPM3D_ERR_ARG, "config: num_res_blocks must be >= 1");
-  DD_CHECK(c.in_channels == 1, DDPM3D_ERR_ARG, "config: in_channels must be 1 (SuperResModel_noatt)");
+  DD_CHECK(c.in_channels >= 1 && c.in_channels <= 64, DDPM3D_ERR_ARG, "config: in_channels out of range");
+  DD_CHECK(c.dims == 0 || c.dims == 2 || c.dims == 3, DDPM3D_ERR_ARG, "config: dims must be 2 or 3");
   DD_CHECK(c.out_channels >= 1, DDPM3D_ERR_ARG, "config: out_channels must be >= 1");
   const int mc = c.model_channels;
   ctx->ted = mc * 4;
   const int heads_up = c.num_heads_upsample == -1 ? c.num_heads : c.num_heads_upsample;
   int ch = c.channel_mult[0] * mc;
   const int input_ch = ch;
-  ctx->input_blocks.push_back({make_conv(L_CONV, "input_blocks.0.0", c.in_channels * 2, ch, 1)});
+  ctx->input_blocks.push_back({make_conv(L_CONV, "input_blocks.0.0", ctx->stem_cin(), ch, 1)});
   std::vector<int> chans{ch};
   int ds = 1;
   for (int level = 0; level < c.n_levels; ++level) {
@@ -293,7 +300,14 @@ int build_topology(ddpm3d_ctx* ctx) {
       ds *= 2;
     }
   }
-  ctx->middle = {make_res("middle_block.0", ch, ch), make_res("middle_block.1", ch, ch)};
+  if (c.middle_attention) {  // UNetModel (unet.py:539-563): ResBlock, AttentionBlock, ResBlock
+    DD_CHECK(c.num_head_channels == -1 || ch % c.num_head_channels == 0, DDPM3D_ERR_ARG,
+             "config: channels not divisible by num_head_channels");
+    ctx->middle = {make_res("middle_block.0", ch, ch), make_attn("middle_block.1", ch, heads_for(c, ch, c.num_heads)),
+                   make_res("middle_block.2", ch, ch)};
+  } else {
+    ctx->middle = {make_res("middle_block.0", ch, ch), make_res("middle_block.1", ch, ch)};
+  }
   int outch = ch;
   for (int level = c.n_levels - 1; level >= 0; --level) {
     for (int i = 0; i < c.num_res_blocks + 1; ++i) {
@@ -332,7 +346,7 @@ int build_topology(ddpm3d_ctx* ctx) {
     for (auto& L : blk) add_layer_params(ctx, L);
   add_param(ctx, "out.0.weight", {ctx->out_norm_ch});
   add_param(ctx, "out.0.bias", {ctx->out_norm_ch});
-  add_param(ctx, "out.2.weight", {c.out_channels, ctx->out_conv_in, 3, 3, 3});
+  add_param(ctx, "out.2.weight", ctx->wshape(c.out_channels, ctx->out_conv_in, 3));
   add_param(ctx, "out.2.bias", {c.out_channels});
   return DDPM3D_OK;
 }
@@ -368,6 +382,8 @@ int pack_conv(ddpm3d_ctx* ctx, int dt, const std::string& wkey, const std::strin
   DD_CHECK(w && w->loaded, DDPM3D_ERR_MISSING, "missing state_dict tensor: " + wkey);
   DD_CHECK(b && b->loaded, DDPM3D_ERR_MISSING, "missing state_dict tensor: " + bkey);
   const int64_t Cout = w->shape[0], Cin = w->shape[1];
+  // dims = 2 (unet.py:396-716 with Conv2d): the images run through the same kernels as (B, C, 1, H, W) volumes
+  const bool flat2d = taps == 27 && w->shape.size() == 4;
   const Param* sw = nullptr;
   const Param* sb = nullptr;
   int64_t Cs = 0;
@@ -385,9 +401,15 @@ int pack_conv(ddpm3d_ctx* ctx, int dt, const std::string& wkey, const std::strin
   std::vector<float> packed((size_t)(Cout * Ktot), 0.f);
   for (int64_t co = 0; co < Cout; ++co) {
     float* row = packed.data() + co * Ktot;
-    const float* src = w->host.data() + co * Cin * taps;
-    for (int64_t ci = 0; ci < Cin; ++ci)
-      for (int t = 0; t < taps; ++t) row[(int64_t)t * Cin + ci] = src[ci * taps + t];
+    if (flat2d) {  // a 3x3 kernel is the centre z-plane (taps 9..17) of a 3x3x3 kernel whose other planes are zero
+      const float* src = w->host.data() + co * Cin * 9;
+      for (int64_t ci = 0; ci < Cin; ++ci)
+        for (int t = 0; t < 9; ++t) row[(int64_t)(9 + t) * Cin + ci] = src[ci * 9 + t];
+    } else {
+      const float* src = w->host.data() + co * Cin * taps;
+      for (int64_t ci = 0; ci < Cin; ++ci)
+        for (int t = 0; t < taps; ++t) row[(int64_t)t * Cin + ci] = src[ci * taps + t];
+    }
     if (sw)
       for (int64_t ci = 0; ci < Cs; ++ci) row[taps * Cin + ci] = sw->host[co * Cs + ci];
     else if (append_identity)
@@ -760,16 +782,20 @@ int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, cons
   }
   // cat([x, low_res], 1).type(dtype)
   Act h;
-  h.C = 2; h.H = H; h.W = W;
-  h.p = R.arena.alloc(R.conv_in_bytes(H, W, 2, ctx->esz));
+  const int Cx = ctx->cfg.in_channels, Cstem = ctx->stem_cin();
+  h.C = Cstem; h.H = H; h.W = W;
+  h.p = R.arena.alloc(R.conv_in_bytes(H, W, Cstem, ctx->esz));
   ++R.launches;
   if (!R.arena.dry) {
-    R.prof_begin(8, (double)B * Z * H * W * (8.0 + 2.0 * ctx->esz));
-    const int r = pack_input(dt, x, low, h.p, B, Z, (int64_t)H * W, R.zp, R.s);
+    DD_CHECK((low != nullptr) == (ctx->cfg.unconditional == 0), DDPM3D_ERR_ARG,
+             "low_res must be given to a conditional model and only to it (unet.py:1687-1694)");
+    R.prof_begin(8, (double)B * Z * H * W * Cstem * (4.0 + ctx->esz));
+    const int r = Cx == 1 && low ? pack_input(dt, x, low, h.p, B, Z, (int64_t)H * W, R.zp, R.s)
+                                 : pack_input_planar(dt, x, low, Cx, h.p, B, Z, (int64_t)H * W, R.zp, R.s);
     R.prof_end();
     DD_TRY(r);
   }
-  DD_TRY(R.halo(h.p, H, W, 2, ctx->esz));
+  DD_TRY(R.halo(h.p, H, W, Cstem, ctx->esz));
   std::vector<Act> skips;
   for (auto& blk : ctx->input_blocks) {
     Act o;
@@ -810,6 +836,7 @@ int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, cons
 int check_geometry(ddpm3d_ctx* ctx, int B, int Z, int H, int W) {
   DD_CHECK(ctx->finalized, DDPM3D_ERR_STATE, "weights not finalized (call ddpm3d_finalize_weights first)");
   DD_CHECK(B >= 1 && Z >= 1 && H >= 1 && W >= 1, DDPM3D_ERR_ARG, "bad geometry");
+  DD_CHECK(!ctx->two_d() || Z == 1, DDPM3D_ERR_ARG, "a dims = 2 model takes (B, C, H, W) images: Z must be 1");
   const int f = 1 << (ctx->cfg.n_levels - 1);
   DD_CHECK(H % f == 0 && W % f == 0, DDPM3D_ERR_ARG, "H and W must be divisible by 2^(levels-1)");
   DD_CHECK(((int64_t)Z * H * W) % 4 == 0, DDPM3D_ERR_ARG, "Z*H*W must be a multiple of 4");
@@ -949,6 +976,9 @@ int ensure_loop_buffers(ddpm3d_ctx* ctx, int B, int64_t n_vox) {
 bool learned_var(int v) { return v == DDPM3D_VAR_LEARNED || v == DDPM3D_VAR_LEARNED_RANGE; }
 
 int check_sampler_shapes(ddpm3d_ctx* ctx) {
+  DD_CHECK(ctx->cfg.in_channels == 1 && !ctx->cfg.unconditional, DDPM3D_ERR_ARG,
+           "the fused UNet + update entry points serve the one-channel conditional model; other model classes go "
+           "through ddpm3d_unet_forward + ddpm3d_p_sample_update");
   const int need = learned_var(ctx->var_type) ? 2 : 1;
   DD_CHECK(ctx->cfg.out_channels == need, DDPM3D_ERR_ARG,
            "model out_channels does not match the variance type (gaussian_diffusion.py:262-263)");
@@ -1117,7 +1147,9 @@ int64_t ddpm3d_workspace_bytes(ddpm3d_ctx* ctx, int B, int Z, int H, int W) {
 
 int ddpm3d_unet_forward(ddpm3d_ctx* ctx, const float* x, const float* low_res, const float* t, const int64_t* y, float* out,
                         int B, int Z, int H, int W, void* stream) {
-  DD_CHECK(ctx && x && low_res && t && out, DDPM3D_ERR_ARG, "unet_forward: null argument");
+  DD_CHECK(ctx && x && t && out, DDPM3D_ERR_ARG, "unet_forward: null argument");
+  DD_CHECK((low_res != nullptr) == (ctx->cfg.unconditional == 0), DDPM3D_ERR_ARG,
+           "unet_forward: low_res must be given to a conditional model and only to it");
   DD_TRY(check_geometry(ctx, B, Z, H, W));
   DD_CUDA(cudaSetDevice(ctx->device));
   DD_TRY(ensure_workspace(ctx, B, Z, H, W));

@@ -107,6 +107,8 @@ int resample_hw(int dt, const void* in, void* out, int B, int Z, int H, int W, i
 // cat([x, low_res], 1) + cast (unet.py:1690-1693,1035): two fp32 (B,1,Z,H,W) -> [B][Z][H][W][2]
 // out_zpad: halo planes on each side of Z in `out` ([B][Z+2p][H][W][2]); plane = H*W voxels
 int pack_input(int dt, const float* x, const float* low, void* out, int B, int Z, int64_t plane, int out_zpad, cudaStream_t s);
+int pack_input_planar(int dt, const float* x, const float* low, int Cx, void* out, int B, int Z, int64_t plane, int out_zpad,
+                      cudaStream_t s);
 
 struct EmbArgs {
   const float* t = nullptr;          // [B]

@@ -238,7 +238,7 @@ class GaussianDiffusion:
         if noise is None:
             noise = torch.randn_like(x)
         from .unet import UNetModel_noatt
-        if isinstance(model, UNetModel_noatt) and x.shape[1] == 1:
+        if isinstance(model, UNetModel_noatt) and model._fused_sampler:
             # native model: UNet + update fused in one graph-cached library call, t stays on the device
             model._bind_schedule(self)
             self._set_sampler(model._ctx, False, 0.0)
@@ -310,7 +310,7 @@ class GaussianDiffusion:
         if progress:
             from tqdm.auto import tqdm
             indices = tqdm(indices)
-        native = isinstance(model, UNetModel_noatt)
+        native = isinstance(model, UNetModel_noatt) and model._fused_sampler
         if native:
             model._bind_schedule(self)
             self._set_sampler(model._ctx, _ddim, _eta)

@@ -12,7 +12,7 @@ import inspect
 
 from . import gaussian_diffusion as gd
 from .respace import SpacedDiffusion, space_timesteps
-from .unet import NUM_CLASSES, SuperResModel_noatt
+from .unet import NUM_CLASSES, SuperResModel_noatt, UNetModel
 
 
 def diffusion_defaults():
@@ -34,12 +34,45 @@ def create_model_and_diffusion(image_size, class_cond, learn_sigma, num_channels
                                diffusion_steps, noise_schedule, timestep_respacing, use_kl, predict_xstart,
                                rescale_timesteps, rescale_learned_sigmas, use_checkpoint, use_scale_shift_norm,
                                resblock_updown, use_fp16, use_new_attention_order):
-    """script_util.py:74-127 builds the 2-D unconditional `UNetModel`, which no script of the reference
-    uses; the B200 path is the 3-D low-dose-conditioned model, so the model half is not built here.
-    The signature is kept so callers fail with a clear message instead of an AttributeError."""
-    raise NotImplementedError(
-        "create_model_and_diffusion builds the reference's unused 2-D UNetModel; use "
-        "sr_create_model_and_diffusion (the 3-D SuperResModel_noatt scripts/test.py instantiates)")
+    """script_util.py:74-127: the 2-D RGB `UNetModel` (no script of the reference uses it; it runs through the
+    same kernels as a one-plane volume) and its diffusion."""
+    model = create_model(image_size, num_channels, num_res_blocks, channel_mult=channel_mult, learn_sigma=learn_sigma,
+                         class_cond=class_cond, use_checkpoint=use_checkpoint,
+                         attention_resolutions=attention_resolutions, num_heads=num_heads,
+                         num_head_channels=num_head_channels, num_heads_upsample=num_heads_upsample,
+                         use_scale_shift_norm=use_scale_shift_norm, dropout=dropout, resblock_updown=resblock_updown,
+                         use_fp16=use_fp16, use_new_attention_order=use_new_attention_order)
+    diffusion = create_gaussian_diffusion(steps=diffusion_steps, learn_sigma=learn_sigma, noise_schedule=noise_schedule,
+                                          use_kl=use_kl, predict_xstart=predict_xstart,
+                                          rescale_timesteps=rescale_timesteps,
+                                          rescale_learned_sigmas=rescale_learned_sigmas,
+                                          timestep_respacing=timestep_respacing)
+    return model, diffusion
+
+
+def create_model(image_size, num_channels, num_res_blocks, channel_mult="", learn_sigma=False, class_cond=False,
+                 use_checkpoint=False, attention_resolutions="16", num_heads=1, num_head_channels=-1,
+                 num_heads_upsample=-1, use_scale_shift_norm=False, dropout=0, resblock_updown=False, use_fp16=False,
+                 use_new_attention_order=False):
+    """script_util.py:130-184."""
+    if channel_mult == "":
+        if image_size == 512:
+            raise NotImplementedError("image_size 512 uses a fractional channel multiplier (0.5), which is not built")
+        mults = {256: (1, 1, 2, 2, 4, 4), 128: (1, 1, 2, 3, 4), 64: (1, 2, 3, 4)}
+        if image_size not in mults:
+            raise ValueError(f"unsupported image size: {image_size}")
+        channel_mult = mults[image_size]
+    else:
+        channel_mult = tuple(int(ch_mult) for ch_mult in channel_mult.split(","))
+    attention_ds = tuple(image_size // int(res) for res in attention_resolutions.split(","))
+    return UNetModel(
+        image_size=image_size, in_channels=3, model_channels=num_channels,
+        out_channels=(3 if not learn_sigma else 6), num_res_blocks=num_res_blocks,
+        attention_resolutions=attention_ds, dropout=dropout, channel_mult=channel_mult,
+        num_classes=(NUM_CLASSES if class_cond else None), use_checkpoint=use_checkpoint, use_fp16=use_fp16,
+        num_heads=num_heads, num_head_channels=num_head_channels, num_heads_upsample=num_heads_upsample,
+        use_scale_shift_norm=use_scale_shift_norm, resblock_updown=resblock_updown,
+        use_new_attention_order=use_new_attention_order)
 
 
 def sr_model_and_diffusion_defaults():

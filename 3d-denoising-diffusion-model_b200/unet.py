@@ -19,10 +19,14 @@ NUM_CLASSES = 1000  # script_util.py:8
 
 def _make_config(*, image_size, model_channels, out_channels, num_res_blocks, attention_resolutions, channel_mult,
                  num_classes, num_heads, num_head_channels, num_heads_upsample, use_scale_shift_norm,
-                 resblock_updown, use_new_attention_order, precision) -> N.Config:
+                 resblock_updown, use_new_attention_order, precision, x_channels=1, dims=3, middle_attention=False,
+                 unconditional=False) -> N.Config:
     cfg = N.Config()
     cfg.image_size = int(image_size)
-    cfg.in_channels = 1
+    cfg.in_channels = int(x_channels)
+    cfg.dims = int(dims)
+    cfg.middle_attention = int(bool(middle_attention))
+    cfg.unconditional = int(bool(unconditional))
     cfg.model_channels = int(model_channels)
     cfg.out_channels = int(out_channels)
     cfg.num_res_blocks = int(num_res_blocks)
@@ -109,19 +113,28 @@ def sampler_only_context(diffusion, device):
 
 
 class UNetModel_noatt:
-    """guided_diffusion/unet.py:720-1044.  Constructor arguments are the reference's."""
+    """guided_diffusion/unet.py:720-1044.  Constructor arguments are the reference's.
+
+    The sibling classes differ only in two switches the library's topology builder understands:
+    `_middle_attention` (UNetModel, unet.py:539-563) and `_concat_low_res` (the SuperRes* classes, which double
+    `in_channels` and concatenate `low_res` in forward, unet.py:1654-1694).  dims=2 networks (Conv2d, (B,C,H,W)
+    images) run through the same kernels as one-plane volumes."""
+
+    _middle_attention = False
+    _concat_low_res = False
 
     def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
                  dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
                  use_checkpoint=False, use_fp16=False, num_heads=1, num_head_channels=-1, num_heads_upsample=-1,
                  use_scale_shift_norm=False, resblock_updown=False, use_new_attention_order=False):
         import torch
-        if dims != 3:
-            raise NotImplementedError("only the 3-D network (dims=3) is on the B200 path")
+        if dims not in (2, 3):
+            raise NotImplementedError("dims must be 2 or 3 (1-D networks are not built)")
         if not conv_resample:
             raise NotImplementedError("conv_resample=False is not reachable from script_util and not built")
-        if in_channels != 2:
-            raise NotImplementedError("the live model takes x and low_res, one channel each (unet.py:1683-1685)")
+        if self._concat_low_res and in_channels % 2:
+            raise ValueError("a SuperRes model's in_channels counts x and low_res")
+        self.dims = dims
         self.image_size = image_size
         self.in_channels = in_channels
         self.model_channels = model_channels
@@ -162,7 +175,19 @@ class UNetModel_noatt:
                             num_classes=self.num_classes, num_heads=self.num_heads,
                             num_head_channels=self.num_head_channels, num_heads_upsample=self.num_heads_upsample,
                             use_scale_shift_norm=self.use_scale_shift_norm, resblock_updown=self.resblock_updown,
-                            use_new_attention_order=self.use_new_attention_order, precision=precision)
+                            use_new_attention_order=self.use_new_attention_order, precision=precision,
+                            x_channels=self._x_channels, dims=self.dims, middle_attention=self._middle_attention,
+                            unconditional=not self._concat_low_res)
+
+    @property
+    def _x_channels(self):
+        """Channels of the `x` argument of forward (the SuperRes classes split in_channels between x and low_res)."""
+        return self.in_channels // 2 if self._concat_low_res else self.in_channels
+
+    @property
+    def _fused_sampler(self):
+        """UNet + posterior update in one library call: built for the live one-channel conditional 3-D model."""
+        return self._concat_low_res and self.in_channels == 2 and self.dims == 3
 
     def _initial_state(self):
         """Same families of initial values as the reference constructor: uniform(+-1/sqrt(fan_in)) for
@@ -350,10 +375,13 @@ class UNetModel_noatt:
 
     # ---- forward (unet.py:1015-1044) -------------------------------------------------------------------
     def _check_io(self, x, low_res):
-        if x.dim() != 5 or x.shape[1] != 1:
-            raise AssertionError("x must be (B, 1, Z, H, W)")
-        if low_res is None or tuple(low_res.shape) != tuple(x.shape):
-            raise AssertionError("low_res must have the shape of x (unet.py:1690-1693)")
+        if x.dim() != self.dims + 2 or x.shape[1] != self._x_channels:
+            raise AssertionError(f"x must be (B, {self._x_channels}, {'Z, ' if self.dims == 3 else ''}H, W)")
+        if self._concat_low_res:
+            if low_res is None or tuple(low_res.shape) != tuple(x.shape):
+                raise AssertionError("low_res must have the shape of x (unet.py:1690-1693)")
+        elif low_res is not None:
+            raise TypeError("forward() got an unexpected keyword argument 'low_res'")  # unet.py:687 / :1015
         if x.device != self._device:
             raise RuntimeError(f"input on {x.device} but model on {self._device}")
 
@@ -370,13 +398,15 @@ class UNetModel_noatt:
         import torch
         ctx = self._ensure_ctx()
         self._check_io(x, low_res)
-        B, _, Z, H, W = x.shape
+        B = x.shape[0]
+        Z = x.shape[2] if self.dims == 3 else 1
+        H, W = x.shape[-2:]
         x = x.contiguous().float()
-        low = low_res.contiguous().float()
+        low = low_res.contiguous().float() if low_res is not None else None
         t = timesteps.to(self._device).float().contiguous()  # nn.py:117 casts to float anyway
         assert t.shape == (B,)
         yy = self._y(y, B)
-        out = torch.empty((B, self.out_channels, Z, H, W), device=self._device, dtype=torch.float32)
+        out = torch.empty((B, self.out_channels, *x.shape[2:]), device=self._device, dtype=torch.float32)
         with torch.cuda.device(self._device):
             N.check(N.lib().ddpm3d_unet_forward(ctx, N.ptr(x), N.ptr(low), N.ptr(t), N.ptr(yy), N.ptr(out),
                                                 B, Z, H, W, N.current_stream_ptr(self._device)))
@@ -456,6 +486,25 @@ class _DeviceTag:
 class SuperResModel_noatt(UNetModel_noatt):
     """unet.py:1676-1694: concatenates `low_res` on the channel axis (done inside the library's
     pack_input kernel, never materialised by torch)."""
+
+    _concat_low_res = True
+
+    def __init__(self, image_size, in_channels, *args, **kwargs):
+        super().__init__(image_size, int(in_channels * 2), *args, **kwargs)
+
+
+class UNetModel(UNetModel_noatt):
+    """unet.py:396-716: the full UNet -- an AttentionBlock sits between the two middle ResBlocks (:539-563).
+    create_model (script_util.py:130-184) instantiates it with dims=2 on RGB images."""
+
+    _middle_attention = True
+
+
+class SuperResModel(UNetModel):
+    """unet.py:1654-1673: UNetModel with `low_res` concatenated as is (same shape as x; the bilinear up-sampling
+    of the upstream code is commented out in the reference)."""
+
+    _concat_low_res = True
 
     def __init__(self, image_size, in_channels, *args, **kwargs):
         super().__init__(image_size, int(in_channels * 2), *args, **kwargs)

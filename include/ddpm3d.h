@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DDPM3D_ABI_VERSION 2
+#define DDPM3D_ABI_VERSION 3
 
 #define DDPM3D_OK 0
 #define DDPM3D_ERR_ARG (-1)     /* bad argument / unsupported configuration */
@@ -61,7 +61,8 @@ typedef struct ddpm3d_ctx ddpm3d_ctx;
  * sr_create_model (script_util.py:334-450). */
 typedef struct ddpm3d_config {
   int32_t image_size;      /* large_size; informational */
-  int32_t in_channels;     /* 1; SuperResModel_noatt doubles it for the low_res concat (unet.py:1683) */
+  int32_t in_channels;     /* channels of x (1 for the PET model); a conditional model doubles it for the low_res
+                              concat (unet.py:1683, :1666-1673) unless `unconditional` is set */
   int32_t model_channels;  /* num_channels */
   int32_t out_channels;    /* 2 if learn_sigma else 1 */
   int32_t num_res_blocks;
@@ -77,6 +78,11 @@ typedef struct ddpm3d_config {
   int32_t resblock_updown;
   int32_t use_new_attention_order;
   int32_t precision;       /* DDPM3D_FP32 | DDPM3D_BF16 | DDPM3D_FP16 */
+  /* ABI 3: the other model classes of unet.py.  All-zero = SuperResModel_noatt with dims=3 (the live model). */
+  int32_t dims;            /* 0 or 3: Conv3d, (1,2,2) resampling; 2: the 2-D UNetModel (unet.py:396-716): weights
+                              are [Cout][Cin][3][3], activations (B,C,H,W) are passed with Z = 1 */
+  int32_t middle_attention; /* 1: UNetModel's AttentionBlock between the two middle ResBlocks (unet.py:548-555) */
+  int32_t unconditional;   /* 1: UNetModel.forward(x, t, y): no low_res concat, low_res must be NULL */
 } ddpm3d_config;
 
 /* Per-timestep scalars of the respaced process, already rounded to fp32 exactly as
@@ -130,8 +136,8 @@ int ddpm3d_set_timestep_freqs(ddpm3d_ctx* ctx, const float* freqs, int n);
 int64_t ddpm3d_workspace_bytes(ddpm3d_ctx* ctx, int B, int Z, int H, int W);
 
 /* ---- one UNet evaluation: replaces SuperResModel_noatt.forward (unet.py:1687-1694) ---------
- * x, low_res: device fp32 (B,1,Z,H,W); t: device fp32 (B); y: device int64 (B) or NULL;
- * out: device fp32 (B,out_channels,Z,H,W). */
+ * x, low_res: device fp32 (B,in_channels,Z,H,W) (low_res NULL for an unconditional model; Z = 1 when dims = 2);
+ * t: device fp32 (B); y: device int64 (B) or NULL; out: device fp32 (B,out_channels,Z,H,W). */
 int ddpm3d_unet_forward(ddpm3d_ctx* ctx, const float* x, const float* low_res, const float* t,
                         const int64_t* y, float* out, int B, int Z, int H, int W, void* stream);
 

@@ -32,8 +32,8 @@ from guided_diffusion.respace import space_timesteps as ref_space  # noqa: E402
 
 from oracle.cases import (  # noqa: E402
     SCHEDULE_CASES, SPACING_CASES, TEMB_CASES, PMV_CASES, UNET_CASES, C1_FLAGS, C1_SHAPE,
-    VOLUME_DIMS, VOLUME_Z, HANN_SIZES,
-    sr_flags, cfg_from_flags,
+    VOLUME_DIMS, VOLUME_Z, HANN_SIZES, UNET2D_CASES,
+    sr_flags, cfg_from_flags, model_flags, unet2d_cfg, unet2d_inputs,
 )
 from oracle.weights import synth_state_dict, synth_inputs  # noqa: E402
 
@@ -103,7 +103,38 @@ def make_ddim_golden():
     np.savez_compressed(os.path.join(OUT, "ddim.npz"), **z)
 
 
+def make_unet2d_golden():
+    """The model classes scripts/test.py does not instantiate: the 2-D RGB UNetModel from
+    create_model_and_diffusion (script_util.py:74-184), the 2-D SuperResModel (unet.py:1654-1673) and a dims=3 UNetModel with its middle-block attention."""
+    from guided_diffusion import unet as ref_unet
+    z, keys = {}, {}
+    for name, case in UNET2D_CASES.items():
+        cfg = unet2d_cfg(case)
+        sd = synth_state_dict(cfg, seed=case.get("seed", 0))
+        if case["kind"] == "create_model":
+            model, _ = su.create_model_and_diffusion(**model_flags(**case["flags"]))
+        else:
+            model = getattr(ref_unet, case["kind"])(**case["ctor"])
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        keys[name] = [[k, list(v.shape)] for k, v in model.state_dict().items()]
+        x, low = unet2d_inputs(case)
+        kw = {}
+        if low is not None:
+            kw["low_res"] = low
+        if "y" in case:
+            kw["y"] = torch.tensor(case["y"])
+        with torch.no_grad():
+            z[f"{name}/out"] = model(x, torch.tensor(case["t"]), **kw).numpy()
+    np.savez_compressed(os.path.join(OUT, "unet2d.npz"), **z)
+    with open(os.path.join(OUT, "state_dict_keys_2d.json"), "w") as f:
+        json.dump(keys, f)
+
+
 def main():
+    if "--unet2d-only" in sys.argv:
+        make_unet2d_golden()
+        return
     if "--volume-only" in sys.argv:
         make_volume_golden()
         return
@@ -221,6 +252,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "c1_loop.npz"), **z)
     make_volume_golden()
     make_ddim_golden()
+    make_unet2d_golden()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

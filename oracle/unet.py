@@ -36,6 +36,36 @@ class UNetConfig:
     resblock_updown: bool = True
     use_new_attention_order: bool = False
     conv_resample: bool = True
+    # the other classes of unet.py: dims=2 Conv2d networks, UNetModel's middle attention (unet.py:539-563), and
+    # models that take no low_res (UNetModel.forward, unet.py:687-716)
+    dims: int = 3
+    middle_attention: bool = False
+    concat_low_res: bool = True
+
+    @property
+    def stem_cin(self) -> int:
+        return self.in_channels * (2 if self.concat_low_res else 1)
+
+    @staticmethod
+    def from_model_flags(
+        image_size, num_channels, num_res_blocks, channel_mult, learn_sigma, class_cond, attention_resolutions,
+        num_heads, num_head_channels, num_heads_upsample, use_scale_shift_norm, resblock_updown,
+        use_new_attention_order, **_ignored,
+    ) -> "UNetConfig":
+        """script_util.py:130-184 create_model: the 2-D RGB UNetModel."""
+        if channel_mult == "":
+            mult = {256: (1, 1, 2, 2, 4, 4), 128: (1, 1, 2, 3, 4), 64: (1, 2, 3, 4)}[image_size]
+        else:
+            mult = tuple(int(m) for m in channel_mult.split(","))
+        ds = tuple(image_size // int(r) for r in attention_resolutions.split(","))
+        return UNetConfig(
+            image_size=image_size, in_channels=3, model_channels=num_channels, out_channels=6 if learn_sigma else 3,
+            num_res_blocks=num_res_blocks, attention_ds=ds, channel_mult=mult,
+            num_classes=1000 if class_cond else None, num_heads=num_heads, num_head_channels=num_head_channels,
+            num_heads_upsample=num_heads_upsample, use_scale_shift_norm=use_scale_shift_norm,
+            resblock_updown=resblock_updown, use_new_attention_order=use_new_attention_order,
+            dims=2, middle_attention=True, concat_low_res=False,
+        )
 
     @staticmethod
     def from_sr_flags(
@@ -94,7 +124,7 @@ def build_plan(cfg: UNetConfig) -> dict:
     mc = cfg.model_channels
     heads_up = cfg.num_heads if cfg.num_heads_upsample == -1 else cfg.num_heads_upsample
     ch = input_ch = int(cfg.channel_mult[0] * mc)
-    inputs = [[dict(kind="conv", prefix="input_blocks.0.0", cin=cfg.in_channels * 2, cout=ch, stride_hw=1)]]
+    inputs = [[dict(kind="conv", prefix="input_blocks.0.0", cin=cfg.stem_cin, cout=ch, stride_hw=1)]]
     chans = [ch]
     ds = 1
     for level, mult in enumerate(cfg.channel_mult):
@@ -116,7 +146,11 @@ def build_plan(cfg: UNetConfig) -> dict:
                 inputs.append([dict(kind="conv", prefix=f"input_blocks.{n}.0.op", cin=ch, cout=ch, stride_hw=2)])
             chans.append(ch)
             ds *= 2
-    middle = [_res("middle_block.0", ch, ch), _res("middle_block.1", ch, ch)]
+    if cfg.middle_attention:
+        middle = [_res("middle_block.0", ch, ch), _attn("middle_block.1", ch, _heads(cfg, ch, cfg.num_heads)),
+                  _res("middle_block.2", ch, ch)]
+    else:
+        middle = [_res("middle_block.0", ch, ch), _res("middle_block.1", ch, ch)]
     outputs = []
     outch = ch
     for level, _mult in list(enumerate(cfg.channel_mult))[::-1]:
@@ -153,22 +187,25 @@ def param_specs(cfg: UNetConfig) -> list:
     if cfg.num_classes is not None:
         specs.append(("label_emb.weight", (cfg.num_classes, ted)))
 
+    def k(n):
+        return (n,) * cfg.dims
+
     def layer_specs(L):
         p = L["prefix"]
         if L["kind"] in ("conv", "upconv"):
-            return [(p + ".weight", (L["cout"], L["cin"], 3, 3, 3)), (p + ".bias", (L["cout"],))]
+            return [(p + ".weight", (L["cout"], L["cin"], *k(3))), (p + ".bias", (L["cout"],))]
         if L["kind"] == "res":
             ci, co = L["cin"], L["cout"]
             e = 2 * co if cfg.use_scale_shift_norm else co
             out = [
                 (p + ".in_layers.0.weight", (ci,)), (p + ".in_layers.0.bias", (ci,)),
-                (p + ".in_layers.2.weight", (co, ci, 3, 3, 3)), (p + ".in_layers.2.bias", (co,)),
+                (p + ".in_layers.2.weight", (co, ci, *k(3))), (p + ".in_layers.2.bias", (co,)),
                 (p + ".emb_layers.1.weight", (e, ted)), (p + ".emb_layers.1.bias", (e,)),
                 (p + ".out_layers.0.weight", (co,)), (p + ".out_layers.0.bias", (co,)),
-                (p + ".out_layers.3.weight", (co, co, 3, 3, 3)), (p + ".out_layers.3.bias", (co,)),
+                (p + ".out_layers.3.weight", (co, co, *k(3))), (p + ".out_layers.3.bias", (co,)),
             ]
             if ci != co:
-                out += [(p + ".skip_connection.weight", (co, ci, 1, 1, 1)), (p + ".skip_connection.bias", (co,))]
+                out += [(p + ".skip_connection.weight", (co, ci, *k(1))), (p + ".skip_connection.bias", (co,))]
             return out
         if L["kind"] == "attn":
             c = L["ch"]
@@ -189,7 +226,7 @@ def param_specs(cfg: UNetConfig) -> list:
             specs += layer_specs(L)
     specs += [
         ("out.0.weight", (plan["out_norm_ch"],)), ("out.0.bias", (plan["out_norm_ch"],)),
-        ("out.2.weight", (cfg.out_channels, plan["out_conv_in"], 3, 3, 3)), ("out.2.bias", (cfg.out_channels,)),
+        ("out.2.weight", (cfg.out_channels, plan["out_conv_in"], *k(3))), ("out.2.bias", (cfg.out_channels,)),
     ]
     return specs
 
@@ -215,16 +252,24 @@ def _gn(x, sd, p):
 
 
 def _conv3(x, sd, p, stride=1):
-    return F.conv3d(x, sd[p + ".weight"], sd[p + ".bias"], stride=stride, padding=1)
+    """conv_nd (nn.py:22-32): Conv3d for (B,C,Z,H,W), Conv2d for (B,C,H,W); `stride` applies to (H, W)."""
+    if x.dim() == 4:
+        return F.conv2d(x, sd[p + ".weight"], sd[p + ".bias"], stride=stride, padding=1)
+    st = (1, stride, stride) if isinstance(stride, int) and stride != 1 else stride
+    return F.conv3d(x, sd[p + ".weight"], sd[p + ".bias"], stride=st, padding=1)
 
 
 def _up_hw(x):
-    """unet.py:100-105 nearest x2 on (H, W) only."""
+    """unet.py:100-108 nearest x2: on (H, W) only for dims=3, scale_factor=2 for dims=2."""
+    if x.dim() == 4:
+        return F.interpolate(x, scale_factor=2, mode="nearest")
     return F.interpolate(x, (x.shape[2], x.shape[3] * 2, x.shape[4] * 2), mode="nearest")
 
 
 def _down_hw(x):
-    """unet.py:129,136-137 AvgPool3d((1,2,2))."""
+    """unet.py:129,136-137 AvgPool3d((1,2,2)) / AvgPool2d(2)."""
+    if x.dim() == 4:
+        return F.avg_pool2d(x, kernel_size=2, stride=2)
     return F.avg_pool3d(x, kernel_size=(1, 2, 2), stride=(1, 2, 2))
 
 
@@ -238,7 +283,7 @@ def _resblock(x, emb, sd, L, cfg):
         h, x = _down_hw(h), _down_hw(x)
     h = _conv3(h, sd, p + ".in_layers.2")
     e = F.linear(F.silu(emb), sd[p + ".emb_layers.1.weight"], sd[p + ".emb_layers.1.bias"]).type(h.dtype)
-    e = e[:, :, None, None, None]
+    e = e[(..., *([None] * (h.dim() - 2)))]
     if cfg.use_scale_shift_norm:
         scale, shift = torch.chunk(e, 2, dim=1)
         h = _gn(h, sd, p + ".out_layers.0") * (1 + scale) + shift
@@ -247,7 +292,8 @@ def _resblock(x, emb, sd, L, cfg):
         h = F.silu(_gn(h + e, sd, p + ".out_layers.0"))
     h = _conv3(h, sd, p + ".out_layers.3")
     if L["cin"] != L["cout"]:
-        x = F.conv3d(x, sd[p + ".skip_connection.weight"], sd[p + ".skip_connection.bias"])
+        skip = F.conv2d if x.dim() == 4 else F.conv3d
+        x = skip(x, sd[p + ".skip_connection.weight"], sd[p + ".skip_connection.bias"])
     return x + h
 
 
@@ -286,8 +332,7 @@ def _run_layers(h, emb, sd, layers, cfg):
         elif k == "attn":
             h = _attention(h, sd, L, cfg)
         elif k == "conv":
-            s = L["stride_hw"]
-            h = _conv3(h, sd, L["prefix"], stride=(1, s, s))
+            h = _conv3(h, sd, L["prefix"], stride=L["stride_hw"])
         elif k == "upconv":
             h = _conv3(_up_hw(h), sd, L["prefix"])
         else:
@@ -297,14 +342,15 @@ def _run_layers(h, emb, sd, layers, cfg):
 
 @torch.no_grad()
 def unet_forward(cfg: UNetConfig, sd: dict, x: torch.Tensor, t: torch.Tensor,
-                 low_res: torch.Tensor, y: Optional[torch.Tensor] = None,
+                 low_res: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None,
                  taps: Optional[dict] = None) -> torch.Tensor:
     """SuperResModel_noatt.forward (unet.py:1687-1694) -> UNetModel_noatt.forward
     (:1015-1044).  x, low_res: (B,1,Z,H,W) fp32; t: (B,) already mapped to the
     ORIGINAL timestep numbering; returns (B,out_channels,Z,H,W) fp32.
     `taps`, if given, receives named intermediate tensors (for kernel tests)."""
     plan = build_plan(cfg)
-    h = torch.cat([x, low_res], dim=1)
+    assert x.dim() == cfg.dims + 2 and (low_res is not None) == cfg.concat_low_res
+    h = torch.cat([x, low_res], dim=1) if cfg.concat_low_res else x
     emb = timestep_embedding(t, cfg.model_channels)
     emb = F.linear(emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])
     emb = F.linear(F.silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])

@@ -201,3 +201,64 @@ def test_unet_with_tensor_core_attention_matches_oracle(fp16):
     kinds = [k for k, _, _ in model.profile_read()]
     assert kinds.count("attention") == 6  # ds = 2 and 4: one block each on the way down, two each on the way up
     assert max_rel(out, want) <= TOL[fp16]
+
+
+@pytest.mark.parametrize("fp16", [False, True])
+@pytest.mark.parametrize("name", list(cases.UNET2D_CASES))
+def test_other_model_classes_match_reference(golden_dir, name, fp16):
+    """the 2-D RGB UNetModel of create_model_and_diffusion (middle-block attention, optional
+    new attention order / class conditioning / learned sigma), the 2-D SuperResModel and a dims=3 UNetModel, on the
+    reference's own outputs (tests/golden/unet2d.npz).  2-D images run as one-plane volumes."""
+    from test_host import build_other_model
+    case = cases.UNET2D_CASES[name]
+    want = torch.from_numpy(np.load(os.path.join(golden_dir, "unet2d.npz"))[f"{name}/out"])
+    model = build_other_model(case)
+    model.load_state_dict(synth_state_dict(cases.unet2d_cfg(case), seed=case.get("seed", 0)))
+    model.to(DEV)
+    if fp16:
+        model.convert_to_fp16()
+    model.eval()
+    x, low = cases.unet2d_inputs(case)
+    kw = {}
+    if low is not None:
+        kw["low_res"] = low.to(DEV)
+    if "y" in case:
+        kw["y"] = torch.tensor(case["y"], device=DEV)
+    t = torch.tensor(case["t"], device=DEV)
+    out = model(x.to(DEV), t, **kw)
+    out2 = model(x.to(DEV), t, **kw)
+    torch.cuda.synchronize()
+    assert out.shape == want.shape and torch.equal(out, out2)
+    err = max_rel(out.cpu(), want)
+    print(f"{name} fp16={fp16}: eps max-rel {err:.3e}")
+    assert err <= TOL[fp16]
+
+
+def test_rgb_model_sampling_through_the_generic_path():
+    """create_model_and_diffusion end to end: p_sample_loop on (B,3,H,W) images goes UNet (library) -> update kernel
+    (library, C = 3, learned sigma) per step and equals stepping p_sample by hand with the same noise."""
+    flags = cases.model_flags(image_size=32, channel_mult="1,2", num_channels=32, num_res_blocks=1, learn_sigma=True,
+                              attention_resolutions="16", timestep_respacing="4")
+    model, diffusion = su.create_model_and_diffusion(**flags)
+    model.load_state_dict(synth_state_dict(cases.UNetConfig.from_model_flags(**flags), seed=6))
+    model.to(DEV).eval()
+    shape = (2, 3, 32, 32)
+    g = torch.Generator().manual_seed(5)
+    x_T = torch.randn(shape, generator=g).to(DEV)
+    noises = [torch.randn(shape, generator=g).to(DEV) for _ in range(4)]
+    a = diffusion.p_sample_loop(model, shape, noise=x_T, step_noise=noises)
+    img = x_T
+    for k, i in enumerate(range(3, -1, -1)):
+        t = torch.tensor([i, i], device=DEV)
+        img = diffusion.p_sample(model, img, t, noise=noises[k])["sample"]
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, img)
+    # one step against the CPU oracle's update (gaussian_diffusion.py:232-326,395-439) fed with this model's own eps
+    from oracle.sampler import model_timesteps, p_sample as o_p_sample
+    from oracle.schedule import make_tables
+    tabs = make_tables(steps=1000, learn_sigma=True, noise_schedule="linear", timestep_respacing="4")
+    t = torch.tensor([2, 2])
+    mo = model(x_T, model_timesteps(tabs, t).to(DEV)).cpu()
+    got = diffusion.p_sample(model, x_T, t.to(DEV), noise=noises[0])["sample"].cpu()
+    want = o_p_sample(tabs, mo, x_T.cpu(), t, noises[0].cpu(), True)["sample"]
+    assert torch.allclose(got, want, rtol=0, atol=2e-6)

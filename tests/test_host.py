@@ -35,13 +35,36 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/ddpm3d.h but not exported"
     assert declared == set(N.SIGNATURES), "ctypes binding and header disagree"
-    assert N.lib().ddpm3d_abi_version() == 2
+    assert N.lib().ddpm3d_abi_version() == 3
 
 
 def test_struct_layouts_match_header():
     assert C.sizeof(N.StepScalars) == 64
     assert C.sizeof(N.ProfRecord) == 24
-    assert C.sizeof(N.Config) == 4 * (6 + 8 + 1 + 8 + 8)
+    assert C.sizeof(N.Config) == 4 * (6 + 8 + 1 + 8 + 8 + 3)
+
+
+def build_other_model(case):
+    """The model classes of cases.UNET2D_CASES through the drop-in factory / class names."""
+    from ddpm3d_b200 import unet
+    if case["kind"] == "create_model":
+        return su.create_model_and_diffusion(**cases.model_flags(**case["flags"]))[0]
+    return getattr(unet, case["kind"])(**case["ctor"])
+
+
+@pytest.mark.parametrize("name", list(cases.UNET2D_CASES))
+def test_state_dict_contract_other_model_classes(golden_dir, name):
+    """create_model_and_diffusion's 2-D UNetModel, SuperResModel and a dims=3 UNetModel: keys, order and shapes of
+    the native topology == the reference module's state_dict(); forward without a GPU fails loudly."""
+    meta = json.load(open(os.path.join(golden_dir, "state_dict_keys_2d.json")))[name]
+    case = cases.UNET2D_CASES[name]
+    model = build_other_model(case)
+    assert [[k, list(v.shape)] for k, v in model.state_dict().items()] == meta
+    assert not model._fused_sampler
+    if not torch.cuda.is_available():
+        x, low = cases.unet2d_inputs(case)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            model(x, torch.tensor(case["t"]), **({"low_res": low} if low is not None else {}))
 
 
 @pytest.mark.parametrize("name", ["C1", "C2", "tiny", "attn", "plainconv", "classcond", "wide"])
@@ -125,8 +148,16 @@ def test_factory_defaults_and_argparse_roundtrip():
     assert kw["use_fp16"] is True and kw["large_size"] == 96 and kw["attention_resolutions"] == "1000"
     with pytest.raises(argparse.ArgumentTypeError):
         su.str2bool("maybe")
+    # create_model_and_diffusion (script_util.py:74-127): 23 kwargs, defaults build the 64x64 RGB UNetModel
+    md = su.model_and_diffusion_defaults()
+    assert len(md) == 23
+    m, dif = su.create_model_and_diffusion(**{**md, "num_channels": 32, "num_res_blocks": 1})
+    assert m.dims == 2 and m.in_channels == 3 and m.out_channels == 3 and m._middle_attention
+    assert dif.num_timesteps == 1000
+    with pytest.raises(ValueError):
+        su.create_model(48, 32, 1)
     with pytest.raises(NotImplementedError):
-        su.create_model_and_diffusion(*([None] * 23))
+        su.create_model(512, 32, 1)
 
 
 def test_model_surface_without_gpu():
