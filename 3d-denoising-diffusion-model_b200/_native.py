@@ -74,6 +74,7 @@ SIGNATURES = {
     "ddpm3d_k_groupnorm": (_I, [_I, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
     "ddpm3d_k_timestep_embedding": (_I, [_P, _P, _P, _I, _I, _P]),
     "ddpm3d_k_attention": (_I, [_I, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ddpm3d_k_attention_window": (_I, [_I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "ddpm3d_k_extract_patch": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "ddpm3d_k_hann_accumulate": (_I, [_P, _P, C.c_double, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ddpm3d_k_hann_finalize": (_I, [_P, _P, C.c_int64, _P]),

@@ -14,7 +14,7 @@ constexpr int KT = 32;   // keys per smem tile
 
 template <typename T, int CH>
 __global__ void __launch_bounds__(QB) attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int T_tok, int C,
-                                                       int heads, int ch, int new_order) {
+                                                       int heads, int ch, int new_order, int q_begin, int Tq) {
   __shared__ float ks[KT][CH];
   __shared__ float vs[KT][CH];
   const int bh = blockIdx.y, b = bh / heads, h = bh % heads;
@@ -23,8 +23,9 @@ __global__ void __launch_bounds__(QB) attention_kernel(const T* __restrict__ qkv
   const int voff = new_order ? 2 * C + h * ch : h * 3 * ch + 2 * ch;
   const int64_t row_stride = 3 * (int64_t)C;
   const T* base = qkv + (int64_t)b * T_tok * row_stride;
-  const int t = blockIdx.x * QB + threadIdx.x;
-  const bool live = t < T_tok;
+  const int tq = blockIdx.x * QB + threadIdx.x;  // query index inside the window
+  const int t = q_begin + tq;
+  const bool live = tq < Tq;
   const float scale = 1.0f / sqrtf(sqrtf((float)ch));
 
   float q[CH], acc[CH];
@@ -58,19 +59,19 @@ __global__ void __launch_bounds__(QB) attention_kernel(const T* __restrict__ qkv
   }
   if (live) {
     const float inv = 1.0f / l;
-    T* o = out + ((int64_t)b * T_tok + t) * C + h * ch;
+    T* o = out + ((int64_t)b * Tq + tq) * C + h * ch;
     for (int c = 0; c < ch; ++c) o[c] = from_f32<T>(acc[c] * inv);
   }
 }
 
 template <typename T>
-int launch(const void* qkv, void* out, int B, int T_tok, int C, int heads, int new_order, cudaStream_t s) {
+int launch(const void* qkv, void* out, int B, int T_tok, int C, int heads, int new_order, int q_begin, int Tq, cudaStream_t s) {
   const int ch = C / heads;
-  dim3 grid((unsigned)ceil_div(T_tok, QB), (unsigned)(B * heads));
-  if (ch <= 16) attention_kernel<T, 16><<<grid, QB, 0, s>>>((const T*)qkv, (T*)out, T_tok, C, heads, ch, new_order);
-  else if (ch <= 32) attention_kernel<T, 32><<<grid, QB, 0, s>>>((const T*)qkv, (T*)out, T_tok, C, heads, ch, new_order);
-  else if (ch <= 64) attention_kernel<T, 64><<<grid, QB, 0, s>>>((const T*)qkv, (T*)out, T_tok, C, heads, ch, new_order);
-  else if (ch <= 128) attention_kernel<T, 128><<<grid, QB, 0, s>>>((const T*)qkv, (T*)out, T_tok, C, heads, ch, new_order);
+  dim3 grid((unsigned)ceil_div(Tq, QB), (unsigned)(B * heads));
+  if (ch <= 16) attention_kernel<T, 16><<<grid, QB, 0, s>>>((const T*)qkv, (T*)out, T_tok, C, heads, ch, new_order, q_begin, Tq);
+  else if (ch <= 32) attention_kernel<T, 32><<<grid, QB, 0, s>>>((const T*)qkv, (T*)out, T_tok, C, heads, ch, new_order, q_begin, Tq);
+  else if (ch <= 64) attention_kernel<T, 64><<<grid, QB, 0, s>>>((const T*)qkv, (T*)out, T_tok, C, heads, ch, new_order, q_begin, Tq);
+  else if (ch <= 128) attention_kernel<T, 128><<<grid, QB, 0, s>>>((const T*)qkv, (T*)out, T_tok, C, heads, ch, new_order, q_begin, Tq);
   else { set_error("attention: head width > 128 unsupported"); return DDPM3D_ERR_ARG; }
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
@@ -79,13 +80,15 @@ int launch(const void* qkv, void* out, int B, int T_tok, int C, int heads, int n
 }  // namespace
 
 int attention_k(int dt, const void* qkv, void* out, int B, int T_tok, int C, int heads, int new_order, void* scratch,
-                size_t scratch_bytes, cudaStream_t s) {
+                size_t scratch_bytes, cudaStream_t s, int q_begin, int q_count) {
   DD_CHECK(heads > 0 && C % heads == 0, DDPM3D_ERR_ARG, "attention: C must be divisible by heads");
+  if (q_count < 0) { q_begin = 0; q_count = T_tok; }
+  DD_CHECK(q_begin >= 0 && q_count >= 1 && q_begin + q_count <= T_tok, DDPM3D_ERR_ARG, "attention: query window out of range");
   const size_t need = attention_tc_scratch_bytes(dt, B, T_tok, C, heads);
-  if (need > 0 && scratch && scratch_bytes >= need) return attention_tc(dt, qkv, out, B, T_tok, C, heads, new_order, scratch, s);
-  if (dt == DDPM3D_BF16) return launch<bf16>(qkv, out, B, T_tok, C, heads, new_order, s);
-  if (dt == DDPM3D_FP16) return launch<f16>(qkv, out, B, T_tok, C, heads, new_order, s);
-  return launch<float>(qkv, out, B, T_tok, C, heads, new_order, s);
+  if (need > 0 && scratch && scratch_bytes >= need) return attention_tc(dt, qkv, out, B, T_tok, C, heads, new_order, scratch, s, q_begin, q_count);
+  if (dt == DDPM3D_BF16) return launch<bf16>(qkv, out, B, T_tok, C, heads, new_order, q_begin, q_count, s);
+  if (dt == DDPM3D_FP16) return launch<f16>(qkv, out, B, T_tok, C, heads, new_order, q_begin, q_count, s);
+  return launch<float>(qkv, out, B, T_tok, C, heads, new_order, q_begin, q_count, s);
 }
 
 }  // namespace ddpm3d

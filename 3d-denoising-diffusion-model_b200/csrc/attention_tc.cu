@@ -25,6 +25,7 @@ constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 channels x 2 B
 
 struct AttnParams {
   int B, T, H, C, Tp;
+  int qb, Tq;                     // query window [qb, qb + Tq) of the T keys (z-slab sharding); out is [B][Tq][C]
   int qoff, koff, voff, hstride;  // channel offsets of q / k / v for head 0 and the per-head stride inside qkv
   float scale2;                   // 1 / sqrt(ch): the reference scales q and k by ch^-1/4 each
   void* out;
@@ -61,12 +62,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
   const uint32_t q_full = bar0, k_full = bar0 + 8, k_empty = bar0 + 16, v_full = bar0 + 24, v_empty = bar0 + 32,
                  s_full = bar0 + 40, s_empty = bar0 + 48, p_full = bar0 + 56, o_full = bar0 + 64;
 
-  const int nq = (p.T + QT - 1) / QT, nk = (p.T + KT - 1) / KT;
+  const int nq = (p.Tq + QT - 1) / QT, nk = (p.T + KT - 1) / KT;
   int blk = blockIdx.x;
   const int qt = blk % nq; blk /= nq;
   const int h = blk % p.H;
   const int b = blk / p.H;
-  const int q0 = qt * QT;
+  const int q0 = p.qb + qt * QT;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapQKV);
@@ -214,14 +215,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
     // epilogue: O -> out[b][t][h*64 + c]
     mbar_wait(o_full, 0);
     tc_fence_after();
-    const int t = q0 + row;
+    const int tq = q0 - p.qb + row;  // query index inside the window
 #pragma unroll 1
     for (int c2 = 0; c2 < 2; ++c2) {
       uint32_t r[32];
       tmem_ld32(o_tmem + t_lane + (uint32_t)(c2 * 32), r);
       tmem_ld_wait();
-      if (t < p.T) {
-        T* op = (T*)p.out + ((size_t)b * p.T + t) * p.C + h * CH + c2 * 32;
+      if (tq < p.Tq) {
+        T* op = (T*)p.out + ((size_t)b * p.Tq + tq) * p.C + h * CH + c2 * 32;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint32_t w4[4];
@@ -256,7 +257,7 @@ int launch_attention(const void* qkv, void* out, void* scratch, const AttnParams
   if (first_use_on_device(&configured)) {
     DD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  const int nq = (int)ceil_div(p.T, QT);
+  const int nq = (int)ceil_div(p.Tq, QT);
   attention_tc_kernel<T><<<p.B * p.H * nq, AT_THREADS, smem, s>>>(mapQKV, mapVt, p);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
@@ -270,10 +271,14 @@ size_t attention_tc_scratch_bytes(int dt, int B, int T, int C, int heads) {
   return (size_t)B * C * Tp * 2;
 }
 
-int attention_tc(int dt, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, void* scratch, cudaStream_t s) {
+int attention_tc(int dt, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, void* scratch, cudaStream_t s,
+                 int q_begin, int q_count) {
   DD_CHECK(attention_tc_scratch_bytes(dt, B, T, C, heads) > 0 && scratch, DDPM3D_ERR_ARG, "attention_tc: not eligible");
+  if (q_count < 0) { q_begin = 0; q_count = T; }
+  DD_CHECK(q_begin >= 0 && q_count >= 1 && q_begin + q_count <= T, DDPM3D_ERR_ARG, "attention_tc: query window out of range");
   AttnParams p{};
   p.B = B; p.T = T; p.H = heads; p.C = C;
+  p.qb = q_begin; p.Tq = q_count;
   p.Tp = (int)ceil_div(T, 64) * 64;
   if (new_order) { p.qoff = 0; p.koff = C; p.voff = 2 * C; p.hstride = CH; }
   else { p.qoff = 0; p.koff = CH; p.voff = 2 * CH; p.hstride = 3 * CH; }

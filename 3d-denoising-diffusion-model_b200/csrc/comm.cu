@@ -126,4 +126,13 @@ int comm_allgather_f64(const SlabComm& c, const double* send, double* recv, size
   return DDPM3D_OK;
 }
 
+int comm_allgather_slabs(const SlabComm& c, const void* send, void* recv, int B, size_t bytes, size_t send_bstride,
+                         size_t recv_bstride, cudaStream_t s) {
+  DD_NCCL(api().GroupStart());
+  for (int b = 0; b < B; ++b)
+    DD_NCCL(api().AllGather((const char*)send + b * send_bstride, (char*)recv + b * recv_bstride, bytes, NCCL_INT8, (NcclComm)c.comm, s));
+  DD_NCCL(api().GroupEnd());
+  return DDPM3D_OK;
+}
+
 }  // namespace ddpm3d

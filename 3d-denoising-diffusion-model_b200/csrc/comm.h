@@ -21,5 +21,8 @@ void comm_destroy(SlabComm* c);
 int comm_halo_exchange(const SlabComm& c, void* base, int B, int Zl, size_t plane_bytes, cudaStream_t s);
 // all-gather `count` doubles per rank: recv[world][count]
 int comm_allgather_f64(const SlabComm& c, const double* send, double* recv, size_t count, cudaStream_t s);
+// all-gather `bytes` bytes per rank and per batch element: recv + b * recv_bstride = [world][bytes] (rank order = z order)
+int comm_allgather_slabs(const SlabComm& c, const void* send, void* recv, int B, size_t bytes, size_t send_bstride,
+                         size_t recv_bstride, cudaStream_t s);
 
 }  // namespace ddpm3d

@@ -668,7 +668,6 @@ int run_attn(Run& R, const Layer& L, const Act& x, Act* out) {
   ddpm3d_ctx* ctx = R.ctx;
   const int dt = ctx->dt, C = L.cin, H = x.H, W = x.W;
   DD_CHECK(x.C == C, DDPM3D_ERR_STATE, "internal: attention channel mismatch");
-  DD_CHECK(!R.zp, DDPM3D_ERR_ARG, "z-slab sharding does not support attention blocks yet (K/V all-gather)");
   out->C = C; out->H = H; out->W = W;
   out->p = R.arena.alloc(R.act_bytes(H, W, C));
   const size_t mark = R.arena.off;
@@ -680,15 +679,36 @@ int run_attn(Run& R, const Layer& L, const Act& x, Act* out) {
   ConvArgs c{};
   c.dt = dt; c.main = {n, C}; c.taps = 1; c.w = L.c1.w; c.bias = L.c1.bias; c.out = qkv; c.Ho = H; c.Wo = W; c.Cout = 3 * C;
   DD_TRY(R.conv(c));
+  // z-slab sharding: the queries stay local, keys and values of the whole volume are all-gathered
+  // along T.  The packed qkv rows travel as they are (the unused third, the other ranks' queries, is cheaper than a
+  // repack at these resolutions); rank order = z order, so the gathered tensor is the global [T][3C] token matrix.
+  const int world = R.zp ? ctx->slab.world : 1;
+  const int T_local = R.Z * H * W, T_all = T_local * world;
+  const void* qkv_all = qkv;
+  int q_begin = 0;
+  if (R.zp) {
+    DD_CHECK(ctx->slab.z_total == world * R.Z && ctx->slab.z_begin == ctx->slab.rank * R.Z, DDPM3D_ERR_ARG,
+             "z-slab sharding with attention blocks needs equal slabs in rank order (z_total = world * Z)");
+    void* gathered = R.arena.alloc((size_t)world * R.act_bytes(H, W, 3 * C));
+    ++R.launches;
+    if (!R.arena.dry) {
+      const size_t per_b = (size_t)T_local * 3 * C * ctx->esz;
+      R.prof_begin(10, (double)R.B * per_b * world);
+      const int r = comm_allgather_slabs(ctx->slab, qkv, gathered, R.B, per_b, per_b, per_b * world, R.s);
+      R.prof_end();
+      DD_TRY(r);
+    }
+    qkv_all = gathered;
+    q_begin = ctx->slab.rank * T_local;
+  }
   void* a = R.arena.alloc(R.act_bytes(H, W, C));
-  const size_t at_bytes = ctx->conv_path == 1 ? 0 : attention_tc_scratch_bytes(dt, R.B, R.Z * H * W, C, L.heads);
+  const size_t at_bytes = ctx->conv_path == 1 ? 0 : attention_tc_scratch_bytes(dt, R.B, T_all, C, L.heads);
   void* at_scratch = at_bytes ? R.arena.alloc(at_bytes) : nullptr;
   R.launches += at_bytes ? 2 : 1;
   if (!R.arena.dry) {
-    const double T = (double)R.Z * H * W;
-    R.prof_begin(7, 4.0 * R.B * T * T * C);
-    const int r = attention_k(dt, qkv, a, R.B, R.Z * H * W, C, L.heads, ctx->cfg.use_new_attention_order, at_scratch, at_bytes,
-                              R.s);
+    R.prof_begin(7, 4.0 * R.B * (double)T_local * T_all * C);
+    const int r = attention_k(dt, qkv_all, a, R.B, T_all, C, L.heads, ctx->cfg.use_new_attention_order, at_scratch, at_bytes,
+                              R.s, q_begin, T_local);
     R.prof_end();
     DD_TRY(r);
   }
@@ -1466,6 +1486,17 @@ int ddpm3d_k_attention(int dtype, const void* qkv, void* out, int B, int T, int 
   void* sc = nullptr;
   if (need) DD_TRY(g_scratch.get(need, &sc));
   return attention_k(dtype, qkv, out, B, T, C, heads, new_order, sc, need, (cudaStream_t)stream);
+}
+
+int ddpm3d_k_attention_window(int dtype, const void* qkv, void* out, int B, int T, int C, int heads, int new_order,
+                              int q_begin, int q_count, void* stream) {
+  DD_CHECK(qkv && out, DDPM3D_ERR_ARG, "k_attention_window: null argument");
+  const int path = new_order >> 8;
+  new_order &= 0xff;
+  const size_t need = path == 1 ? 0 : attention_tc_scratch_bytes(dtype, B, T, C, heads);
+  void* sc = nullptr;
+  if (need) DD_TRY(g_scratch.get(need, &sc));
+  return attention_k(dtype, qkv, out, B, T, C, heads, new_order, sc, need, (cudaStream_t)stream, q_begin, q_count);
 }
 
 }  // extern "C"

@@ -154,9 +154,12 @@ int step_advance_k(int32_t* step_counter, float* t_model, const ddpm3d_step_scal
 // ---- attention core (K12) --------------------------------------------------------------------
 // scratch (optional): attention_tc_scratch_bytes() bytes for the tensor-core path (64-wide heads, 16-bit types);
 // without it, or for other head widths / fp32, the CUDA-core kernel runs
-int attention_k(int dt, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, void* scratch,
-                size_t scratch_bytes, cudaStream_t s);
+// q_begin / q_count: the queries are tokens [q_begin, q_begin + q_count) of the T_tok keys (z-slab sharding: local
+// queries against the all-gathered keys / values); out is [B][q_count][C].  q_count < 0 = all tokens.
+int attention_k(int dt, const void* qkv, void* out, int B, int T_tok, int C, int heads, int new_order, void* scratch,
+                size_t scratch_bytes, cudaStream_t s, int q_begin = 0, int q_count = -1);
 size_t attention_tc_scratch_bytes(int dt, int B, int T, int C, int heads);
-int attention_tc(int dt, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, void* scratch, cudaStream_t s);
+int attention_tc(int dt, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, void* scratch, cudaStream_t s,
+                 int q_begin = 0, int q_count = -1);
 
 }  // namespace ddpm3d

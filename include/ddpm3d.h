@@ -243,6 +243,10 @@ int ddpm3d_k_timestep_embedding(const float* t, const float* freqs, float* out, 
 /* QKVAttentionLegacy / QKVAttention core (unet.py:328-393): qkv [B][T][3C] channels-last -> out [B][T][C].
  * 16-bit types with 64-wide heads run the fused tcgen05 kernel; new_order | 0x100 forces the CUDA-core kernel. */
 int ddpm3d_k_attention(int dtype, const void* qkv, void* out, int B, int T, int C, int heads, int new_order, void* stream);
+/* The same with the queries restricted to tokens [q_begin, q_begin + q_count) of the T keys (what a z-slab rank runs
+ * after the K/V all-gather); out is [B][q_count][C]. */
+int ddpm3d_k_attention_window(int dtype, const void* qkv, void* out, int B, int T, int C, int heads, int new_order,
+                              int q_begin, int q_count, void* stream);
 
 /* ---- the steps either side of the loop (scripts/test.py) and the ensemble reduction ----------------
  * extract_patch: scripts/test.py:205-230 -- vol device fp32 (D,H,W); out (P,P,P) in (Z,H,W) order, zero padded. */

@@ -165,6 +165,25 @@ def test_attention_core(dt, B, T, C, heads, new_order):
     assert max_rel(out.float().permute(0, 2, 1).cpu(), ref) <= tol
 
 
+@pytest.mark.parametrize("dt", [N.FP32, N.BF16])
+@pytest.mark.parametrize("B,T,C,heads,q_begin,q_count", [(1, 300, 64, 4, 100, 150), (2, 512, 128, 2, 256, 256),
+                                                          (1, 1000, 192, 3, 872, 128), (2, 384, 64, 1, 0, 192)])
+def test_attention_query_window(dt, B, T, C, heads, q_begin, q_count):
+    """What a z-slab rank runs after the K/V all-gather: queries [q_begin, q_begin + q_count) against all T keys.
+    Rows are independent, so the window must equal the slice of the full result bit for bit (both kernels)."""
+    g = torch.Generator().manual_seed(T + q_begin)
+    tdt = TDT[dt]
+    qd = torch.randn((B, T, 3 * C), generator=g).to(DEV, tdt)
+    full = torch.empty((B, T, C), device=DEV, dtype=tdt)
+    win = torch.full((B, q_count, C), float("nan"), device=DEV, dtype=tdt)
+    N.check(N.lib().ddpm3d_k_attention(dt, N.ptr(qd), N.ptr(full), B, T, C, heads, 0, stream()))
+    N.check(N.lib().ddpm3d_k_attention_window(dt, N.ptr(qd), N.ptr(win), B, T, C, heads, 0, q_begin, q_count, stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(win, full[:, q_begin:q_begin + q_count])
+    with pytest.raises(RuntimeError):
+        N.check(N.lib().ddpm3d_k_attention_window(dt, N.ptr(qd), N.ptr(win), B, T, C, heads, 0, T - 1, q_count, stream()))
+
+
 @pytest.mark.parametrize("i", [i for i, c in enumerate(cases.PMV_CASES) if not (c.get("previous_x") or c.get("learned"))])
 def test_ddim_update_bit_exact(golden_dir, i):
     """ddim_sample (gaussian_diffusion.py:537-585) against the unmodified reference's outputs.  pred_xstart is

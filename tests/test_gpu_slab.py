@@ -1,5 +1,6 @@
 """-m gpu, needs >= 2 GPUs (skipped otherwise; run with `gpurun --gpus 2`): one volume sharded as z-slabs
-over two ranks (halo exchange + GroupNorm all-gather over NCCL) must reproduce the single-GPU result."""
+over two ranks (halo exchange + GroupNorm all-gather + K/V all-gather for attention blocks, over NCCL) must
+reproduce the single-GPU result."""
 import os
 import sys
 
@@ -28,10 +29,17 @@ def _worker(rank, world, port, q):
     try:
         # the last case is the shipped network on 96x96 planes: 8 planes per rank make 296 strip tiles, so the
         # halo planes are read by the strip kernel's row-shifted descriptors (the C4 bench configuration)
-        for mode, shape, tol, ch in ((False, (1, 1, 10, 16, 16), 2e-5, 64), (False, (2, 1, 9, 16, 32), 2e-5, 64),
-                                     (True, (1, 1, 12, 32, 32), 3e-2, 64), (True, (1, 1, 16, 96, 96), 3e-2, 128)):
+        # the "8,4" / "8" cases carry attention blocks (ds = 2, 4): local queries against all-gathered keys / values,
+        # CUDA-core kernel in fp32, tcgen05 kernel (64-wide heads) in bf16, batch 2 = one all-gather per element
+        for mode, shape, tol, ch, att in ((False, (1, 1, 10, 16, 16), 2e-5, 64, "1000"),
+                                          (False, (2, 1, 9, 16, 32), 2e-5, 64, "1000"),
+                                          (True, (1, 1, 12, 32, 32), 3e-2, 64, "1000"),
+                                          (False, (1, 1, 8, 16, 16), 2e-5, 64, "8,4"),
+                                          (False, (2, 1, 4, 16, 16), 2e-5, 64, "8"),
+                                          (True, (1, 1, 8, 32, 32), 3e-2, 64, "8,4"),
+                                          (True, (1, 1, 16, 96, 96), 3e-2, 128, "1000")):
             over = dict(large_size=16, small_size=16, num_channels=ch, num_res_blocks=2, num_head_channels=64,
-                        timestep_respacing="10" if ch == 64 else "3", use_fp16=bool(mode))
+                        timestep_respacing="10" if ch == 64 else "3", use_fp16=bool(mode), attention_resolutions=att)
             flags = cases.sr_flags(**over)
             cfg = cases.cfg_from_flags(flags)
             sd = synth_state_dict(cfg, seed=11)
@@ -63,7 +71,7 @@ def _worker(rank, world, port, q):
             want_s = diffusion.p_sample_loop(single, shape, noise=x_T, model_kwargs={"low_res": low}, rng="philox", seed=5)
             got_s = slab.sample_volume_slabs(sharded, diffusion, low, noise=x_T, rng="philox", seed=5)
             e2 = float((got_s - want_s).pow(2).mean().sqrt() / want_s.pow(2).mean().sqrt())  # NRMSE of the volume
-            res[str((mode, shape))] = (e1, e2, tol, sharded.launch_count())
+            res[str((mode, shape, att))] = (e1, e2, tol, sharded.launch_count())
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
