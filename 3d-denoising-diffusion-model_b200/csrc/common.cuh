@@ -143,7 +143,7 @@ __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v));
 // Two SFU ops per element: at 16 SFU lanes/clk/SM this caps the GroupNorm apply pass near 4.5 TB/s under the
 // power-capped clock.  The one-SFU form h + h*tanh.approx(h), h = x/2, was measured 8 % faster on that pass but its
 // 2^-11 error is a BIAS (same sign for all positive activations) that the next convolution sums coherently: eps
-// max-rel of the shipped network went 9.0e-3 -> 1.08e-2, across the 1e-2 line, so it is not used.
+// max-rel of the shipped network went 9.4e-3 -> 1.08e-2, across the 1e-2 line, so it is not used.
 __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 template <typename T> __device__ __forceinline__ float silu_t(float v) { return sizeof(T) == 2 ? silu_fast(v) : silu_f(v); }
 

@@ -1,11 +1,12 @@
-// The two thin convolutions at the ends of the network, on the CUDA cores:
+// The two thin convolutions at the ends of the network:
 //
-//  * stem:  Conv3d(2 -> C, 3x3x3)   (unet.py:809-811)  K = 54: far too short for a tensor-core tile,
-//           bound by writing the (B,Z,H,W,C) result.
+//  * stem:  Conv3d(2 -> C, 3x3x3)   (unet.py:809-811)  K = 54, bound by writing the (B,Z,H,W,C) result.
+//           16-bit modes: one tcgen05 tile per 128 voxels, im2col rows built by hand (stem_tc_kernel);
+//           fp32 mode: CUDA cores with an smem-staged halo brick (stem_conv_kernel).
 //  * head:  Conv3d(C -> 1|2, 3x3x3) (unet.py:993-997)  N = 1|2: fp32 in the reference (it runs after
-//           h.type(x.dtype), unet.py:1043-1044), bound by reading the fp32 input once.
+//           h.type(x.dtype), unet.py:1043-1044), so it stays fp32 FMA on the CUDA cores; bound by smem reads.
 //
-// Both stage a haloed input brick in shared memory (zero padding applied while staging) so every
+// The CUDA-core kernels stage a haloed input brick in shared memory (zero padding applied while staging) so every
 // input voxel is fetched from L2/HBM once per CTA and reused by the 27 taps from smem.
 #include <type_traits>
 

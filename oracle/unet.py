@@ -238,7 +238,7 @@ def param_specs(cfg: UNetConfig) -> list:
 def timestep_embedding(t: torch.Tensor, dim: int, max_period: int = 10000) -> torch.Tensor:
     """guided_diffusion/nn.py:103-121 -- cos block first, then sin."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(t.device)
     ang = t[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1)
     if dim % 2:
@@ -343,14 +343,19 @@ def _run_layers(h, emb, sd, layers, cfg):
 @torch.no_grad()
 def unet_forward(cfg: UNetConfig, sd: dict, x: torch.Tensor, t: torch.Tensor,
                  low_res: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None,
-                 taps: Optional[dict] = None) -> torch.Tensor:
+                 taps: Optional[dict] = None, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """SuperResModel_noatt.forward (unet.py:1687-1694) -> UNetModel_noatt.forward
     (:1015-1044).  x, low_res: (B,1,Z,H,W) fp32; t: (B,) already mapped to the
     ORIGINAL timestep numbering; returns (B,out_channels,Z,H,W) fp32.
-    `taps`, if given, receives named intermediate tensors (for kernel tests)."""
+    `taps`, if given, receives named intermediate tensors (for kernel tests).
+    `dtype` (torch.float16 / bfloat16): the reference's use_fp16 flow -- h.type(self.dtype) before the input blocks
+    (unet.py:1035) and h.type(x.dtype) before `out` (:1043); `sd` must then hold the torso's conv tensors in that
+    dtype (fp16_util.py:15-22).  Half-precision pooling only runs on CUDA, so this is a GPU-side cross-check."""
     plan = build_plan(cfg)
     assert x.dim() == cfg.dims + 2 and (low_res is not None) == cfg.concat_low_res
     h = torch.cat([x, low_res], dim=1) if cfg.concat_low_res else x
+    if dtype is not None:
+        h = h.type(dtype)
     emb = timestep_embedding(t, cfg.model_channels)
     emb = F.linear(emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])
     emb = F.linear(F.silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
@@ -373,5 +378,6 @@ def unet_forward(cfg: UNetConfig, sd: dict, x: torch.Tensor, t: torch.Tensor,
         h = _run_layers(h, emb, sd, blk, cfg)
         if taps is not None:
             taps[f"output_blocks.{i}"] = h
+    h = h.type(x.dtype)
     h = F.silu(_gn(h, sd, "out.0"))
     return _conv3(h, sd, "out.2")
