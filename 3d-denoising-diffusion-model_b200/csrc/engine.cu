@@ -172,7 +172,7 @@ struct ddpm3d_ctx {
   float* d_img = nullptr;
   size_t img_cap = 0;
   // options
-  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 1, fold_identity = 1, stem_tc = 1;
+  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 1, fold_identity = 1, stem_tc = 1, head_v2 = 1;
   float* splitk_buf = nullptr;  // fp32 partial tiles of split-K convolutions (sized by the dry run)
   size_t splitk_cap = 0, splitk_need = 0;
   cudaStream_t cap_stream = nullptr;
@@ -521,6 +521,7 @@ struct Run {
     a.cluster_allowed = ctx->cluster;
     a.strip_allowed = ctx->strip;
     a.stem_tc_allowed = ctx->stem_tc;
+    a.head_v2_allowed = ctx->head_v2;
     ++launches;
     if (arena.dry) {
       if (is_half_dt(a.dt) && ctx->conv_path != 1 && a.splitk_allowed)
@@ -1384,6 +1385,7 @@ int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value) {
   else if (n == "strip") ctx->strip = value != 0;
   else if (n == "fold_identity") ctx->fold_identity = value != 0;
   else if (n == "stem_tc") ctx->stem_tc = value != 0;
+  else if (n == "head_v2") ctx->head_v2 = value != 0;
   else { set_error("unknown option: " + n); return DDPM3D_ERR_ARG; }
   // cached graphs bake the options in
   if (ctx->device >= 0) {

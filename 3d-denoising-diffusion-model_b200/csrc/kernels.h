@@ -44,6 +44,7 @@ struct ConvArgs {
   int splitk_allowed = 0;
   int strip_allowed = 1;    // (unit-test entry point default; the engine passes its `strip` option) strip variant: A staged once per (dz, chunk), 9 in-plane taps by row-shifted descriptors
   int cluster_allowed = 1;  // 2-CTA clusters sharing the weight tile by TMA multicast (big layers)
+  int head_v2_allowed = 1;  // head conv: 32x16x4 bricks, 8 voxels per thread, cp.async double-buffered channel stages
   int stem_tc_allowed = 1;  // Cin == 2 stem as one M128 x Cout x K64 tcgen05 tile per 128 voxels (16-bit modes)
 };
 constexpr int CHSUM_SLOTS = 148;  // one per persistent CTA (unused slots are zeroed by the launcher)
