@@ -31,13 +31,17 @@ def _worker(rank, world, port, q):
         # halo planes are read by the strip kernel's row-shifted descriptors (the C4 bench configuration)
         # the "8,4" / "8" cases carry attention blocks (ds = 2, 4): local queries against all-gathered keys / values,
         # CUDA-core kernel in fp32, tcgen05 kernel (64-wide heads) in bf16, batch 2 = one all-gather per element
-        for mode, shape, tol, ch, att in ((False, (1, 1, 10, 16, 16), 2e-5, 64, "1000"),
+        pick = os.environ.get("DDPM3D_SLAB_CASES")  # e.g. "0,5": run a subset (quick re-checks)
+        for idx, (mode, shape, tol, ch, att) in enumerate((
+                                          (False, (1, 1, 10, 16, 16), 2e-5, 64, "1000"),
                                           (False, (2, 1, 9, 16, 32), 2e-5, 64, "1000"),
                                           (True, (1, 1, 12, 32, 32), 3e-2, 64, "1000"),
                                           (False, (1, 1, 8, 16, 16), 2e-5, 64, "8,4"),
                                           (False, (2, 1, 4, 16, 16), 2e-5, 64, "8"),
                                           (True, (1, 1, 8, 32, 32), 3e-2, 64, "8,4"),
-                                          (True, (1, 1, 16, 96, 96), 3e-2, 128, "1000")):
+                                          (True, (1, 1, 16, 96, 96), 3e-2, 128, "1000"))):
+            if pick and str(idx) not in pick.split(","):
+                continue
             over = dict(large_size=16, small_size=16, num_channels=ch, num_res_blocks=2, num_head_channels=64,
                         timestep_respacing="10" if ch == 64 else "3", use_fp16=bool(mode), attention_resolutions=att)
             flags = cases.sr_flags(**over)
