@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libddpm3d.so")
 
-FP32, BF16, FP16 = 0, 1, 2
+FP32, BF16, FP16, BF16_STRICT = 0, 1, 2, 3
 MEAN_PREVIOUS_X, MEAN_START_X, MEAN_EPSILON = 0, 1, 2
 VAR_LEARNED, VAR_FIXED_SMALL, VAR_FIXED_LARGE, VAR_LEARNED_RANGE = 0, 1, 2, 3
 MAX_LEVELS = 8

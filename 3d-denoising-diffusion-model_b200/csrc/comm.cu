@@ -93,6 +93,7 @@ void comm_destroy(SlabComm* c) {
   c->comm = nullptr;
   c->world = 1;
   c->rank = 0;
+  c->enabled = false;
 }
 
 int comm_halo_exchange(const SlabComm& c, void* base, int B, int Zl, size_t plane_bytes, cudaStream_t s) {

@@ -11,7 +11,8 @@ struct SlabComm {
   void* comm = nullptr;  // ncclComm_t
   int rank = 0, world = 1;
   int z_begin = 0, z_total = 0;  // this rank's slab within the global volume (set per problem)
-  bool active() const { return comm != nullptr && world > 1; }
+  bool enabled = false;          // set_slab(z_begin, z_total > 0) switches the sharded path on, set_slab(0, 0) off
+  bool active() const { return comm != nullptr && world > 1 && enabled; }
 };
 
 int comm_unique_id(void* out128);

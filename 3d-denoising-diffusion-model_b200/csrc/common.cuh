@@ -56,6 +56,19 @@ inline bool first_use_on_device(uint64_t* mask) {
   return true;
 }
 
+// SM count of the current device (persistent grids, launch sizing, per-CTA statistics slots): queried, never assumed
+inline int sm_count() {
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& c = n[dev & 63];
+  if (c == 0) {
+    cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
+    if (c <= 0) c = 1;
+  }
+  return c;
+}
+
 // ---- scalar conversions ------------------------------------------------------------------
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
@@ -85,6 +98,22 @@ template <> __device__ __forceinline__ uint32_t pack2<f16>(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+
+// ---- 16-bit elements whose format (bf16 / fp16) is a run-time property ---------------------------------
+// The CUDA-core convolution reads tensors of two 16-bit formats in one launch (bf16 conv operands next to fp16
+// block inputs / outputs, see DESIGN.md "storage formats"); both are 2 bytes, only the conversion differs.
+struct h16 { uint16_t raw; };
+__device__ __forceinline__ float h16_to_f32(uint16_t raw, int is_f16) {
+  return is_f16 ? __half2float(__ushort_as_half(raw)) : __uint_as_float((uint32_t)raw << 16);
+}
+__device__ __forceinline__ uint16_t f32_to_h16(float v, int is_f16) {
+  return is_f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ void unpack2_rt(uint32_t w, int is_f16, float& a, float& b) {
+  if (is_f16) unpack2<f16>(w, a, b);
+  else unpack2<bf16>(w, a, b);
+}
+__device__ __forceinline__ uint32_t pack2_rt(float a, float b, int is_f16) { return is_f16 ? pack2<f16>(a, b) : pack2<bf16>(a, b); }
 
 // ---- 16-byte vectors of activations ---------------------------------------------------------
 // A "vec" is 16 bytes: 4 floats or 8 bf16.  All channel counts on the path are multiples of 8

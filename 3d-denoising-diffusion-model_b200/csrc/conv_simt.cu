@@ -32,50 +32,42 @@ struct SimtParams {
   int B, Z, Ho, Wo, Hin, Win, Cout, Ktot, wld;
   int zp;  // halo planes of source 0
   int64_t M;
+  // 16-bit launches: element format (1 = fp16, 0 = bf16) of the main source + its weight columns, and of the
+  // extra sources + their weight columns + residual + output
+  int f16_main, f16_io;
 };
 
 template <typename T> struct Ld8;  // 8 consecutive elements -> 8 floats
 template <> struct Ld8<float> {
-  __device__ static void ld(const float* p, float* f) {
+  __device__ static void ld(const float* p, float* f, int) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
   }
 };
-template <> struct Ld8<bf16> {
-  __device__ static void ld(const bf16* p, float* f) {
-    Vec<bf16> v;
-    v.load(p);
-    v.unpack(f);
-  }
-};
-template <> struct Ld8<f16> {
-  __device__ static void ld(const f16* p, float* f) {
-    Vec<f16> v;
-    v.load(p);
-    v.unpack(f);
+template <> struct Ld8<h16> {
+  __device__ static void ld(const h16* p, float* f, int is_f16) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) unpack2_rt(w[i], is_f16, f[2 * i], f[2 * i + 1]);
   }
 };
 template <typename T> struct Ld4;
 template <> struct Ld4<float> {
-  __device__ static void ld(const float* p, float* f) {
+  __device__ static void ld(const float* p, float* f, int) {
     const float4 a = *reinterpret_cast<const float4*>(p);
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
   }
 };
-template <> struct Ld4<f16> {
-  __device__ static void ld(const f16* p, float* f) {
+template <> struct Ld4<h16> {
+  __device__ static void ld(const h16* p, float* f, int is_f16) {
     const uint2 r = *reinterpret_cast<const uint2*>(p);
-    unpack2<f16>(r.x, f[0], f[1]);
-    unpack2<f16>(r.y, f[2], f[3]);
+    unpack2_rt(r.x, is_f16, f[0], f[1]);
+    unpack2_rt(r.y, is_f16, f[2], f[3]);
   }
 };
-template <> struct Ld4<bf16> {
-  __device__ static void ld(const bf16* p, float* f) {
-    const uint2 r = *reinterpret_cast<const uint2*>(p);
-    f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
-    f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
-  }
-};
+__device__ __forceinline__ float ld1(const float* p, int) { return *p; }
+__device__ __forceinline__ float ld1(const h16* p, int is_f16) { return h16_to_f32(p->raw, is_f16); }
 
 // VEC: every source C % 8 == 0 and Ktot % 4 == 0 -> a 16-wide K chunk never straddles a tap/source
 template <typename T, bool VEC>
@@ -126,7 +118,7 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(SimtParams p) {
         const int zi = az + dz + zpl, hi = aho * st + dh, wi = awo * st + dw;
         if (zi >= 0 && zi < Zs && hi >= 0 && hi < Hs && wi >= 0 && wi < Ws) {
           const T* src = (const T*)p.src[s] + ((((int64_t)ab * Zs + zi) * Hs + hi) * Ws + wi) * C + ci;
-          Ld8<T>::ld(src, ra);
+          Ld8<T>::ld(src, ra, s == 0 ? p.f16_main : p.f16_io);
         }
       }
     } else {
@@ -147,7 +139,7 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(SimtParams p) {
           const int zpl = s == 0 ? p.zp : 0, Zs = p.Z + 2 * zpl;
           const int zi = az + dz + zpl, hi = aho * st + dh, wi = awo * st + dw;
           if (zi >= 0 && zi < Zs && hi >= 0 && hi < Hs && wi >= 0 && wi < Ws)
-            ra[j] = to_f32(((const T*)p.src[s])[((((int64_t)ab * Zs + zi) * Hs + hi) * Ws + wi) * C + ci]);
+            ra[j] = ld1((const T*)p.src[s] + ((((int64_t)ab * Zs + zi) * Hs + hi) * Ws + wi) * C + ci, s == 0 ? p.f16_main : p.f16_io);
         }
       }
     }
@@ -156,10 +148,10 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(SimtParams p) {
     if (VEC) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) rb[j] = 0.f;
-      if (b_ok && kb < p.Ktot) Ld4<T>::ld(wrow + kb, rb);
+      if (b_ok && kb < p.Ktot) Ld4<T>::ld(wrow + kb, rb, kb < p.kbeg[1] ? p.f16_main : p.f16_io);
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) rb[j] = (b_ok && kb + j < p.Ktot) ? to_f32(wrow[kb + j]) : 0.f;
+      for (int j = 0; j < 4; ++j) rb[j] = (b_ok && kb + j < p.Ktot) ? ld1(wrow + kb + j, kb + j < p.kbeg[1] ? p.f16_main : p.f16_io) : 0.f;
     }
   };
   auto store_tiles = [&](int buf) {
@@ -228,7 +220,7 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(SimtParams p) {
       if (p.res_mode == RES_SAME) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (nb + j < p.Cout) v[j] += to_f32(r[m * p.Cout + nb + j]);
+          if (nb + j < p.Cout) v[j] += ld1(r + m * p.Cout + nb + j, p.f16_io);
       } else if (p.res_mode == RES_POOL) {
         const int Hr = 2 * p.Ho, Wr = 2 * p.Wo;
         const int64_t r0 = (((int64_t)b * p.Z + z) * Hr + 2 * ho) * Wr + 2 * wo;
@@ -237,8 +229,8 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(SimtParams p) {
           if (nb + j < p.Cout) {
             const int c = nb + j;
             // avg_pool3d sums the 4 taps then scales; same here
-            const float sum = to_f32(r[r0 * p.Cout + c]) + to_f32(r[(r0 + 1) * p.Cout + c]) +
-                              to_f32(r[(r0 + Wr) * p.Cout + c]) + to_f32(r[(r0 + Wr + 1) * p.Cout + c]);
+            const float sum = ld1(r + r0 * p.Cout + c, p.f16_io) + ld1(r + (r0 + 1) * p.Cout + c, p.f16_io) +
+                              ld1(r + (r0 + Wr) * p.Cout + c, p.f16_io) + ld1(r + (r0 + Wr + 1) * p.Cout + c, p.f16_io);
             v[j] += 0.25f * sum;
           }
       } else {  // RES_UP
@@ -246,7 +238,7 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(SimtParams p) {
         const int64_t r0 = (((int64_t)b * p.Z + z) * Hr + ho / 2) * Wr + wo / 2;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (nb + j < p.Cout) v[j] += to_f32(r[r0 * p.Cout + nb + j]);
+          if (nb + j < p.Cout) v[j] += ld1(r + r0 * p.Cout + nb + j, p.f16_io);
       }
     }
     if (p.planar) {
@@ -263,8 +255,8 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(SimtParams p) {
           *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
         } else {
           uint2 pk;
-          pk.x = pack2<T>(v[0], v[1]);
-          pk.y = pack2<T>(v[2], v[3]);
+          pk.x = pack2_rt(v[0], v[1], p.f16_io);
+          pk.y = pack2_rt(v[2], v[3], p.f16_io);
           *reinterpret_cast<uint2*>(o) = pk;
         }
       }
@@ -272,7 +264,10 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(SimtParams p) {
       T* o = (T*)p.out + m * p.Cout;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (nb + j < p.Cout) o[nb + j] = from_f32<T>(v[j]);
+        if (nb + j < p.Cout) {
+          if constexpr (sizeof(T) == 4) o[nb + j] = v[j];
+          else o[nb + j].raw = f32_to_h16(v[j], p.f16_io);
+        }
     }
   }
 }
@@ -315,12 +310,11 @@ int conv_simt(const ConvArgs& a, cudaStream_t s) {
   DD_CHECK(!(p.res_mode == RES_UP) || (a.Ho % 2 == 0 && a.Wo % 2 == 0), DDPM3D_ERR_ARG, "conv: RES_UP needs even output H, W");
   DD_CHECK(!a.out_planar_f32 || a.dt == DDPM3D_FP32, DDPM3D_ERR_ARG, "conv: planar output is fp32 only");
   dim3 grid((unsigned)ceil_div(p.M, BM), (unsigned)ceil_div(a.Cout, BN));
-  if (a.dt == DDPM3D_BF16) {
-    if (vec) conv_simt_kernel<bf16, true><<<grid, THREADS, 0, s>>>(p);
-    else conv_simt_kernel<bf16, false><<<grid, THREADS, 0, s>>>(p);
-  } else if (a.dt == DDPM3D_FP16) {
-    if (vec) conv_simt_kernel<f16, true><<<grid, THREADS, 0, s>>>(p);
-    else conv_simt_kernel<f16, false><<<grid, THREADS, 0, s>>>(p);
+  if (is_half_dt(a.dt)) {
+    p.f16_main = a.dt == DDPM3D_FP16;
+    p.f16_io = a.io_dt() == DDPM3D_FP16;
+    if (vec) conv_simt_kernel<h16, true><<<grid, THREADS, 0, s>>>(p);
+    else conv_simt_kernel<h16, false><<<grid, THREADS, 0, s>>>(p);
   } else {
     if (vec) conv_simt_kernel<float, true><<<grid, THREADS, 0, s>>>(p);
     else conv_simt_kernel<float, false><<<grid, THREADS, 0, s>>>(p);

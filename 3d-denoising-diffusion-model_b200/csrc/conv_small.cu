@@ -460,10 +460,7 @@ int stem_tc_launch(const ConvArgs& a, cudaStream_t s) {
   uint32_t cols = 32;
   while ((int)cols < a.Cout) cols *= 2;
   const int per_sm = std::max(1, std::min(6, 512 / (int)cols));   // TMEM columns bound the co-resident CTAs
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (sms <= 0) sms = 148;
+  const int sms = sm_count();
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sms * per_sm);
   const size_t smem = 1024 + 128 * 128 + (size_t)a.Cout * 128;
   static uint64_t configured = 0;

@@ -62,7 +62,8 @@ struct TcParams {
   int sk;
   int max_slots;
   float* partial;
-  float* chsum;      // [B][CHSUM_SLOTS][Cout][2] per-CTA channel sums of the output, or NULL
+  float* chsum;      // [B][cs_slots][Cout][2] per-CTA channel sums of the output, or NULL
+  int cs_slots;      // = chsum_slots() (one slot per SM)
   uint32_t cs_off;   // byte offset of the channel-sum accumulators in dynamic smem
 };
 
@@ -126,7 +127,9 @@ struct WorkIter {
 // first CTA whose k-range touches k-step x (ranges are [c*T/G, (c+1)*T/G))
 __host__ __device__ inline int sk_owner(int64_t x, int64_t T, int G) { return (int)(((x + 1) * G - 1) / T); }
 
-template <typename T, int MT, int BN, int NSTAGE, int CL>
+// T: format of the main source and its weight columns; TS: format of the extra (1x1x1) sources and their weight
+// columns, of the residual and of the output (both 16 bit; the MMA instruction descriptor is chosen per k-step)
+template <typename T, typename TS, int MT, int BN, int NSTAGE, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
@@ -222,7 +225,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, sizeof(T) == 2 && !std::is_same<T, f16>::value);
+      constexpr uint32_t idesc_main = make_idesc(BM, BN, !std::is_same<T, f16>::value);
+      constexpr uint32_t idesc_extra = make_idesc(BM, BN, !std::is_same<TS, f16>::value);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -238,6 +242,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
           const uint64_t bdesc = make_sw128_desc(a_addr + MT * A_BYTES);
+          const uint32_t idesc = kk < p.n_main_steps ? idesc_main : idesc_extra;
 #pragma unroll
           for (int j = 0; j < MT; ++j) {
             const uint64_t adesc = make_sw128_desc(a_addr + j * A_BYTES);
@@ -300,7 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (res1) {
           int64_t rrow = vox;
           if (p.res_mode == RES_UP) rrow = (((int64_t)b * p.Z + z) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2;
-          const uint4* rp = reinterpret_cast<const uint4*>((const T*)p.res + rrow * p.Cout + n0 + c);
+          const uint4* rp = reinterpret_cast<const uint4*>((const TS*)p.res + rrow * p.Cout + n0 + c);
 #pragma unroll
           for (int j = 0; j < 4; ++j) rres[j] = rp[j];
         }
@@ -329,7 +334,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
           if (res1) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) add8r<T>(v + 8 * j, rres[j]);
+            for (int j = 0; j < 4; ++j) add8r<TS>(v + 8 * j, rres[j]);
           } else if (p.res_mode == RES_POOL) {  // residual = AvgPool(1,2,2) of a (2Ho, 2Wo) tensor
             const int Hr = 2 * p.Ho, Wr = 2 * p.Wo;
             const int64_t r0 = (((int64_t)b * p.Z + z) * Hr + 2 * h) * Wr + 2 * w;
@@ -339,19 +344,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int64_t offs[4] = {r0, r0 + 1, r0 + Wr, r0 + Wr + 1};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const T* rp = (const T*)p.res + offs[q] * p.Cout + n0 + c;
+              const TS* rp = (const TS*)p.res + offs[q] * p.Cout + n0 + c;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) add8<T>(s + 8 * j, rp + 8 * j, 1.0f);
+              for (int j = 0; j < 4; ++j) add8<TS>(s + 8 * j, rp + 8 * j, 1.0f);
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += 0.25f * s[j];
           }
-          T* op = (T*)p.out + vox * p.Cout + n0 + c;
+          TS* op = (TS*)p.out + vox * p.Cout + n0 + c;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint32_t w4[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) w4[q] = pack2<T>(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
+            for (int q = 0; q < 4; ++q) w4[q] = pack2<TS>(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
             *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
         } else {
@@ -390,7 +395,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       for (int i = et; i < n; i += 128) {
         const float t = ((cs_acc[i] + cs_acc[n + i]) + cs_acc[2 * n + i]) + cs_acc[3 * n + i];
         const int bb = i / (p.Cout * 2), rem = i - bb * p.Cout * 2;
-        p.chsum[((size_t)bb * CHSUM_SLOTS + blockIdx.x) * p.Cout * 2 + rem] = t;
+        p.chsum[((size_t)bb * p.cs_slots + blockIdx.x) * p.Cout * 2 + rem] = t;
       }
     }
   }
@@ -430,10 +435,11 @@ struct StripParams {
   int res_mode;
   void* out;
   float* chsum;      // only without a residual (the sums are taken channel-major, before the transpose)
+  int cs_slots;
   uint32_t cs_off;
 };
 
-template <typename T, int NB, int NW>
+template <typename T, typename TS, int NB, int NW>
 __global__ void __launch_bounds__(STRIP_THREADS, 1)
 conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW, const StripParams p) {
@@ -548,7 +554,8 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
   } else if (warp == 1) {
     // ===================================== MMA issuer =========================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, p.NV, sizeof(T) == 2 && !std::is_same<T, f16>::value);
+      const uint32_t idesc_main = make_idesc(128, p.NV, !std::is_same<T, f16>::value);
+      const uint32_t idesc_extra = make_idesc(128, p.NV, !std::is_same<TS, f16>::value);
       int sb = 0, ws = 0, acc = 0;
       uint32_t sph = 0, wph = 0, aph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -564,6 +571,7 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
           tc_fence_after();
           const uint32_t strip = smem_base + sb * p.strip_stride;
           const int ntaps = m < p.n_macro_main ? 9 : 1;
+          const uint32_t idesc = m < p.n_macro_main ? idesc_main : idesc_extra;
           for (int t = 0; t < ntaps; ++t) {
             const int dh = ntaps == 9 ? t / 3 - 1 : 0, dw = ntaps == 9 ? t % 3 - 1 : 0;
             mbar_wait(wfull(ws), wph);
@@ -646,9 +654,9 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
         if (valid) {
           const int cb = n0 + sub * 32;
           if (p.res_mode == RES_SAME) {
-            const T* rp = (const T*)p.res + vox * p.Cout + cb;
+            const TS* rp = (const TS*)p.res + vox * p.Cout + cb;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) add8<T>(v + 8 * i, rp + 8 * i, 1.0f);
+            for (int i = 0; i < 4; ++i) add8<TS>(v + 8 * i, rp + 8 * i, 1.0f);
           } else if (p.res_mode == RES_POOL) {  // residual = AvgPool(1,2,2) of a (2H, 2W) tensor
             const int Wr = 2 * p.W;
             const int64_t r0 = (((int64_t)b * p.Z + z) * (2 * p.H) + 2 * hq) * Wr + 2 * w;
@@ -658,24 +666,24 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
             const int64_t offs[4] = {r0, r0 + 1, r0 + Wr, r0 + Wr + 1};
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) {
-              const T* rp = (const T*)p.res + offs[qd] * p.Cout + cb;
+              const TS* rp = (const TS*)p.res + offs[qd] * p.Cout + cb;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) add8<T>(sacc + 8 * i, rp + 8 * i, 1.0f);
+              for (int i = 0; i < 4; ++i) add8<TS>(sacc + 8 * i, rp + 8 * i, 1.0f);
             }
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += 0.25f * sacc[i];
           } else if (p.res_mode == RES_UP) {  // residual = nearest x2 of a (H/2, W/2) tensor
             const int64_t r0 = (((int64_t)b * p.Z + z) * (p.H / 2) + hq / 2) * (p.W / 2) + w / 2;
-            const T* rp = (const T*)p.res + r0 * p.Cout + cb;
+            const TS* rp = (const TS*)p.res + r0 * p.Cout + cb;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) add8<T>(v + 8 * i, rp + 8 * i, 1.0f);
+            for (int i = 0; i < 4; ++i) add8<TS>(v + 8 * i, rp + 8 * i, 1.0f);
           }
-          T* op = (T*)p.out + vox * p.Cout + cb;
+          TS* op = (TS*)p.out + vox * p.Cout + cb;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint32_t w4[4];
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) w4[qq] = pack2<T>(v[8 * i + 2 * qq], v[8 * i + 2 * qq + 1]);
+            for (int qq = 0; qq < 4; ++qq) w4[qq] = pack2<TS>(v[8 * i + 2 * qq], v[8 * i + 2 * qq + 1]);
             *reinterpret_cast<uint4*>(op + 8 * i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
         }
@@ -695,7 +703,7 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
       const int n = p.B * p.Cout * 2;
       for (int i = (warp - 2) * 32 + lane; i < n; i += 128) {
         const int bb = i / (p.Cout * 2), rem = i - bb * p.Cout * 2;
-        p.chsum[((size_t)bb * CHSUM_SLOTS + blockIdx.x) * p.Cout * 2 + rem] = cs_acc[i];
+        p.chsum[((size_t)bb * p.cs_slots + blockIdx.x) * p.Cout * 2 + rem] = cs_acc[i];
       }
     }
   }
@@ -788,25 +796,14 @@ void choose_brick(int Z, int H, int W, int* bw_, int* bh_, int* bz_) {
   *bw_ = bbw; *bh_ = bbh; *bz_ = bbz;
 }
 
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
-template <typename T, int MT, int BN, int NSTAGE, int CL>
+template <typename T, typename TS, int MT, int BN, int NSTAGE, int CL>
 int launch_cl(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s) {
   constexpr size_t stage_smem = (size_t)NSTAGE * (MT * A_BYTES + BN * BK * 2) + 1024;
   constexpr size_t smem_max = stage_smem + CS_SMEM_MAX;
   static_assert(smem_max <= 227 * 1024, "shared memory budget");
   static uint64_t configured = 0;
   if (first_use_on_device(&configured)) {
-    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, MT, BN, NSTAGE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<T, TS, MT, BN, NSTAGE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   }
   int grid;
   if (p.sk) {
@@ -821,8 +818,9 @@ int launch_cl(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& 
   if (q.chsum) {
     q.cs_off = (uint32_t)stage_smem;
     smem += CS_TR_BYTES + (size_t)4 * q.B * q.Cout * 2 * sizeof(float);
-    if (grid < CHSUM_SLOTS)  // slots of CTAs that do not exist must read as zero
-      DD_CUDA(cudaMemsetAsync(q.chsum, 0, (size_t)q.B * CHSUM_SLOTS * q.Cout * 2 * sizeof(float), s));
+    q.cs_slots = chsum_slots();
+    if (grid < q.cs_slots)  // slots of CTAs that do not exist must read as zero
+      DD_CUDA(cudaMemsetAsync(q.chsum, 0, (size_t)q.B * q.cs_slots * q.Cout * 2 * sizeof(float), s));
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -836,19 +834,26 @@ int launch_cl(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<T, MT, BN, NSTAGE, CL>, maps[0], maps[1], maps[2], mapW, q));
+  DD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<T, TS, MT, BN, NSTAGE, CL>, maps[0], maps[1], maps[2], mapW, q));
   if (p.sk) {
-    sk_fixup_kernel<T, MT, BN><<<dim3(p.num_tiles, 8), 256, 0, s>>>(p, grid);
+    sk_fixup_kernel<TS, MT, BN><<<dim3(p.num_tiles, 8), 256, 0, s>>>(p, grid);
     DD_CUDA(cudaGetLastError());
   }
   return DDPM3D_OK;
 }
 
 // stream-K ranges differ per CTA, so those launches cannot share weight tiles (CL = 1)
-template <typename T, int MT, int BN, int NSTAGE>
+template <typename T, typename TS, int MT, int BN, int NSTAGE>
 int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s, int cl) {
-  if (cl == 2) return launch_cl<T, MT, BN, NSTAGE, 2>(maps, mapW, p, s);
-  return launch_cl<T, MT, BN, NSTAGE, 1>(maps, mapW, p, s);
+  if (cl == 2) return launch_cl<T, TS, MT, BN, NSTAGE, 2>(maps, mapW, p, s);
+  return launch_cl<T, TS, MT, BN, NSTAGE, 1>(maps, mapW, p, s);
+}
+template <typename T, typename TS>
+int launch_plan(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s, int cl, int MT, int BN) {
+  if (MT == 2) return launch<T, TS, 2, 128, 4>(maps, mapW, p, s, cl);
+  if (BN == 256) return launch<T, TS, 1, 256, 4>(maps, mapW, p, s, cl);
+  if (BN == 128) return launch<T, TS, 1, 128, 6>(maps, mapW, p, s, cl);
+  return launch<T, TS, 1, 64, 8>(maps, mapW, p, s, cl);
 }
 
 // ---- probe (test-only): does a SWIZZLE_128B K-major operand descriptor work when its start address is an
@@ -1028,16 +1033,16 @@ bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
   return false;
 }
 
-template <typename T, int NW>
+template <typename T, typename TS, int NW>
 int launch_strip(const CUtensorMap* maps, const CUtensorMap& mapW, const StripParams& p, const StripPlan& plan, cudaStream_t s) {
   static uint64_t configured = 0;
   if (first_use_on_device(&configured)) {
-    DD_CUDA(cudaFuncSetAttribute(conv_tc_strip_kernel<T, 2, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_strip_kernel<T, TS, 2, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
   }
   const int grid = std::min(p.num_tiles, sm_count());
-  if (p.chsum && grid < CHSUM_SLOTS)
-    DD_CUDA(cudaMemsetAsync(p.chsum, 0, (size_t)p.B * CHSUM_SLOTS * p.Cout * 2 * sizeof(float), s));
-  conv_tc_strip_kernel<T, 2, NW><<<grid, STRIP_THREADS, plan.smem, s>>>(maps[0], maps[1], maps[2], mapW, p);
+  if (p.chsum && grid < p.cs_slots)
+    DD_CUDA(cudaMemsetAsync(p.chsum, 0, (size_t)p.B * p.cs_slots * p.Cout * 2 * sizeof(float), s));
+  conv_tc_strip_kernel<T, TS, 2, NW><<<grid, STRIP_THREADS, plan.smem, s>>>(maps[0], maps[1], maps[2], mapW, p);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }
@@ -1067,19 +1072,23 @@ int conv_tc_strip(ConvArgs& a, const StripPlan& plan, bool chsum, cudaStream_t s
   p.out = a.out;
   if (a.residual) chsum = false;
   p.chsum = chsum ? a.chsum_out : nullptr;
+  p.cs_slots = chsum_slots();
   p.cs_off = (uint32_t)((size_t)2 * plan.strip_stride + (size_t)plan.NW * 128 * BK * 2 + 1024);
   a.chsum_written = chsum ? 1 : 0;
-  const CUtensorMapDataType tdt = a.dt == DDPM3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapDataType tdt = tmap_dtype(a.dt), tdt_io = tmap_dtype(a.io_dt());
   CUtensorMap maps[3];
   DD_TRY(make_act_map(&maps[0], tdt, a.main.ptr, a.B, a.Z + 2 * a.in_zpad, a.Ho, a.Wo, a.main.C, plan.Wp, plan.nh, 1));
   maps[1] = maps[0];
   maps[2] = maps[0];
   for (int e = 0; e < a.n_extra; ++e)
-    DD_TRY(make_act_map(&maps[1 + e], tdt, a.extra[e].ptr, a.B, a.Z, a.Ho, a.Wo, a.extra[e].C, plan.Wp, plan.nh, 1));
+    DD_TRY(make_act_map(&maps[1 + e], tdt_io, a.extra[e].ptr, a.B, a.Z, a.Ho, a.Wo, a.extra[e].C, plan.Wp, plan.nh, 1));
   CUtensorMap mapW;
   DD_TRY(make_w_map(&mapW, tdt, a.w, a.Cout, a.w_ld ? a.w_ld : Ktot, 128));
-  if (a.dt == DDPM3D_BF16) return plan.NW == 4 ? launch_strip<bf16, 4>(maps, mapW, p, plan, s) : launch_strip<bf16, 3>(maps, mapW, p, plan, s);
-  return plan.NW == 4 ? launch_strip<f16, 4>(maps, mapW, p, plan, s) : launch_strip<f16, 3>(maps, mapW, p, plan, s);
+  if (a.dt == DDPM3D_BF16 && a.io_dt() == DDPM3D_BF16)
+    return plan.NW == 4 ? launch_strip<bf16, bf16, 4>(maps, mapW, p, plan, s) : launch_strip<bf16, bf16, 3>(maps, mapW, p, plan, s);
+  if (a.dt == DDPM3D_BF16)
+    return plan.NW == 4 ? launch_strip<bf16, f16, 4>(maps, mapW, p, plan, s) : launch_strip<bf16, f16, 3>(maps, mapW, p, plan, s);
+  return plan.NW == 4 ? launch_strip<f16, f16, 4>(maps, mapW, p, plan, s) : launch_strip<f16, f16, 3>(maps, mapW, p, plan, s);
 }
 
 }  // namespace
@@ -1101,7 +1110,8 @@ size_t conv_tc_scratch_bytes(const ConvArgs& a0) {
 }
 
 bool conv_tc_eligible(const ConvArgs& a) {
-  if (!is_half_dt(a.dt) || a.out_planar_f32 || a.stride_hw != 1) return false;
+  if (!is_half_dt(a.dt) || !is_half_dt(a.io_dt()) || a.out_planar_f32 || a.stride_hw != 1) return false;
+  if (a.dt == DDPM3D_FP16 && a.io_dt() != DDPM3D_FP16) return false;  // built: bf16/bf16, bf16/fp16, fp16/fp16
   if (a.taps != 27 && a.taps != 1) return false;
   if (a.main.C % BK != 0 || a.Cout % 64 != 0) return false;
   for (int e = 0; e < a.n_extra; ++e)
@@ -1117,15 +1127,14 @@ bool conv_tc_eligible(const ConvArgs& a) {
 int conv_tc(ConvArgs& a, cudaStream_t s) {
   DD_CHECK(conv_tc_eligible(a), DDPM3D_ERR_ARG, "conv_tc: shape not eligible");
   {
-    const bool want_cs = a.chsum_out && CS_TR_BYTES + (size_t)4 * a.B * a.Cout * 2 * sizeof(float) <= (size_t)CS_SMEM_MAX &&
-                         sm_count() <= CHSUM_SLOTS;
+    const bool want_cs = a.chsum_out && CS_TR_BYTES + (size_t)4 * a.B * a.Cout * 2 * sizeof(float) <= (size_t)CS_SMEM_MAX;
     StripPlan sp;
     if (strip_plan(a, want_cs, &sp)) return conv_tc_strip(a, sp, want_cs, s);
     if (want_cs && strip_plan(a, false, &sp)) return conv_tc_strip(a, sp, false, s);
   }
   TcParams p{};
   a.chsum_written = 0;
-  if (a.chsum_out && CS_TR_BYTES + (size_t)4 * a.B * a.Cout * 2 * sizeof(float) <= (size_t)CS_SMEM_MAX && sm_count() <= CHSUM_SLOTS) {
+  if (a.chsum_out && CS_TR_BYTES + (size_t)4 * a.B * a.Cout * 2 * sizeof(float) <= (size_t)CS_SMEM_MAX) {
     p.chsum = a.chsum_out;
     a.chsum_written = 1;
   }
@@ -1165,26 +1174,19 @@ int conv_tc(ConvArgs& a, cudaStream_t s) {
   p.res_mode = a.residual ? a.res_mode : RES_NONE;
   p.out = a.out;
 
-  const CUtensorMapDataType tdt = a.dt == DDPM3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapDataType tdt = tmap_dtype(a.dt), tdt_io = tmap_dtype(a.io_dt());
   CUtensorMap maps[3];
   DD_TRY(make_act_map(&maps[0], tdt, a.main.ptr, a.B, a.Z + 2 * a.in_zpad, a.Ho, a.Wo, a.main.C, p.bw, p.bh, p.bz));
   maps[1] = maps[0];
   maps[2] = maps[0];
   for (int e = 0; e < a.n_extra; ++e)
-    DD_TRY(make_act_map(&maps[1 + e], tdt, a.extra[e].ptr, a.B, a.Z, a.Ho, a.Wo, a.extra[e].C, p.bw, p.bh, p.bz));
+    DD_TRY(make_act_map(&maps[1 + e], tdt_io, a.extra[e].ptr, a.B, a.Z, a.Ho, a.Wo, a.extra[e].C, p.bw, p.bh, p.bz));
   CUtensorMap mapW;
   const int cl = (!p.sk && a.cluster_allowed && p.num_tiles / p.nNt >= 2 * sm_count()) ? 2 : 1;
   DD_TRY(make_w_map(&mapW, tdt, a.w, a.Cout, a.w_ld ? a.w_ld : Ktot, BN / cl));
-  if (a.dt == DDPM3D_BF16) {
-    if (MT == 2) return launch<bf16, 2, 128, 4>(maps, mapW, p, s, cl);
-    if (BN == 256) return launch<bf16, 1, 256, 4>(maps, mapW, p, s, cl);
-    if (BN == 128) return launch<bf16, 1, 128, 6>(maps, mapW, p, s, cl);
-    return launch<bf16, 1, 64, 8>(maps, mapW, p, s, cl);
-  }
-  if (MT == 2) return launch<f16, 2, 128, 4>(maps, mapW, p, s, cl);
-  if (BN == 256) return launch<f16, 1, 256, 4>(maps, mapW, p, s, cl);
-  if (BN == 128) return launch<f16, 1, 128, 6>(maps, mapW, p, s, cl);
-  return launch<f16, 1, 64, 8>(maps, mapW, p, s, cl);
+  if (a.dt == DDPM3D_BF16 && a.io_dt() == DDPM3D_BF16) return launch_plan<bf16, bf16>(maps, mapW, p, s, cl, MT, BN);
+  if (a.dt == DDPM3D_BF16) return launch_plan<bf16, f16>(maps, mapW, p, s, cl, MT, BN);
+  return launch_plan<f16, f16>(maps, mapW, p, s, cl, MT, BN);
 }
 
 }  // namespace ddpm3d

@@ -23,7 +23,7 @@ __global__ void pack_input_kernel(const float* __restrict__ x, const float* __re
 int pack_input(int dt, const float* x, const float* low, void* out, int B, int Z, int64_t plane, int out_zpad, cudaStream_t s) {
   const int64_t n = (int64_t)B * Z * plane, per_b = (int64_t)Z * plane, pad_vox = (int64_t)out_zpad * plane;
   const int threads = 256;
-  const int blocks = (int)std::min<int64_t>(ceil_div(n, threads), 148 * 16);
+  const int blocks = (int)std::min<int64_t>(ceil_div(n, threads), sm_count() * 16);
   if (dt == DDPM3D_BF16)
     pack_input_kernel<bf16><<<blocks, threads, 0, s>>>(x, low, (bf16*)out, n, per_b, pad_vox);
   else if (dt == DDPM3D_FP16)
@@ -56,7 +56,7 @@ int pack_input_planar(int dt, const float* x, const float* low, int Cx, void* ou
                       cudaStream_t s) {
   const int64_t n = (int64_t)B * Z * plane, per_b = (int64_t)Z * plane, pad_vox = (int64_t)out_zpad * plane;
   const int threads = 256;
-  const int blocks = (int)std::min<int64_t>(ceil_div(n, threads), 148 * 16);
+  const int blocks = (int)std::min<int64_t>(ceil_div(n, threads), sm_count() * 16);
   if (dt == DDPM3D_BF16) pack_planar_kernel<bf16><<<blocks, threads, 0, s>>>(x, low, Cx, (bf16*)out, n, per_b, pad_vox);
   else if (dt == DDPM3D_FP16) pack_planar_kernel<f16><<<blocks, threads, 0, s>>>(x, low, Cx, (f16*)out, n, per_b, pad_vox);
   else pack_planar_kernel<float><<<blocks, threads, 0, s>>>(x, low, Cx, (float*)out, n, per_b, pad_vox);
@@ -463,7 +463,7 @@ static int gn_apply_launch(const GnArgs& a, cudaStream_t s) {
   const int Ho = a.resample == RS_POOL ? a.H / 2 : a.H, Wo = a.resample == RS_POOL ? a.W / 2 : a.W;
   const int rows_it = a.Z * Ho * Wo;
   // ~8 CTAs per SM over the whole launch, at least 4 passes of the row lanes per CTA
-  int blocks = (int)std::min<int64_t>(ceil_div(rows_it, 4 * rpi), std::max(1, 148 * 8 / a.B));
+  int blocks = (int)std::min<int64_t>(ceil_div(rows_it, 4 * rpi), std::max(1, sm_count() * 8 / a.B));
   const int rows_per_block = (int)ceil_div(rows_it, blocks);
   blocks = (int)ceil_div(rows_it, rows_per_block);
   dim3 grid(blocks, a.B);
@@ -519,8 +519,15 @@ static int gn_stats_any(const GnArgs& a, cudaStream_t s) {
 }
 
 static int gn_apply_any(const GnArgs& a, cudaStream_t s) {
-  if (a.dt == DDPM3D_BF16) return a.out_f32 ? gn_apply_launch<bf16, float>(a, s) : gn_apply_launch<bf16, bf16>(a, s);
-  if (a.dt == DDPM3D_FP16) return a.out_f32 ? gn_apply_launch<f16, float>(a, s) : gn_apply_launch<f16, f16>(a, s);
+  const int dto = a.dt_out < 0 ? a.dt : a.dt_out;  // 16-bit output format (block inputs are fp16, conv operands bf16)
+  if (a.dt == DDPM3D_BF16) {
+    if (a.out_f32) return gn_apply_launch<bf16, float>(a, s);
+    return dto == DDPM3D_FP16 ? gn_apply_launch<bf16, f16>(a, s) : gn_apply_launch<bf16, bf16>(a, s);
+  }
+  if (a.dt == DDPM3D_FP16) {
+    if (a.out_f32) return gn_apply_launch<f16, float>(a, s);
+    return dto == DDPM3D_BF16 ? gn_apply_launch<f16, bf16>(a, s) : gn_apply_launch<f16, f16>(a, s);
+  }
   return gn_apply_launch<float, float>(a, s);
 }
 
@@ -542,7 +549,7 @@ int gn_forward_chsum(const GnArgs& a, cudaStream_t s) {
   const int Ctot = a.C[0] + a.C[1];
   DD_CHECK(a.chsum[0] && (a.C[1] == 0 || a.chsum[1]) && !a.pre_add, DDPM3D_ERR_STATE, "groupnorm: channel sums missing");
   const double inv_count = 1.0 / ((double)a.Z * a.H * a.W * (Ctot / 32));
-  gn_finalize_chsum_kernel<<<dim3(32, a.B), 128, 0, s>>>(a.chsum[0], a.chsum[1], a.C[0], a.C[1], CHSUM_SLOTS, inv_count, a.gamma,
+  gn_finalize_chsum_kernel<<<dim3(32, a.B), 128, 0, s>>>(a.chsum[0], a.chsum[1], a.C[0], a.C[1], chsum_slots(), inv_count, a.gamma,
                                                          a.beta, a.film, a.film_stride, a.ab);
   DD_CUDA(cudaGetLastError());
   return gn_apply_any(a, s);
@@ -578,7 +585,7 @@ __global__ void __launch_bounds__(128) gn_chsum_local_kernel(const float* __rest
 int gn_chsum_local(const GnArgs& a, double* sums, cudaStream_t s) {
   DD_TRY(gn_check(a));
   DD_CHECK(a.chsum[0] && (a.C[1] == 0 || a.chsum[1]), DDPM3D_ERR_STATE, "groupnorm: channel sums missing");
-  gn_chsum_local_kernel<<<dim3(32, a.B), 128, 0, s>>>(a.chsum[0], a.chsum[1], a.C[0], a.C[1], CHSUM_SLOTS, sums);
+  gn_chsum_local_kernel<<<dim3(32, a.B), 128, 0, s>>>(a.chsum[0], a.chsum[1], a.C[0], a.C[1], chsum_slots(), sums);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }
@@ -659,7 +666,7 @@ int resample_hw(int dt, const void* in, void* out, int B, int Z, int H, int W, i
   const int Ho = mode == RS_POOL ? H / 2 : H, Wo = mode == RS_POOL ? W / 2 : W;
   const int64_t total = (int64_t)B * Z * Ho * Wo * (C / N);
   const int threads = 256;
-  const int blocks = (int)std::min<int64_t>(ceil_div(total, threads), 148 * 32);
+  const int blocks = (int)std::min<int64_t>(ceil_div(total, threads), sm_count() * 32);
   if (dt == DDPM3D_BF16) {
     if (mode == RS_POOL) resample_kernel<bf16, RS_POOL><<<blocks, threads, 0, s>>>((const bf16*)in, (bf16*)out, B, Z, H, W, C);
     else resample_kernel<bf16, RS_UP><<<blocks, threads, 0, s>>>((const bf16*)in, (bf16*)out, B, Z, H, W, C);
@@ -809,7 +816,10 @@ __global__ void p_sample_update_kernel(UpdateArgs a) {
     const int64_t i = i4 * 4;
     const int b = (int)(i / per_b);
     const int64_t off = i - (int64_t)b * per_b;  // c*n + j
-    const int ti = a.t_index ? a.t_index[b] : cur;
+    int ti = a.t_index ? a.t_index[b] : cur;
+    // the reference's table gather raises IndexError for t outside [0, T) (gaussian_diffusion.py:897-910); a kernel
+    // cannot raise, so the index is clamped here (like step_from_tensor_kernel) and range-checked by the host mirror
+    ti = ti < 0 ? 0 : (ti >= a.T ? a.T - 1 : ti);
     const ddpm3d_step_scalars sc = a.table[ti];
     const int64_t mo_base = (int64_t)b * (LEARNED ? 2 : 1) * per_b + off;
     const float4 x4 = *reinterpret_cast<const float4*>(a.x + i);
@@ -893,7 +903,7 @@ int p_sample_update_k(const UpdateArgs& a, cudaStream_t s) {
   DD_CHECK(a.table != nullptr, DDPM3D_ERR_STATE, "p_sample_update: schedule not set");
   const int64_t total4 = (int64_t)a.B * a.C * a.n / 4;
   const int threads = 256;
-  const int blocks = (int)std::min<int64_t>(ceil_div(total4, threads), 148 * 16);
+  const int blocks = (int)std::min<int64_t>(ceil_div(total4, threads), sm_count() * 16);
   switch (a.mean_type) {
     case DDPM3D_MEAN_PREVIOUS_X: DD_TRY(update_dispatch_var<DDPM3D_MEAN_PREVIOUS_X>(a, blocks, threads, s)); break;
     case DDPM3D_MEAN_START_X: DD_TRY(update_dispatch_var<DDPM3D_MEAN_START_X>(a, blocks, threads, s)); break;
@@ -906,8 +916,14 @@ int p_sample_update_k(const UpdateArgs& a, cudaStream_t s) {
 
 // step bookkeeping for the device-resident loop: counter = {current index i, executed steps k}
 __global__ void step_advance_kernel(int32_t* counter, float* t_model, const ddpm3d_step_scalars* table, int B) {
-  const int next = counter[0] - 1;
-  if (threadIdx.x == 0) { counter[0] = next; counter[1] = counter[1] + 1; }
+  // one warp: lane 0 reads the counter, the others get it by shuffle (no lane reads after lane 0's write)
+  int next = 0;
+  if (threadIdx.x == 0) {
+    next = counter[0] - 1;
+    counter[0] = next;
+    counter[1] = counter[1] + 1;
+  }
+  next = __shfl_sync(0xffffffffu, next, 0);
   if (next >= 0)
     for (int b = threadIdx.x; b < B; b += blockDim.x) t_model[b] = table[next].model_t;
 }

@@ -146,7 +146,9 @@ struct ddpm3d_ctx {
   int out_norm_ch = 0, out_conv_in = 0, ted = 0;
   bool finalized = false;
   int device = -1;
-  int dt = DDPM3D_FP32;
+  int dt = DDPM3D_FP32;   // conv operands: GroupNorm outputs and the 3x3x3 / qkv / proj weights
+  int dts = DDPM3D_FP32;  // block inputs / outputs and the tensor between the two convs of a ResBlock (read only by GroupNorm,
+                          // the skip path and residual adds): fp16 in the default bf16 mode -- same bytes, 3 more mantissa bits
   size_t esz = 4;
   std::vector<void*> dev_allocs;
   // embedding path
@@ -376,7 +378,9 @@ int upload_f32(ddpm3d_ctx* ctx, const std::string& key, float** out) {
 
 // [Cout][Cin][taps] (reference) -> [Cout][taps*Cin (+ Cskip)], element type dt; bias (+ skip bias) fp32
 int pack_conv(ddpm3d_ctx* ctx, int dt, const std::string& wkey, const std::string& bkey, int taps,
-              const std::string* skip_w, const std::string* skip_b, DevConv* out, bool append_identity = false) {
+              const std::string* skip_w, const std::string* skip_b, DevConv* out, bool append_identity = false,
+              int dt_extra = -1) {
+  if (dt_extra < 0) dt_extra = dt;
   const Param* w = find(ctx, wkey);
   const Param* b = find(ctx, bkey);
   DD_CHECK(w && w->loaded, DDPM3D_ERR_MISSING, "missing state_dict tensor: " + wkey);
@@ -421,9 +425,14 @@ int pack_conv(ddpm3d_ctx* ctx, int dt, const std::string& wkey, const std::strin
   out->Ktot = (int)Ktot;
   DD_TRY(upload(ctx, bias.data(), bias.size() * sizeof(float), (void**)&out->bias));
   if (is_half_dt(dt)) {
+    // the columns of the folded skip (1x1x1 over the block input) carry the block input's 16-bit format
     std::vector<uint16_t> h(packed.size());
-    if (dt == DDPM3D_BF16) for (size_t i = 0; i < packed.size(); ++i) h[i] = f32_to_bf16_rn(packed[i]);
-    else for (size_t i = 0; i < packed.size(); ++i) h[i] = f32_to_f16_rn(packed[i]);
+    const int64_t kmain = taps * Cin;
+    for (int64_t co = 0; co < Cout; ++co)
+      for (int64_t k = 0; k < Ktot; ++k) {
+        const size_t i = (size_t)(co * Ktot + k);
+        h[i] = (k < kmain ? dt : dt_extra) == DDPM3D_BF16 ? f32_to_bf16_rn(packed[i]) : f32_to_f16_rn(packed[i]);
+      }
     DD_TRY(upload(ctx, h.data(), h.size() * 2, &out->w));
   } else {
     DD_TRY(upload(ctx, packed.data(), packed.size() * 4, &out->w));
@@ -433,9 +442,10 @@ int pack_conv(ddpm3d_ctx* ctx, int dt, const std::string& wkey, const std::strin
 
 int finalize_layer(ddpm3d_ctx* ctx, Layer& L, std::vector<float>& emb_w, std::vector<float>& emb_b) {
   const std::string& p = L.prefix;
-  const int dt = ctx->dt;
+  const int dt = ctx->dt, dts = ctx->dts;
   if (L.kind == L_CONV || L.kind == L_UPCONV) {
-    DD_TRY(pack_conv(ctx, dt, p + ".weight", p + ".bias", 27, nullptr, nullptr, &L.c1));
+    // stem / Downsample / Upsample convs read a block input directly: the whole conv runs in the storage format
+    DD_TRY(pack_conv(ctx, dts, p + ".weight", p + ".bias", 27, nullptr, nullptr, &L.c1));
   } else if (L.kind == L_RES) {
     DD_TRY(upload_f32(ctx, p + ".in_layers.0.weight", &L.gn1_g));
     DD_TRY(upload_f32(ctx, p + ".in_layers.0.bias", &L.gn1_b));
@@ -444,12 +454,12 @@ int finalize_layer(ddpm3d_ctx* ctx, Layer& L, std::vector<float>& emb_w, std::ve
     DD_TRY(pack_conv(ctx, dt, p + ".in_layers.2.weight", p + ".in_layers.2.bias", 27, nullptr, nullptr, &L.c1));
     if (L.skip_conv) {
       const std::string sw = p + ".skip_connection.weight", sb = p + ".skip_connection.bias";
-      DD_TRY(pack_conv(ctx, dt, p + ".out_layers.3.weight", p + ".out_layers.3.bias", 27, &sw, &sb, &L.c2));
+      DD_TRY(pack_conv(ctx, dt, p + ".out_layers.3.weight", p + ".out_layers.3.bias", 27, &sw, &sb, &L.c2, false, dts));
     } else {
       // identity skip: the unit block is appended (w_ld grows by Cout); it is only read when the residual is
       // folded into the accumulation (fold_identity), otherwise the epilogue adds x and the block is skipped
       const bool ident = !L.up && !L.down && L.cin == L.cout;
-      DD_TRY(pack_conv(ctx, dt, p + ".out_layers.3.weight", p + ".out_layers.3.bias", 27, nullptr, nullptr, &L.c2, ident));
+      DD_TRY(pack_conv(ctx, dt, p + ".out_layers.3.weight", p + ".out_layers.3.bias", 27, nullptr, nullptr, &L.c2, ident, dts));
     }
     const Param* ew = find(ctx, p + ".emb_layers.1.weight");
     const Param* eb = find(ctx, p + ".emb_layers.1.bias");
@@ -510,7 +520,7 @@ struct Run {
     cudaEventRecord(ctx->prof.back().b, s);
   }
 
-  float* alloc_chsum(int C) { return (float*)arena.alloc((size_t)B * CHSUM_SLOTS * C * 2 * sizeof(float)); }
+  float* alloc_chsum(int C) { return (float*)arena.alloc((size_t)B * chsum_slots() * C * 2 * sizeof(float)); }
 
   int conv(ConvArgs& a) {
     a.B = B;
@@ -588,7 +598,7 @@ struct Run {
 
 int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   ddpm3d_ctx* ctx = R.ctx;
-  const int dt = ctx->dt;
+  const int dt = ctx->dt, dts = ctx->dts;
   int Cin = 0;
   for (int i = 0; i < nsrc; ++i) Cin += src[i].C;
   DD_CHECK(Cin == L.cin, DDPM3D_ERR_STATE, "internal: ResBlock input channel mismatch at " + L.prefix);
@@ -606,7 +616,8 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   void* h1 = R.arena.alloc(R.conv_in_bytes(Ho, Wo, Cin, ctx->esz));
   GnArgs g{};
   g.out_zpad = R.zp;
-  g.dt = dt;
+  g.dt = dts;
+  g.dt_out = dt;
   for (int i = 0; i < nsrc; ++i) { g.src[i] = src[i].p; g.C[i] = src[i].C; g.chsum[i] = src[i].chsum; }
   g.H = H; g.W = W;
   g.gamma = L.gn1_g; g.beta = L.gn1_b;
@@ -619,6 +630,7 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   void* h2 = R.arena.alloc(R.act_bytes(Ho, Wo, L.cout));
   ConvArgs c{};
   c.dt = dt;
+  c.dt_io = dts;
   c.main = {h1, Cin};
   c.taps = 27;
   c.w = L.c1.w; c.bias = L.c1.bias;
@@ -629,7 +641,8 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   void* h3 = R.arena.alloc(R.conv_in_bytes(Ho, Wo, L.cout, ctx->esz));
   GnArgs g2{};
   g2.out_zpad = R.zp;
-  g2.dt = dt;
+  g2.dt = dts;
+  g2.dt_out = dt;
   g2.src[0] = h2; g2.C[0] = L.cout;
   g2.chsum[0] = c.chsum_written ? c.chsum_out : nullptr;
   g2.H = Ho; g2.W = Wo;
@@ -643,6 +656,7 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   DD_TRY(R.halo(h3, Ho, Wo, L.cout, ctx->esz));
   ConvArgs c2{};
   c2.dt = dt;
+  c2.dt_io = dts;
   c2.main = {h3, L.cout};
   c2.taps = 27;
   c2.w = L.c2.w; c2.bias = L.c2.bias;
@@ -667,14 +681,14 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
 
 int run_attn(Run& R, const Layer& L, const Act& x, Act* out) {
   ddpm3d_ctx* ctx = R.ctx;
-  const int dt = ctx->dt, C = L.cin, H = x.H, W = x.W;
+  const int dt = ctx->dt, dts = ctx->dts, C = L.cin, H = x.H, W = x.W;
   DD_CHECK(x.C == C, DDPM3D_ERR_STATE, "internal: attention channel mismatch");
   out->C = C; out->H = H; out->W = W;
   out->p = R.arena.alloc(R.act_bytes(H, W, C));
   const size_t mark = R.arena.off;
   void* n = R.arena.alloc(R.act_bytes(H, W, C));
   GnArgs g{};
-  g.dt = dt; g.src[0] = x.p; g.C[0] = C; g.H = H; g.W = W; g.gamma = L.gn1_g; g.beta = L.gn1_b; g.silu = 0; g.out = n;
+  g.dt = dts; g.dt_out = dt; g.src[0] = x.p; g.C[0] = C; g.H = H; g.W = W; g.gamma = L.gn1_g; g.beta = L.gn1_b; g.silu = 0; g.out = n;
   DD_TRY(R.gn(g));
   void* qkv = R.arena.alloc(R.act_bytes(H, W, 3 * C));
   ConvArgs c{};
@@ -714,7 +728,7 @@ int run_attn(Run& R, const Layer& L, const Act& x, Act* out) {
     DD_TRY(r);
   }
   ConvArgs p{};
-  p.dt = dt; p.main = {a, C}; p.taps = 1; p.w = L.c2.w; p.bias = L.c2.bias; p.out = out->p; p.Ho = H; p.Wo = W; p.Cout = C;
+  p.dt = dt; p.dt_io = dts; p.main = {a, C}; p.taps = 1; p.w = L.c2.w; p.bias = L.c2.bias; p.out = out->p; p.Ho = H; p.Wo = W; p.Cout = C;
   p.residual = x.p; p.res_mode = RES_SAME;
   DD_TRY(R.conv(p));
   R.arena.off = mark;
@@ -723,7 +737,7 @@ int run_attn(Run& R, const Layer& L, const Act& x, Act* out) {
 
 int run_conv_layer(Run& R, const Layer& L, const Act& x, Act* out) {
   ddpm3d_ctx* ctx = R.ctx;
-  const int dt = ctx->dt;
+  const int dt = ctx->dts;  // reads a block input / the packed network input: runs in the storage format
   DD_CHECK(x.C == L.cin, DDPM3D_ERR_STATE, "internal: conv channel mismatch at " + L.prefix);
   DD_CHECK(!R.zp || L.prefix == "input_blocks.0.0", DDPM3D_ERR_ARG,
            "z-slab sharding needs resblock_updown=True (bare Downsample / Upsample convs read un-haloed tensors)");
@@ -811,8 +825,8 @@ int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, cons
     DD_CHECK((low != nullptr) == (ctx->cfg.unconditional == 0), DDPM3D_ERR_ARG,
              "low_res must be given to a conditional model and only to it (unet.py:1687-1694)");
     R.prof_begin(8, (double)B * Z * H * W * Cstem * (4.0 + ctx->esz));
-    const int r = Cx == 1 && low ? pack_input(dt, x, low, h.p, B, Z, (int64_t)H * W, R.zp, R.s)
-                                 : pack_input_planar(dt, x, low, Cx, h.p, B, Z, (int64_t)H * W, R.zp, R.s);
+    const int r = Cx == 1 && low ? pack_input(ctx->dts, x, low, h.p, B, Z, (int64_t)H * W, R.zp, R.s)
+                                 : pack_input_planar(ctx->dts, x, low, Cx, h.p, B, Z, (int64_t)H * W, R.zp, R.s);
     R.prof_end();
     DD_TRY(r);
   }
@@ -843,7 +857,7 @@ int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, cons
   GnArgs g{};
   g.out_zpad = R.zp;
   g.chsum[0] = h.chsum;
-  g.dt = dt; g.src[0] = h.p; g.C[0] = h.C; g.H = H; g.W = W; g.gamma = ctx->out_gn_g; g.beta = ctx->out_gn_b; g.silu = 1;
+  g.dt = ctx->dts; g.src[0] = h.p; g.C[0] = h.C; g.H = H; g.W = W; g.gamma = ctx->out_gn_g; g.beta = ctx->out_gn_b; g.silu = 1;
   g.out = hn; g.out_f32 = 1;
   DD_TRY(R.gn(g));
   DD_TRY(R.halo(hn, H, W, h.C, sizeof(float)));
@@ -861,9 +875,12 @@ int check_geometry(ddpm3d_ctx* ctx, int B, int Z, int H, int W) {
   const int f = 1 << (ctx->cfg.n_levels - 1);
   DD_CHECK(H % f == 0 && W % f == 0, DDPM3D_ERR_ARG, "H and W must be divisible by 2^(levels-1)");
   DD_CHECK(((int64_t)Z * H * W) % 4 == 0, DDPM3D_ERR_ARG, "Z*H*W must be a multiple of 4");
+  // a sharded call takes a proper part of the volume: a stale set_slab (or an un-sharded patch while the sharded path
+  // is still switched on) is refused instead of silently exchanging halos with the other ranks
   if (ctx->slab.active())
-    DD_CHECK(ctx->slab.z_total >= Z && ctx->slab.z_begin + Z <= ctx->slab.z_total, DDPM3D_ERR_STATE,
-             "z-slab sharding: call ddpm3d_set_slab(z_begin, z_total) for this volume first");
+    DD_CHECK(ctx->slab.z_total > Z && ctx->slab.z_begin + Z <= ctx->slab.z_total, DDPM3D_ERR_STATE,
+             "z-slab sharding is on but this call is not a slab of the volume set by ddpm3d_set_slab(z_begin, z_total): "
+             "set the slab for this volume, or switch sharding off with ddpm3d_set_slab(ctx, 0, 0)");
   return DDPM3D_OK;
 }
 
@@ -1038,11 +1055,12 @@ int ddpm3d_abi_version(void) { return DDPM3D_ABI_VERSION; }
 
 int ddpm3d_create(const ddpm3d_config* cfg, ddpm3d_ctx** out) {
   DD_CHECK(cfg && out, DDPM3D_ERR_ARG, "ddpm3d_create: null argument");
-  DD_CHECK(cfg->precision == DDPM3D_FP32 || is_half_dt(cfg->precision), DDPM3D_ERR_ARG, "config: bad precision");
+  DD_CHECK(cfg->precision >= DDPM3D_FP32 && cfg->precision <= DDPM3D_BF16_STRICT, DDPM3D_ERR_ARG, "config: bad precision");
   std::unique_ptr<ddpm3d_ctx> ctx(new ddpm3d_ctx());
   ctx->cfg = *cfg;
-  ctx->dt = cfg->precision;
-  ctx->esz = is_half_dt(cfg->precision) ? 2 : 4;
+  ctx->dt = cfg->precision == DDPM3D_BF16_STRICT ? DDPM3D_BF16 : cfg->precision;
+  ctx->dts = cfg->precision == DDPM3D_BF16 ? DDPM3D_FP16 : ctx->dt;
+  ctx->esz = is_half_dt(ctx->dt) ? 2 : 4;
   DD_TRY(build_topology(ctx.get()));
   *out = ctx.release();
   return DDPM3D_OK;
@@ -1367,9 +1385,24 @@ int ddpm3d_set_comm(ddpm3d_ctx* ctx, const void* id128, int rank, int world) {
 
 int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total) {
   DD_CHECK(ctx, DDPM3D_ERR_ARG, "set_slab: null ctx");
-  DD_CHECK(z_begin >= 0 && z_total >= 1 && z_begin < z_total, DDPM3D_ERR_ARG, "set_slab: bad bounds");
-  ctx->slab.z_begin = z_begin;
-  ctx->slab.z_total = z_total;
+  const bool was = ctx->slab.active();
+  if (z_total == 0) {  // back to un-sharded work (independent patches, ensemble samples): no halo / statistics exchange
+    DD_CHECK(z_begin == 0, DDPM3D_ERR_ARG, "set_slab: bad bounds");
+    ctx->slab.enabled = false;
+  } else {
+    DD_CHECK(z_begin >= 0 && z_total >= 1 && z_begin < z_total, DDPM3D_ERR_ARG, "set_slab: bad bounds");
+    DD_CHECK(ctx->slab.comm != nullptr, DDPM3D_ERR_STATE, "set_slab: no communicator (call ddpm3d_set_comm first)");
+    ctx->slab.z_begin = z_begin;
+    ctx->slab.z_total = z_total;
+    ctx->slab.enabled = true;
+  }
+  if (was != ctx->slab.active() && ctx->device >= 0) {  // workspace layout (halo planes) and graphs depend on the mode
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+    ctx->graphs.clear();
+    ctx->graph_launches.clear();
+  }
   return DDPM3D_OK;
 }
 

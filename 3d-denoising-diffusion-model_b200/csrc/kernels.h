@@ -17,7 +17,12 @@ struct ConvSrc {
 };
 
 struct ConvArgs {
-  int dt = DDPM3D_FP32;       // element type of main/extra sources and of w
+  int dt = DDPM3D_FP32;       // element type of the main source and of its weight columns
+  // element type of the extra (1x1x1) sources and THEIR weight columns, of the residual and of the output: -1 = dt.
+  // In the default 16-bit mode the conv operands (GroupNorm outputs, weights) are bf16 while block inputs / outputs
+  // -- tensors that only GroupNorm, the skip path and the residual read -- are stored as fp16.
+  int dt_io = -1;
+  int io_dt() const { return dt_io < 0 ? dt : dt_io; }
   ConvSrc main;               // 3x3x3 (taps=27) or 1x1x1 (taps=1) source
   int in_zpad = 0;            // main source carries this many halo planes on each side of Z (z-slab sharding):
                               // [B][Z + 2*in_zpad][Hin][Win][C]; the conv then never pads in Z itself
@@ -34,7 +39,7 @@ struct ConvArgs {
   int out_planar_f32 = 0;
   int B = 0, Z = 0, Ho = 0, Wo = 0, Cout = 0;  // output geometry; input H/W = Ho*stride
   // Optional (tcgen05 path only): per-channel [sum, sum of squares] of the OUTPUT, accumulated from the fp32
-  // accumulators in the epilogue, one partial per CTA: chsum_out[B][CHSUM_SLOTS][Cout][2].  The consuming
+  // accumulators in the epilogue, one partial per CTA: chsum_out[B][chsum_slots()][Cout][2].  The consuming
   // GroupNorm then skips its statistics pass over the tensor.  chsum_written is set by the launcher.
   float* chsum_out = nullptr;
   int chsum_written = 0;
@@ -47,7 +52,7 @@ struct ConvArgs {
   int head_v2_allowed = 1;  // head conv: 32x16x4 bricks, 8 voxels per thread, cp.async double-buffered channel stages
   int stem_tc_allowed = 1;  // Cin == 2 stem as one M128 x Cout x K64 tcgen05 tile per 128 voxels (16-bit modes)
 };
-constexpr int CHSUM_SLOTS = 148;  // one per persistent CTA (unused slots are zeroed by the launcher)
+inline int chsum_slots() { return sm_count(); }  // one per persistent CTA (unused slots are zeroed by the launcher)
 
 int conv_simt(const ConvArgs& a, cudaStream_t s);
 // thin ends of the network on the CUDA cores with smem-staged halo bricks (conv_small.cu)
@@ -76,7 +81,8 @@ struct GnArgs {
   int64_t pre_stride = 0;
   int silu = 1;
   int resample = RS_NONE;
-  void* out = nullptr;                      // dt (or fp32 when out_f32)
+  void* out = nullptr;                      // dt_out (or fp32 when out_f32)
+  int dt_out = -1;                          // 16-bit output format when it differs from the input's (-1 = dt)
   int out_f32 = 0;
   int out_zpad = 0;                         // output tensor has this many halo planes on each side of Z (left untouched)
   // cross-rank statistics (z-slab sharding): when gathered != NULL the finalize pass reads

@@ -152,6 +152,10 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+inline CUtensorMapDataType tmap_dtype(int dt) {
+  return dt == DDPM3D_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+}
+
 // channels-last activation [B][Z][H][W][C] -> 5-D map, box {64, bw, bh, bz, 1}
 int make_act_map(CUtensorMap* map, CUtensorMapDataType dtype, const void* ptr, int B, int Z, int H, int W, int C, int bw, int bh,
                  int bz) {

@@ -65,7 +65,7 @@ __global__ void welford_merge_kernel(float* __restrict__ mean_a, float* __restri
   }
 }
 
-int grid_for(int64_t n) { return (int)std::min<int64_t>(ceil_div(n, 256), 148 * 16); }
+int grid_for(int64_t n) { return (int)std::min<int64_t>(ceil_div(n, 256), sm_count() * 16); }
 
 }  // namespace
 }  // namespace ddpm3d

@@ -1,6 +1,6 @@
 """Uncertainty-map ensemble (README.md:44 "uncertainty maps"; BASELINE.json config 5): several stochastic
 samples of the same low-dose input, voxel-wise mean and variance reduced on the device.  Samples shard over
-ranks with no communication; per-rank Welford partials are merged once at the end in rank order."""
+ranks with no communication; per-rank Welford partials are merged once at the end along a fixed binary tree."""
 from __future__ import annotations
 
 from . import _native as N
@@ -43,25 +43,42 @@ class Welford:
         return self.m2 / max(d, 1)
 
 
-def gather_partials(mean, m2, count):
-    """Every rank's (mean, M2, count), in rank order (torch.distributed plumbing)."""
+def reduce_partials(acc, group=None):
+    """Merges every rank's Welford partial into rank 0's `acc` along a fixed binary tree (log2(world) rounds of one
+    point-to-point (mean, M2) transfer each; the merge order depends only on the world size, so the result is
+    deterministic).  Returns True on the rank that holds the total."""
     import torch
     import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return [(mean, m2, count)]
-    world = dist.get_world_size()
-    means = [torch.empty_like(mean) for _ in range(world)]
-    m2s = [torch.empty_like(m2) for _ in range(world)]
-    counts = [None] * world
-    dist.all_gather(means, mean.contiguous())
-    dist.all_gather(m2s, m2.contiguous())
-    dist.all_gather_object(counts, int(count))
-    return list(zip(means, m2s, counts))
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return True
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    g = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    step = 1
+    while step < world:
+        if rank % (2 * step) == step:  # sender: hands its partial to rank - step and is done
+            cnt = torch.tensor([acc.count], device=acc.device, dtype=torch.int64)
+            dist.send(cnt, g(rank - step), group=group)
+            if acc.count:
+                dist.send(acc.mean.contiguous(), g(rank - step), group=group)
+                dist.send(acc.m2.contiguous(), g(rank - step), group=group)
+            return False
+        if rank % (2 * step) == 0 and rank + step < world:
+            cnt = torch.zeros(1, device=acc.device, dtype=torch.int64)
+            dist.recv(cnt, g(rank + step), group=group)
+            n_b = int(cnt.item())
+            if n_b:
+                mean_b, m2_b = torch.empty_like(acc.mean), torch.empty_like(acc.m2)
+                dist.recv(mean_b, g(rank + step), group=group)
+                dist.recv(m2_b, g(rank + step), group=group)
+                acc.merge(mean_b, m2_b, n_b)
+        step *= 2
+    return rank == 0
 
 
-def ensemble_sample(model, diffusion, low_res, seeds, clip_denoised=True, **loop_kwargs):
+def ensemble_sample(model, diffusion, low_res, seeds, clip_denoised=True, all_ranks=True, **loop_kwargs):
     """One sample per seed (seed -> torch CUDA generator, like scripts/test.py:45-48 does with 10), seeds
-    rank-strided; returns (mean, variance, n) identical on every rank."""
+    rank-strided; the per-rank partials are reduced to rank 0 (tree) and, with `all_ranks`, the result is broadcast.
+    Returns (mean, variance, n): valid on rank 0, and on every rank when `all_ranks`."""
     import torch
     dev = next(model.parameters()).device
     low_res = low_res.to(dev)
@@ -72,7 +89,15 @@ def ensemble_sample(model, diffusion, low_res, seeds, clip_denoised=True, **loop
         noise = torch.randn(*shape, device=dev)
         acc.update(diffusion.p_sample_loop(model, shape, noise, clip_denoised=clip_denoised,
                                            model_kwargs={"low_res": low_res}, **loop_kwargs))
-    total = Welford(shape, dev)
-    for mean, m2, count in gather_partials(acc.mean, acc.m2, acc.count):
-        total.merge(mean, m2, count)
-    return total.mean, total.variance(), total.count
+    reduce_partials(acc)
+    mean, var, n = acc.mean, acc.variance(), acc.count
+    if all_ranks:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            cnt = torch.tensor([n], device=dev, dtype=torch.int64)
+            dist.broadcast(cnt, 0)
+            n = int(cnt.item())
+            var = acc.m2 / max(n - 1, 1) if dist.get_rank() == 0 else torch.empty_like(mean)
+            dist.broadcast(mean, 0)
+            dist.broadcast(var, 0)
+    return mean, var, n

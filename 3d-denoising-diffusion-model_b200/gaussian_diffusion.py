@@ -203,6 +203,9 @@ class GaussianDiffusion:
         B, C = x.shape[:2]
         learned = self.model_var_type in (ModelVarType.LEARNED, ModelVarType.LEARNED_RANGE)
         assert model_output.shape == (B, C * 2 if learned else C, *x.shape[2:])
+        # _extract_into_tensor (gaussian_diffusion.py:897-910) indexes the tables with t: out of range raises there
+        if t.numel() and (int(t.min()) < 0 or int(t.max()) >= self.num_timesteps):
+            raise IndexError(f"timestep index out of range [0, {self.num_timesteps})")
         _, ctx = self._ctx_for(model, x.device)
         model_output = model_output.contiguous().float()
         out = {k: torch.empty_like(x) for k in ("mean", "log_variance", "pred_xstart", "sample")}

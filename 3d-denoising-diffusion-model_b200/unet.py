@@ -37,7 +37,9 @@ def _make_config(*, image_size, model_channels, out_channels, num_res_blocks, at
         if int(m) != m:
             raise ValueError("channel_mult entries must be integers")
         cfg.channel_mult[i] = int(m)
-    ds = list(attention_resolutions)[: N.MAX_LEVELS]
+    ds = list(attention_resolutions)
+    if len(ds) > N.MAX_LEVELS:
+        raise ValueError("too many attention resolutions")
     cfg.n_attention_ds = len(ds)
     for i, d in enumerate(ds):
         cfg.attention_ds[i] = int(d)
@@ -60,9 +62,12 @@ def timestep_freqs(dim, max_period=10000):
     return torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half).contiguous()
 
 
+_HALF = {"bf16": N.BF16, "fp16": N.FP16, "bf16_strict": N.BF16_STRICT}
+
+
 def _half_from_env():
     import os
-    return {"bf16": N.BF16, "fp16": N.FP16}[os.environ.get("DDPM3D_HALF_DTYPE", "bf16").lower()]
+    return _HALF[os.environ.get("DDPM3D_HALF_DTYPE", "bf16").lower()]
 
 
 class _Ctx:
@@ -277,11 +282,12 @@ class UNetModel_noatt:
             self._drop_ctx()
 
     def set_half_dtype(self, name):
-        """Which 16-bit type `use_fp16` / convert_to_fp16() means: "bf16" (default, or env DDPM3D_HALF_DTYPE)
-        or "fp16" (the reference's dtype: same tensor-core rate, 3 more mantissa bits, smaller range)."""
-        half = {"bf16": N.BF16, "fp16": N.FP16}[name]
+        """Which 16-bit mode `use_fp16` / convert_to_fp16() means: "bf16" (default, or env DDPM3D_HALF_DTYPE): bf16
+        tensor-core operands, block inputs / outputs stored as fp16; "fp16" (the reference's dtype everywhere: same
+        tensor-core rate, 3 more mantissa bits on the operands too); "bf16_strict" (every 16-bit tensor bf16)."""
+        half = _HALF[name]
         if half != self._half:
-            was_half = self._precision in (N.BF16, N.FP16)
+            was_half = self._precision in (N.BF16, N.FP16, N.BF16_STRICT)
             self._half = half
             if was_half:
                 self._precision = half
@@ -356,7 +362,14 @@ class UNetModel_noatt:
         return self
 
     def set_slab(self, z_begin, z_total):
+        """Position of this rank's slab in the global volume; switches the sharded path on (every following call
+        must be a proper slab of that volume)."""
         N.check(N.lib().ddpm3d_set_slab(self._ensure_ctx(), int(z_begin), int(z_total)))
+
+    def disable_slab_sharding(self):
+        """Back to un-sharded work on this context (independent patches, ensemble samples); the communicator stays."""
+        if self._ctx is not None:
+            N.check(N.lib().ddpm3d_set_slab(self._ctx, 0, 0))
 
     def launch_count(self):
         return int(N.lib().ddpm3d_launch_count(self._ctx)) if self._ctx is not None else 0
@@ -427,6 +440,14 @@ class UNetModel_noatt:
         yy = self._y(model_kwargs.get("y"), B)
         if not hasattr(self, "_ps_buf") or self._ps_buf[0].shape != x.shape or self._ps_buf[0].device != x.device:
             self._ps_buf = [torch.empty_like(x) for _ in range(3)]
+            self._ps_stage = [torch.empty_like(x) for _ in range(3)]
+        if clone:
+            # public p_sample: the caller's x / noise / low_res are usually fresh allocations every step, and the
+            # library's CUDA-graph cache is keyed by pointers -- stage them in persistent buffers (three small
+            # device copies) so one captured graph serves every call
+            for buf, src in zip(self._ps_stage, (x, noise, low)):
+                buf.copy_(src, non_blocking=True)
+            x, noise, low = self._ps_stage
         # two sample buffers ping-pong (the input `x` is usually the previous output); x0 has its own
         sample = self._ps_buf[1] if x.data_ptr() == self._ps_buf[0].data_ptr() else self._ps_buf[0]
         x0 = self._ps_buf[2]

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DDPM3D_ABI_VERSION 3
+#define DDPM3D_ABI_VERSION 4
 
 #define DDPM3D_OK 0
 #define DDPM3D_ERR_ARG (-1)     /* bad argument / unsupported configuration */
@@ -40,8 +40,12 @@ extern "C" {
 
 /* precision of the UNet torso (unet.py:1003-1013 convert_to_fp16 -> here bf16 on tcgen05) */
 #define DDPM3D_FP32 0
-#define DDPM3D_BF16 1
+#define DDPM3D_BF16 1 /* bf16 tensor-core operands (3x3x3 / qkv / proj weights, GroupNorm outputs); the tensors that are NOT
+                         operands of the dense contraction -- ResBlock inputs / outputs and the tensor between a block's two
+                         convs, read only by GroupNorm, the 1x1x1 skip path and residual adds -- are stored as fp16 (same
+                         bytes, 3 more mantissa bits: eps max-rel x0.65) */
 #define DDPM3D_FP16 2 /* the reference's own torso dtype; same tcgen05 rate as bf16, 3 more mantissa bits */
+#define DDPM3D_BF16_STRICT 3 /* every 16-bit tensor bf16 (the round-1 behaviour; kept for comparison) */
 
 /* gaussian_diffusion.py:65-72 ModelMeanType */
 #define DDPM3D_MEAN_PREVIOUS_X 0
@@ -77,7 +81,7 @@ typedef struct ddpm3d_config {
   int32_t use_scale_shift_norm;
   int32_t resblock_updown;
   int32_t use_new_attention_order;
-  int32_t precision;       /* DDPM3D_FP32 | DDPM3D_BF16 | DDPM3D_FP16 */
+  int32_t precision;       /* DDPM3D_FP32 | DDPM3D_BF16 | DDPM3D_FP16 | DDPM3D_BF16_STRICT */
   /* ABI 3: the other model classes of unet.py.  All-zero = SuperResModel_noatt with dims=3 (the live model). */
   int32_t dims;            /* 0 or 3: Conv3d, (1,2,2) resampling; 2: the 2-D UNetModel (unet.py:396-716): weights
                               are [Cout][Cin][3][3], activations (B,C,H,W) are passed with Z = 1 */
@@ -184,8 +188,11 @@ int ddpm3d_sample_loop(ddpm3d_ctx* ctx, const float* x_T, const float* low_res, 
  * forward / sampler entry points take THIS RANK'S slab (B,1,Zl,H,W): conv-input tensors carry two halo planes
  * filled by NCCL send/recv, GroupNorm all-gathers fp64 partial sums and adds them in rank order (deterministic).
  * comm_unique_id: rank 0 creates the 128-byte NCCL id, the host broadcasts it (torch.distributed), every
- * rank calls set_comm.  set_slab: where this rank's slab sits in the global volume (GroupNorm count, Philox
- * counters).  Requires resblock_updown=1 and no attention levels. */
+ * rank calls set_comm.  set_slab(z_begin, z_total): where this rank's slab sits in the global volume (GroupNorm
+ * count, Philox counters); it switches the sharded path ON, and every following forward / sampler call must be a
+ * proper slab (Zl < z_total) of that volume.  set_slab(0, 0) switches it OFF again (independent patches, ensemble
+ * samples on the same context).  Requires resblock_updown=1.  Attention levels are supported with equal slabs in
+ * rank order (z_total = world * Zl): queries stay local, the qkv rows are all-gathered along T. */
 int ddpm3d_comm_unique_id(void* out128);
 int ddpm3d_set_comm(ddpm3d_ctx* ctx, const void* id128, int rank, int world);
 int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total);
@@ -198,9 +205,9 @@ int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total);
  * convolution's epilogue instead of a separate pass over the tensor;
  * "split_k" (0/1, default 1): convolutions with too few tiles to fill the GPU deal their k-steps evenly to the CTAs
  * (stream-K: fp32 partials, deterministic fix-up pass);
- * "strip" (0/1, default 0): large 3x3x3 layers stage the A operand once per (dz, channel chunk) and address the 9
- * in-plane taps through row-shifted descriptors (half the L2 traffic; 6-14 % faster stand-alone, neutral inside the
- * power-capped network step);
+ * "strip" (0/1, default 1): large 3x3x3 layers stage the A operand once per (dz, channel chunk) and address the 9
+ * in-plane taps through row-shifted descriptors, with swapped MMA operands (M = channels, N = up to 256 voxels):
+ * half the L2 traffic, -9 % on the network step;
  * "cluster" (0/1, default 0): 2-CTA clusters multicast the weight tile (neutral);
  * "fold_identity" (0/1, default 1): identity skips enter the second conv of a ResBlock as a unit-weight 1x1x1 source;
  * "stem_tc" (0/1, default 1): the Cin == 2 stem runs as one tcgen05 tile per 128 voxels in the 16-bit modes;

@@ -17,22 +17,43 @@ pytestmark = pytest.mark.gpu
 from gpu_util import DEV, max_rel  # noqa: E402
 
 # eps max-rel (||d||_inf / ||ref||_inf) against the fp32 reference.  fp32 mode: the north star's 1e-4.
-# bf16 mode: the north star asks 1e-2; measured 1.2e-2 .. 2.1e-2 on these random-weight networks, which
-# is the rounding floor of 8-bit mantissas: each ResBlock rounds 4 tensors (2^-9/sqrt(3) = 1.1e-3 rms
-# each), 25-35 blocks in sequence -> ~1.2e-2 rms.  The bound asserted here is 3e-2; DESIGN.md has the table.
-TOL = {False: 1e-4, True: 3e-2, "fp16": 1e-2}
+# 16-bit modes: the north star's 1e-2 for the default bf16 mode (bf16 tensor-core operands, fp16 storage of the tensors
+# that are not operands -- DESIGN.md section 5); the reference's own fp16 measures <= 3.2e-3 everywhere and is asserted
+# at 5e-3; "bf16_strict" (every tensor bf16, the round-1 design) measures 1.2 .. 2.5e-2 and keeps its 3e-2 bound.
+TOL = {False: 1e-4, True: 1e-2, "fp16": 5e-3, "bf16_strict": 3e-2}
+# The toy networks on which the default bf16 mode does NOT reach 1e-2, by name, with what was measured on B200 and the
+# bound asserted instead (everything else, including the shipped architecture on the slab, 7.7e-3, and on the full
+# 96^3 patch, 6.6e-3, is asserted at 1e-2).  tests/test_rounding_floor.py shows on the CPU oracle why no bf16-operand
+# design can get there: rounding ONLY the conv weights to bf16 already costs 1.0e-2 on C1.
+BF16_ABOVE_1E2 = {
+    "tiny_b2": dict(measured=1.22e-2, bound=1.5e-2),        # 32 channels, batch 2
+    "c1_first_eps": dict(measured=1.72e-2, bound=2.2e-2),   # BASELINE configs[0]: 32 channels, 32^3
+    "attn64": dict(measured=1.07e-2, bound=1.3e-2),         # 64 channels, six attention blocks (qkv, P and PV operands bf16)
+}
+
+
+# final-volume bounds of the C2-architecture loop test: <= 2x the NRMSE measured on B200
+# (measured: bf16 NRMSE 2.7e-3 / PSNR 59.2 dB, fp16 5.2e-4 / 73.6 dB)
+C2_LOOP_BOUND = {True: dict(nrmse=5.5e-3, psnr=53.0), "fp16": dict(nrmse=1.1e-3, psnr=67.0)}
+
+
+def tol(fp16, name=None):
+    if fp16 is True and name in BF16_ABOVE_1E2:
+        return BF16_ABOVE_1E2[name]["bound"]
+    return TOL[fp16]
 
 
 def build(flags_over, seed=0, fp16=False, graph=True):
-    """fp16: False (fp32 mode), True (bf16 torso, the default 16-bit type) or "fp16" (the reference's dtype)."""
+    """fp16: False (fp32 mode), True (the default 16-bit mode: bf16 operands), "fp16" (the reference's dtype) or
+    "bf16_strict" (every 16-bit tensor bf16)."""
     flags = cases.sr_flags(**{**flags_over, "use_fp16": bool(fp16)})
     cfg = cases.cfg_from_flags(flags)
     sd = synth_state_dict(cfg, seed=seed)
     model, diffusion = su.sr_create_model_and_diffusion(**flags)
     model.load_state_dict(sd)
     model.to(DEV)
-    if fp16 == "fp16":
-        model.set_half_dtype("fp16")
+    if isinstance(fp16, str):
+        model.set_half_dtype(fp16)
     if fp16:
         model.convert_to_fp16()
     model.eval()
@@ -40,7 +61,7 @@ def build(flags_over, seed=0, fp16=False, graph=True):
     return model, diffusion, cfg, sd
 
 
-@pytest.mark.parametrize("fp16", [False, True, "fp16"])
+@pytest.mark.parametrize("fp16", [False, True, "fp16", "bf16_strict"])
 @pytest.mark.parametrize("name", list(cases.UNET_CASES))
 def test_unet_matches_reference(golden_dir, name, fp16):
     """SuperResModel_noatt.forward on the reference's own outputs (tests/golden/unet_tiny.npz)."""
@@ -54,7 +75,9 @@ def test_unet_matches_reference(golden_dir, name, fp16):
     torch.cuda.synchronize()
     assert out.shape == want.shape
     assert torch.equal(out, out2)
-    assert max_rel(out.cpu(), want) <= TOL[fp16]
+    err = max_rel(out.cpu(), want)
+    print(f"unet case {name}, mode {fp16}: eps max-rel {err:.3e}")
+    assert err <= tol(fp16, name)
     assert model.launch_count() > 0
 
 
@@ -80,7 +103,9 @@ def test_c1_full_loop_matches_reference(golden_dir, fp16):
     kw = {"low_res": low.to(DEV)}
     # first eps
     mo = model(x_T.to(DEV), diffusion._map_timesteps(torch.tensor([T - 1], device=DEV)), **kw)
-    assert max_rel(mo.cpu(), torch.from_numpy(g["mo_first"])) <= TOL[fp16]
+    e_first = max_rel(mo.cpu(), torch.from_numpy(g["mo_first"]))
+    print(f"C1 first eps, mode {fp16}: max-rel {e_first:.3e}")
+    assert e_first <= tol(fp16, "c1_first_eps")
     # python-stepped loop (reference RNG order, noise injected)
     s1 = diffusion.p_sample_loop(model, cases.C1_SHAPE, noise=x_T.to(DEV), clip_denoised=True, model_kwargs=kw,
                                  step_noise=[n.to(DEV) for n in noises])
@@ -93,13 +118,15 @@ def test_c1_full_loop_matches_reference(golden_dir, fp16):
     err = (s1.cpu() - want)
     nrmse = float(err.pow(2).mean().sqrt() / want.pow(2).mean().sqrt())
     psnr = float(10 * torch.log10(4.0 / err.pow(2).mean()))  # data range [-1, 1]
+    print(f"C1 10-step loop, mode {fp16}: NRMSE {nrmse:.3e}, PSNR {psnr:.1f} dB")
+    # final-volume bounds: <= 2x what was measured on B200 (fp16: NRMSE 1.0e-3 / 67.9 dB; bf16: 5.1e-3 / 53.9 dB;
+    # fp32: 1.7e-6 / 123.7 dB)
     if fp16 == "fp16":
-        assert nrmse <= 1e-2 and psnr >= 45.0, (nrmse, psnr)
+        assert nrmse <= 2e-3 and psnr >= 62.0, (nrmse, psnr)
     elif fp16:
-        # 10 respaced steps amplify eps errors by up to sqrt(1/abar - 1) = 157 before the clamp
-        assert nrmse <= 1e-1 and psnr >= 25.0, (nrmse, psnr)
+        assert nrmse <= 1e-2 and psnr >= 48.0, (nrmse, psnr)
     else:
-        assert nrmse <= 1e-4 and psnr >= 80.0, (nrmse, psnr)
+        assert nrmse <= 1e-5 and psnr >= 110.0, (nrmse, psnr)
 
 
 def test_progressive_and_p_sample_api():
@@ -159,7 +186,7 @@ def test_errors_are_python_exceptions():
                                 model_kwargs={"low_res": torch.zeros((1, 1, 4, 16, 16), device=DEV)})
 
 
-@pytest.mark.parametrize("fp16", [False, True, "fp16"])
+@pytest.mark.parametrize("fp16", [False, True, "fp16", "bf16_strict"])
 def test_c2_architecture_matches_oracle(fp16):
     """The shipped network (128 ch, 2 res blocks, mult 1-1-2-3-4; 207 M parameters) on a (1,1,8,96,96) slab of
     the BASELINE config-2 patch against the CPU oracle: every layer shape class of the 96^3 bench workload
@@ -170,8 +197,8 @@ def test_c2_architecture_matches_oracle(fp16):
     model, _ = su.sr_create_model_and_diffusion(**flags)
     model.load_state_dict(sd)
     model.to(DEV)
-    if fp16 == "fp16":
-        model.set_half_dtype("fp16")
+    if isinstance(fp16, str):
+        model.set_half_dtype(fp16)
     if fp16:
         model.convert_to_fp16()
     model.eval()
@@ -183,6 +210,39 @@ def test_c2_architecture_matches_oracle(fp16):
     err = max_rel(out, want)
     print(f"C2 architecture, mode {fp16}: eps max-rel {err:.3e}")
     assert err <= TOL[fp16], err
+
+
+@pytest.mark.parametrize("fp16", [True, "fp16"])
+def test_c2_architecture_loop_matches_oracle(fp16):
+    """Final denoised volume at the headline configuration: the shipped network, 16-bit, the respaced ("10") reverse
+    loop with injected noise on a (1,1,8,96,96) slab of the C2 patch, against the CPU oracle's fp32 loop
+    (gaussian_diffusion.py:441-485 driven as scripts/test.py:61-69 does).  Smooth phantom as low_res."""
+    from oracle.sampler import p_sample_loop
+    from oracle.schedule import make_tables
+    flags = cases.sr_flags(use_fp16=True, timestep_respacing="10")
+    cfg = cases.cfg_from_flags(flags)
+    sd = synth_state_dict(cfg, seed=4)
+    model, diffusion = su.sr_create_model_and_diffusion(**flags)
+    model.load_state_dict(sd)
+    model.to(DEV)
+    if isinstance(fp16, str):
+        model.set_half_dtype(fp16)
+    model.convert_to_fp16()
+    model.eval()
+    shape = (1, 1, 8, 96, 96)
+    T = diffusion.num_timesteps
+    low, x_T, noises = synth_inputs(shape, T, phantom=True)
+    got = diffusion.p_sample_loop(model, shape, noise=x_T.to(DEV), clip_denoised=True, model_kwargs={"low_res": low.to(DEV)},
+                                  step_noise=torch.stack(noises).to(DEV)).cpu()
+    tabs = make_tables(steps=1000, learn_sigma=True, noise_schedule="linear", timestep_respacing="10")
+    want = p_sample_loop(tabs, lambda x, t: unet_forward(cfg, sd, x, t, low), x_T, noises)
+    err = got - want
+    nrmse = float(err.pow(2).mean().sqrt() / want.pow(2).mean().sqrt())
+    psnr = float(10 * torch.log10(4.0 / err.pow(2).mean()))
+    print(f"C2 architecture 10-step loop, mode {fp16}: NRMSE {nrmse:.3e}, PSNR {psnr:.1f} dB")
+    assert torch.isfinite(got).all()
+    bound = C2_LOOP_BOUND[fp16]
+    assert nrmse <= bound["nrmse"] and psnr >= bound["psnr"], (nrmse, psnr)
 
 
 @pytest.mark.parametrize("fp16", [True, "fp16"])
@@ -200,7 +260,9 @@ def test_unet_with_tensor_core_attention_matches_oracle(fp16):
     out = model(x.to(DEV), t.to(DEV), low_res=low.to(DEV)).cpu()
     kinds = [k for k, _, _ in model.profile_read()]
     assert kinds.count("attention") == 6  # ds = 2 and 4: one block each on the way down, two each on the way up
-    assert max_rel(out, want) <= TOL[fp16]
+    err = max_rel(out, want)
+    print(f"attention network (64-wide heads), mode {fp16}: eps max-rel {err:.3e}")
+    assert err <= tol(fp16, "attn64")
 
 
 @pytest.mark.parametrize("fp16", [False, True])

@@ -35,11 +35,11 @@ def _worker(rank, world, port, q):
         for idx, (mode, shape, tol, ch, att) in enumerate((
                                           (False, (1, 1, 10, 16, 16), 2e-5, 64, "1000"),
                                           (False, (2, 1, 9, 16, 32), 2e-5, 64, "1000"),
-                                          (True, (1, 1, 12, 32, 32), 3e-2, 64, "1000"),
+                                          (True, (1, 1, 12, 32, 32), 1e-2, 64, "1000"),
                                           (False, (1, 1, 8, 16, 16), 2e-5, 64, "8,4"),
                                           (False, (2, 1, 4, 16, 16), 2e-5, 64, "8"),
-                                          (True, (1, 1, 8, 32, 32), 3e-2, 64, "8,4"),
-                                          (True, (1, 1, 16, 96, 96), 3e-2, 128, "1000"))):
+                                          (True, (1, 1, 8, 32, 32), 1.3e-2, 64, "8,4"),
+                                          (True, (1, 1, 16, 96, 96), 1e-2, 128, "1000"))):
             if pick and str(idx) not in pick.split(","):
                 continue
             over = dict(large_size=16, small_size=16, num_channels=ch, num_res_blocks=2, num_head_channels=64,
@@ -48,11 +48,11 @@ def _worker(rank, world, port, q):
             cfg = cases.cfg_from_flags(flags)
             sd = synth_state_dict(cfg, seed=11)
 
-            def make():
-                m, d = su.sr_create_model_and_diffusion(**flags)
+            def make(half=mode):
+                m, d = su.sr_create_model_and_diffusion(**dict(flags, use_fp16=bool(half)))
                 m.load_state_dict(sd)
                 m.to(dev)
-                if mode:
+                if half:
                     m.convert_to_fp16()
                 return m.eval(), d
 
@@ -62,9 +62,10 @@ def _worker(rank, world, port, q):
             low, x_T, _ = synth_inputs(shape, 0)
             low, x_T = low.to(dev), x_T.to(dev)
             B, _, Z, H, W = shape
-            # (a) one evaluation
+            # (a) one evaluation: the sharded result against the single-GPU network in FP32 (16-bit cases: the north
+            # star's eps bound, with the attention toy network listed in tests/test_gpu_model.py at its own bound)
             t = torch.tensor([555.0] * B, device=dev)
-            want = single(x_T, t, low_res=low)
+            want = make(False)[0](x_T, t, low_res=low) if mode else single(x_T, t, low_res=low)
             bounds = slab.slab_bounds(Z, world)
             z0, z1 = bounds[rank], bounds[rank + 1]
             sharded.set_slab(z0, Z)

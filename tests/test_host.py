@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/ddpm3d.h but not exported"
     assert declared == set(N.SIGNATURES), "ctypes binding and header disagree"
-    assert N.lib().ddpm3d_abi_version() == 3
+    assert N.lib().ddpm3d_abi_version() == 4
 
 
 def test_struct_layouts_match_header():

@@ -1,6 +1,6 @@
 """CPU: tiling / Hann helpers (oracle pinned to the reference's functions, host mirror equal to the oracle)
 and the world_size-2 gloo tests of the N>1 host logic (rank-strided patches, gather with n % world != 0,
-ensemble partial gather)."""
+ensemble partial tree reduction)."""
 import os
 import sys
 
@@ -59,28 +59,51 @@ def _worker(rank, world, port, n_patches, q):
         got = vol.gather_patches(local, n_patches, device=torch.device("cpu"))
         ok = len(got) == n_patches and all(torch.equal(got[i], torch.full((2, 3, 4), float(i)) + torch.arange(4.0))
                                            for i in range(n_patches))
-        parts = ensemble.gather_partials(torch.full((3,), float(rank)), torch.full((3,), 10.0 + rank), rank + 1)
-        ok = ok and [c for _, _, c in parts] == list(range(1, world + 1))
-        ok = ok and all(float(m[0]) == r for r, (m, _, _) in enumerate(parts))
+
+        class Acc:  # CPU stand-in of ensemble.Welford (whose merge is a CUDA kernel): Chan's pairwise update
+            def __init__(self, r):
+                g = torch.Generator().manual_seed(100 + r)
+                self.x = torch.randn(r + 1, 5, generator=g, dtype=torch.float64)  # rank r holds r + 1 samples
+                self.count = r + 1
+                self.mean = self.x.mean(0)
+                self.m2 = ((self.x - self.mean) ** 2).sum(0)
+                self.device = torch.device("cpu")
+
+            def merge(self, mean_b, m2_b, nb):
+                n = self.count + nb
+                d = mean_b - self.mean
+                self.m2 = self.m2 + m2_b + d * d * (self.count * nb / n)
+                self.mean = self.mean + d * (nb / n)
+                self.count = n
+
+        acc = Acc(rank)
+        holds = ensemble.reduce_partials(acc)
+        ok = ok and holds == (rank == 0)
+        if rank == 0:  # the tree reduction equals the statistics of all samples pooled
+            allx = torch.cat([Acc(r).x for r in range(world)])
+            ok = ok and acc.count == allx.shape[0]
+            ok = ok and torch.allclose(acc.mean, allx.mean(0), atol=1e-12)
+            ok = ok and torch.allclose(acc.m2, ((allx - allx.mean(0)) ** 2).sum(0), atol=1e-10)
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_patches", [5, 4, 1])
-def test_gloo_world2_gather(n_patches):
-    """n % world != 0 must not deadlock (the reference's all_gather does)."""
+@pytest.mark.parametrize("n_patches,world", [(5, 2), (4, 2), (1, 2), (7, 3)])
+def test_gloo_gather_and_tree_reduce(n_patches, world):
+    """n % world != 0 must not deadlock (the reference's all_gather does); the ensemble's
+    Welford partials reduce to rank 0 along a binary tree (world 3: a rank without a partner in round 1)."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + n_patches + (os.getpid() % 200)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_patches, q)) for r in range(2)]
+    port = 29600 + n_patches + 10 * world + (os.getpid() % 200)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_patches, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    res = dict(q.get(timeout=10) for _ in range(2))
-    assert res == {0: True, 1: True}
+    res = dict(q.get(timeout=10) for _ in range(world))
+    assert res == {r: True for r in range(world)}
 
 
 def test_tiff_and_npz_roundtrip(tmp_path):
