@@ -540,8 +540,9 @@ struct Run {
     }
     a.splitk_scratch = ctx->splitk_buf;
     a.splitk_bytes = ctx->splitk_cap;
+    // algorithmic flops: the unit-weight K block of a folded identity skip is an addition, not part of the contraction
     double K = (double)a.taps * a.main.C;
-    for (int e = 0; e < a.n_extra; ++e) K += a.extra[e].C;
+    for (int e = 0; e < a.n_extra; ++e) K += a.extra_is_identity ? 0.0 : a.extra[e].C;
     const double flops = 2.0 * B * Z * a.Ho * a.Wo * (double)a.Cout * K;
     const bool tc = is_half_dt(a.dt) && ctx->conv_path != 1 && conv_tc_eligible(a);
     const bool stem = !tc && ctx->conv_path != 1 && conv_stem_eligible(a);
@@ -580,7 +581,13 @@ struct Run {
       r = gn_forward_chsum(g, s);
     } else if (zp) {  // z-slab sharding: statistics span all ranks (fp64 sums all-gathered, summed in rank order)
       r = have_cs ? gn_chsum_local(g, sums, s) : gn_stats_local(g, sums, s);
-      if (r == DDPM3D_OK) r = comm_allgather_f64(ctx->slab, sums, gathered, (size_t)B * 64, s);
+      if (r == DDPM3D_OK) {
+        prof_end();
+        prof_begin(11, (double)ctx->slab.world * B * 64 * sizeof(double));
+        r = comm_allgather_f64(ctx->slab, sums, gathered, (size_t)B * 64, s);
+        prof_end();
+        prof_begin(4, 0.0);
+      }
       if (r == DDPM3D_OK) {
         g.gathered = gathered;
         g.world = ctx->slab.world;
@@ -667,6 +674,7 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   } else if (!L.up && !L.down && ctx->fold_identity && is_half_dt(dt)) {
     c2.n_extra = 1;  // Identity skip as a unit-weight 1x1x1 source: no residual traffic in the epilogue
     c2.extra[0] = {src[0].p, src[0].C};
+    c2.extra_is_identity = 1;
   } else {
     c2.residual = src[0].p;
     c2.res_mode = L.down ? RES_POOL : (L.up ? RES_UP : RES_SAME);

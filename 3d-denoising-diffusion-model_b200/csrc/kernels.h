@@ -30,6 +30,7 @@ struct ConvArgs {
   int stride_hw = 1;          // Downsample(use_conv=True): (1,2,2)  (unet.py:129-133)
   ConvSrc extra[2];           // 1x1x1 sources appended along K (skip_connection folded in; K11 concat elision)
   int n_extra = 0;
+  int extra_is_identity = 0;  // the extra source is the block's identity skip folded in with unit weights (profiling only)
   const void* w = nullptr;    // [Cout][w_ld], first Ktot = taps*main.C + sum(extra.C) columns used; k = tap*C + ci
   int w_ld = 0;               // row pitch of w in elements (0 = Ktot)
   const float* bias = nullptr;  // [Cout] (already includes the folded skip bias)

@@ -87,8 +87,11 @@ def ensemble_sample(model, diffusion, low_res, seeds, clip_denoised=True, all_ra
     for k in dist_util.patch_indices(len(seeds)):
         torch.cuda.manual_seed_all(int(seeds[k]))
         noise = torch.randn(*shape, device=dev)
+        kw = dict(loop_kwargs)
+        if kw.get("rng") == "philox":  # device-resident loop: the per-step noise is drawn in-kernel from the sample's seed
+            kw["seed"] = int(seeds[k])
         acc.update(diffusion.p_sample_loop(model, shape, noise, clip_denoised=clip_denoised,
-                                           model_kwargs={"low_res": low_res}, **loop_kwargs))
+                                           model_kwargs={"low_res": low_res}, **kw))
     reduce_partials(acc)
     mean, var, n = acc.mean, acc.variance(), acc.count
     if all_ranks:

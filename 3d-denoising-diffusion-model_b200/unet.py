@@ -165,6 +165,7 @@ class UNetModel_noatt:
         self._ctx = None
         self._ctx_sig = None
         self._bound = None
+        self._slab = None
         self._options = {}
         # enumerate the state_dict contract from the native topology builder (works without a GPU)
         probe = _Ctx(self._config(N.FP32))
@@ -312,6 +313,7 @@ class UNetModel_noatt:
             self._ctx.close()
         self._ctx = None
         self._bound = None
+        self._slab = None  # the NCCL communicator lived in the context
 
     def _ensure_ctx(self):
         import torch

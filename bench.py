@@ -13,8 +13,12 @@ UNet (BASELINE.json configs[1]): one UNet evaluation + the posterior / noise upd
              every step, inside the timed region.
 * `roofline`: the dominant kernel class (the 3x3x3 implicit-GEMM convolution) from a profiled pass
              of the same step (CUDA events around every launch on the launching stream).
-* `cpu_baseline` / `--impl reference`: the CPU oracle (a port of the reference's PyTorch path; the
-             reference itself cannot travel to the GPU box) on a bounded z-slab of the same patch.
+* `cpu_baseline` / `--impl reference`: the reference's own CPU implementation (its unmodified modules staged under
+             oracle/_ref by `python -m oracle.build_ref`; the oracle's restatement where that is absent) on the host
+             cores: full 96^3 fp32 p_sample steps.
+* `library_bar`: the reference's own nn.Module in its use_fp16 flow (torch-eager + cuDNN) on the same GPU.
+* `c4` / `c5`: BASELINE configs 4 and 5 -- ONE 640x192x192 volume split into z-slabs over the N ranks (strong scaling;
+             with a sharded-vs-single-GPU parity check) and the 16-sample uncertainty ensemble.
 """
 from __future__ import annotations
 
@@ -36,6 +40,11 @@ import torch  # noqa: E402
 PATCH = (1, 1, 96, 96, 96)
 FLOPS_PER_EVAL = 19.68e12  # SURVEY.md section 6 (meta-device trace of the reference)
 PATCHES_PER_VOLUME = 18    # scripts/test.py:205-230 tiling of a (110,200,200) volume
+C2_CONFIG = {"workload": "C2: paper-default 3D UNet (128ch, 2 res blocks, mult 1-1-2-3-4), one 96x96x96 low-dose-conditioned "
+                         "patch per GPU, one DDPM reverse step (UNet eval + posterior update) per bench step"}
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch, from the committed ncu capture
+DOMINANT_LAUNCH_DRAM_BYTES = 227427584 + 183572480
+DOMINANT_LAUNCH_PROFILE = "profiles/r1k_conv_tc_ncu_full.txt"
 C2_FLAGS = dict(
     large_size=96, small_size=96, class_cond=False, learn_sigma=True, num_channels=128, num_res_blocks=2,
     num_heads=4, num_head_channels=64, num_heads_upsample=-1, attention_resolutions="1000", dropout=0.0,
@@ -114,140 +123,278 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline_sample(sd, threads, z_slab=16, repeats=1):
-    """The oracle (CPU port of the reference's fp32 PyTorch path) on a z-slab of the bench patch.
-    Returns (evals/s extrapolated to the full 96^3 patch, description)."""
-    from oracle import cases
-    from oracle.unet import unet_forward
-    torch.set_num_threads(threads)
-    flags = dict(C2_FLAGS, use_fp16=False)
-    cfg = cases.cfg_from_flags(flags)
-    g = torch.Generator().manual_seed(3)
-    shape = (1, 1, z_slab, PATCH[3], PATCH[4])
-    x = torch.randn(shape, generator=g)
-    low = torch.rand(shape, generator=g)
-    t = torch.tensor([500])
-    best = float("inf")
-    for _ in range(repeats):
+class CpuReference:
+    """The reference's CPU implementation of the path: sr_create_model_and_diffusion + SpacedDiffusion.p_sample of the
+    UNMODIFIED reference staged under oracle/_ref (kind "reference"), or -- where that directory is absent -- the
+    oracle's restatement (kind "port").  fp32, all host threads.  Weights: the same synthetic tensors as the GPU arm,
+    keyed by the oracle's param_specs (no native library is loaded on this path)."""
+
+    def __init__(self, threads):
+        from oracle import build_ref, cases
+        from oracle.unet import param_specs
+        torch.set_num_threads(threads)
+        self.threads = threads
+        flags = dict(C2_FLAGS, use_fp16=False)
+        self.cfg = cases.cfg_from_flags(flags)
+        self.sd = synth_weights(param_specs(self.cfg))
+        su = build_ref.load_ref()
+        self.t_top = 999
+        if su is not None:
+            self.kind = "reference"
+            self.model, self.diffusion = su.sr_create_model_and_diffusion(**flags)
+            self.model.load_state_dict(self.sd)
+            self.model.eval()
+        else:
+            self.kind = "port"
+            from oracle.schedule import make_tables
+            self.tabs = make_tables(steps=1000, learn_sigma=True, noise_schedule="linear", timestep_respacing="")
+
+    @torch.no_grad()
+    def step(self, x, low, i):
+        """One DDPM reverse step (UNet evaluation + posterior update) at step index i."""
+        t = torch.tensor([i] * x.shape[0])
+        if self.kind == "reference":
+            return self.diffusion.p_sample(self.model, x, t, clip_denoised=True, model_kwargs={"low_res": low})["sample"]
+        from oracle.sampler import model_timesteps, p_sample
+        from oracle.unet import unet_forward
+        mo = unet_forward(self.cfg, self.sd, x, model_timesteps(self.tabs, t), low)
+        return p_sample(self.tabs, mo, x, t, torch.randn_like(x), True)["sample"]
+
+    def timed_steps(self, n_warm, n_steps, budget_s):
+        """Times n_steps steps after n_warm untimed ones.  The step is the full 96^3 patch when (n_warm + n_steps) of
+        them fit `budget_s` on this host, otherwise a z-slab of it (the network never strides Z, cost is linear in Z)
+        with the time scaled to the full patch.  Returns (seconds per full-patch step, description)."""
+        g = torch.Generator().manual_seed(3)
+        probe_z = 8
+        x = torch.randn((1, 1, probe_z, PATCH[3], PATCH[4]), generator=g)
+        low = torch.rand(x.shape, generator=g)
+        self.step(x, low, self.t_top)  # thread pool / primitive caches
         t0 = time.perf_counter()
-        out = unet_forward(cfg, sd, x, t, low)
-        best = min(best, time.perf_counter() - t0)
-    assert torch.isfinite(out).all()
-    scale = PATCH[2] / z_slab
-    return 1.0 / (best * scale), (f"oracle fp32 UNet eval on a (1,1,{z_slab},96,96) z-slab of the 96^3 patch "
-                                  f"({best:.2f} s, x{scale:.0f} extrapolated to the full patch; the posterior "
-                                  f"update is <0.1% of a CPU step)")
+        self.step(x, low, self.t_top)
+        probe = time.perf_counter() - t0
+        pred_full = probe * PATCH[2] / probe_z
+        z = PATCH[2]
+        total = max(1, n_warm + n_steps)
+        if pred_full * total > budget_s:
+            z = int(max(probe_z, min(PATCH[2], (budget_s / (probe / probe_z * total)) // 8 * 8)))
+        x = torch.randn((1, 1, z, PATCH[3], PATCH[4]), generator=g)
+        low = torch.rand(x.shape, generator=g)
+        for k in range(n_warm):
+            self.step(x, low, self.t_top - k)
+        times = []
+        for k in range(n_steps):
+            t0 = time.perf_counter()
+            out = self.step(x, low, self.t_top - n_warm - k)
+            times.append(time.perf_counter() - t0)
+        assert torch.isfinite(out).all()
+        sec = sum(times) / len(times) * PATCH[2] / z
+        what = "the reference's own modules (oracle/_ref: sr_create_model_and_diffusion + SpacedDiffusion.p_sample)" \
+            if self.kind == "reference" else "the oracle's restatement of the reference"
+        desc = (f"{n_steps} DDPM step(s) (UNet eval + update, fp32, {self.threads} threads) of {what} on "
+                + ("the full (1,1,96,96,96) patch" if z == PATCH[2] else
+                   f"a (1,1,{z},96,96) z-slab of the patch, time x{PATCH[2] / z:.1f} (cost is linear in Z)")
+                + f": {sum(times) / len(times):.2f} s per step")
+        return sec, desc, z == PATCH[2]
 
 
 def run_reference(args, rank):
-    """--impl reference: the CPU implementation of the path on the host cores (oracle port)."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
     if rank != 0:
         return
-    from ddpm3d_b200.unet import _Ctx
-    from ddpm3d_b200 import script_util as su
     threads = os.cpu_count() or 1
-    model, _ = su.sr_create_model_and_diffusion(**dict(C2_FLAGS, use_fp16=False))
-    sd = synth_weights(model._specs)
-    del model
-    vals = []
-    desc = ""
-    z = 8 if threads < 32 else 16
-    for k in range(args.warmup + args.steps):
-        v, desc = cpu_baseline_sample(sd, threads, z_slab=z)
-        if k >= args.warmup:
-            vals.append(v)
-    v = sum(vals) / len(vals)
+    ref = CpuReference(threads)
+    sec, desc, full = ref.timed_steps(args.warmup, args.steps, budget_s=float(os.environ.get("DDPM3D_REF_BUDGET_S", "420")))
+    v = 1.0 / sec
     line = {
         "impl": "reference", "metric": "unet_evals_per_sec", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sec, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: paper-default 3D UNet, one 96^3 low-dose-conditioned patch, one DDPM step"},
-        "cpu_baseline": {"value": v, "unit": "evals/s", "cores": threads, "kind": "port", "sample": desc},
+        "config": dict(C2_CONFIG, parallelism=f"{threads} host threads (rank 0 only)", full_patch_per_step=full),
+        "cpu_baseline": {"value": v, "unit": "evals/s", "cores": threads, "kind": ref.kind, "sample": desc},
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "volumes_per_min": v * 60.0 / (PATCHES_PER_VOLUME * 1000),
+        # this arm is the reference's own code on the CPU: the repo's native library is never mapped into the process
+        "native_so_loaded": any("libddpm3d" in ln for ln in open("/proc/self/maps")),
     }
     print(json.dumps(line), flush=True)
 
 
-def run_c4(args, rank, world, dev):
-    """BASELINE.json config 4: one whole-body volume, Z split over the ranks (halo exchange + GroupNorm sums
-    over NCCL inside the library).  value = whole-volume UNet evals/s; scaling is strong."""
+def library_bar(dev, sd):
+    """What the reference itself would execute on this GPU: its own nn.Module in its use_fp16
+    flow -- PyTorch eager ops, cuDNN convolutions -- on the same 96^3 patch.  Reported, not a target."""
+    from oracle import build_ref
+    su = build_ref.load_ref()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(PATCH, generator=g).to(dev)
+    low = torch.rand(PATCH, generator=g).to(dev)
+    t = torch.tensor([500], device=dev)
+    if su is not None:
+        kind = "the reference's own nn.Module (oracle/_ref), use_fp16 flow: torch-eager fp16 + cuDNN"
+        model, _ = su.sr_create_model_and_diffusion(**C2_FLAGS)
+        model.load_state_dict(sd)
+        model.to(dev)
+        model.convert_to_fp16()
+        model.eval()
+        fn = lambda: model(x, t, low_res=low)  # noqa: E731
+    else:
+        kind = "oracle restatement of the reference's use_fp16 flow: torch-eager fp16 + cuDNN"
+        from oracle import cases
+        from oracle.unet import unet_forward
+        cfg = cases.cfg_from_flags(C2_FLAGS)
+        torso = ("input_blocks.", "middle_block.", "output_blocks.")
+        leaf = ("in_layers.2.", "out_layers.3.", "skip_connection.", ".op.", ".conv.", "qkv.", "proj_out.", "input_blocks.0.0.")
+        sdd = {k: v.to(dev, torch.float16 if (k.startswith(torso) and any(c in k for c in leaf)) else torch.float32)
+               for k, v in sd.items()}
+        fn = lambda: unet_forward(cfg, sdd, x, t, low, dtype=torch.float16)  # noqa: E731
+    bench_flag = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        with torch.no_grad():
+            for _ in range(2):
+                out = fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+    finally:
+        torch.backends.cudnn.benchmark = bench_flag
+    assert torch.isfinite(out.float()).all()
+    return {"ms_per_eval": e0.elapsed_time(e1) / 3, "kind": kind}
+
+
+def profile_breakdown(model, run, steps):
+    model.set_option("profile", 1)
+    run()
+    recs = model.profile_read()
+    model.set_option("profile", 0)
+    out = {}
+    for kind, t_ms, work in recs:
+        b = out.setdefault(kind, {"ms": 0.0, "work": 0.0, "launches": 0})
+        b["ms"] += t_ms / steps
+        b["work"] += work / steps
+        b["launches"] += 1.0 / steps
+    return out
+
+
+def slab_parity(model_bf16, sd, rank, world, dev):
+    """Sharded-vs-single check on a (1,1,16,96,96) volume of the shipped network: every rank evaluates its z-slab in
+    the bench's bf16 mode and in fp32 mode; rank 0 also evaluates the whole volume on one GPU in fp32.  Returns
+    max-rel / rms-rel of the gathered sharded eps against that single-GPU fp32 result (rank 0)."""
     import torch.distributed as dist
     from ddpm3d_b200 import script_util as su, slab
-    shape = (1, 1, 640, 192, 192)
-    if args.shape:
-        z, h, w = (int(v) for v in args.shape.split(","))
-        shape = (1, 1, z, h, w)
+    Z = max(16, 2 * world)
+    shape = (1, 1, Z, 96, 96)
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(shape, generator=g).to(dev)
+    low = torch.rand(shape, generator=g).to(dev)
+    t = torch.tensor([555.0], device=dev)
+    m32, _ = su.sr_create_model_and_diffusion(**dict(C2_FLAGS, use_fp16=False))
+    m32.load_state_dict(sd)
+    m32.to(dev).eval()
+    want = m32(x, t, low_res=low) if rank == 0 else None
+    bounds = slab.slab_bounds(Z, world)
+    z0, z1 = bounds[rank], bounds[rank + 1]
+    res = {"shape": list(shape)}
+    for name, m in (("bf16", model_bf16), ("fp32", m32)):
+        if world > 1:
+            if getattr(m, "_slab", None) is None:
+                m.enable_slab_sharding()
+            m.set_slab(z0, Z)
+        part = m(x[:, :, z0:z1].contiguous(), t, low_res=low[:, :, z0:z1].contiguous())
+        got = slab.gather_slabs(part, bounds) if world > 1 else part
+        if world > 1:
+            m.disable_slab_sharding()
+        if rank == 0:
+            d = (got - want).double()
+            res[f"parity_max_rel_{name}"] = float(d.abs().max() / want.abs().max())
+            res[f"parity_nrmse_{name}"] = float(d.pow(2).mean().sqrt() / want.double().pow(2).mean().sqrt())
+    del m32
+    torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+    return res
+
+
+def c4_leg(model, diffusion, sd, rank, world, dev, shape, steps=3, warm=2):
+    """BASELINE.json config 4: ONE whole-body volume, Z split over the ranks (1-plane halo per 3x3x3 conv, GroupNorm
+    fp64 sums all-gathered, both over NCCL inside the library).  Strong scaling: the same volume at every N."""
+    import torch.distributed as dist
+    from ddpm3d_b200 import slab
+    out = slab_parity(model, sd, rank, world, dev)
     Z = shape[2]
-    model, diffusion = su.sr_create_model_and_diffusion(**C2_FLAGS)
-    model.load_state_dict(synth_weights(model._specs))
-    model.to(dev)
-    model.convert_to_fp16()
-    model.eval()
-    for o in args.opt:
-        model.set_option(o.split("=")[0], int(o.split("=")[1]))
     bounds = slab.slab_bounds(Z, world)
     z0, z1 = bounds[rank], bounds[rank + 1]
     if world > 1:
-        model.enable_slab_sharding()
         model.set_slab(z0, Z)
     g = torch.Generator().manual_seed(1234)
     lshape = (1, 1, z1 - z0, shape[3], shape[4])
     low = torch.rand(lshape, generator=g).to(dev)
     x_T = torch.randn(lshape, generator=g).to(dev)
     kw = {"low_res": low}
-    K, Wm = args.steps, max(args.warmup, 3)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    model._sample_loop(diffusion, x_T, kw, None, 1, True, n_steps=Wm)
+    model._sample_loop(diffusion, x_T, kw, None, 1, True, n_steps=warm)
     barrier()
-    l0 = model.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(dev.index) as clocks:
-        barrier()
-        e0.record()
-        out = model._sample_loop(diffusion, x_T, kw, None, 1, True, n_steps=K)
-        e1.record()
-        barrier()
-    ms = e0.elapsed_time(e1)
-    launches = model.launch_count() - l0
-    assert torch.isfinite(out).all()
+    e0.record()
+    res = model._sample_loop(diffusion, x_T, kw, None, 1, True, n_steps=steps)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    assert torch.isfinite(res).all()
     if world > 1:
         tt = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt[0])
-    breakdown = {}
-    if rank == 0 or world > 1:  # the profiled pass contains collectives: every rank runs it
-        model.set_option("profile", 1)
-        model._sample_loop(diffusion, x_T, kw, None, 1, True, n_steps=1)
-        for kind, t_ms, work in model.profile_read():
-            b = breakdown.setdefault(kind, {"ms": 0.0, "work": 0.0, "launches": 0})
-            b["ms"] += t_ms
-            b["work"] += work
-            b["launches"] += 1
-        model.set_option("profile", 0)
-    if rank == 0:
-        vox = shape[2] * shape[3] * shape[4]
-        flops = FLOPS_PER_EVAL * vox / 96 ** 3
-        line = {
-            "metric": "unet_evals_per_sec", "value": K / (ms * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": K,
-            "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"C4: paper-default 3D UNet on ONE {shape[2]}x{shape[3]}x{shape[4]} volume, Z split into "
-                                   f"{world} slab(s); one DDPM reverse step per bench step",
-                       "parallelism": f"z-slabs x{world}: 1-plane halo per 3x3x3 conv (NCCL send/recv), GroupNorm fp64 sums "
-                                      "all-gathered"},
-            "tflops_total": flops * K / (ms * 1e-3) / 1e12, "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "kernel_breakdown_ms_per_step_rank0": breakdown,
-        }
-        print(json.dumps(line), flush=True)
+    # the profiled pass contains collectives: every rank runs it; rank 0's breakdown is reported
+    bd = profile_breakdown(model, lambda: model._sample_loop(diffusion, x_T, kw, None, 1, True, n_steps=1), 1)
+    if world > 1:
+        model.disable_slab_sharding()
+    del low, x_T, res
+    torch.cuda.empty_cache()
+    vox = shape[2] * shape[3] * shape[4]
+    out.update({
+        "volume": list(shape[2:]), "ms_per_step": ms, "evals_per_s": 1000.0 / ms,
+        "tflops_total": FLOPS_PER_EVAL * vox / 96 ** 3 / (ms * 1e-3) / 1e12,
+        "halo_ms": bd.get("halo_exchange", {}).get("ms", 0.0), "gn_allgather_ms": bd.get("gn_allgather", {}).get("ms", 0.0),
+        "halo_launches": bd.get("halo_exchange", {}).get("launches", 0.0),
+        "comm_note": "halo / all-gather times are from the eager profiled pass (CUDA events around every launch)",
+        "steps": steps, "warmup": warm, "scaling": "strong"})
+    return out
+
+
+def c5_leg(model, sd, rank, world, dev, samples=16, respacing="50"):
+    """BASELINE.json config 5: uncertainty-map ensemble -- `samples` stochastic samples of one 96^3 patch, seeds
+    rank-strided (no communication while sampling), voxel-wise Welford mean / variance on the device, tree-reduced."""
+    import torch.distributed as dist
+    from ddpm3d_b200 import ensemble, script_util as su
+    _, diffusion = su.sr_create_model_and_diffusion(**dict(C2_FLAGS, timestep_respacing=respacing))
+    g = torch.Generator().manual_seed(1234)
+    low = torch.rand(PATCH, generator=g).to(dev)
+    seeds = list(range(10, 10 + samples))
+    ensemble.ensemble_sample(model, diffusion, low, seeds[:world], rng="philox", all_ranks=False)  # warm-up (graph capture)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    mean, var, n = ensemble.ensemble_sample(model, diffusion, low, seeds, rng="philox", all_ranks=False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sec = time.perf_counter() - t0
+    out = {"seconds": sec, "samples": samples, "steps": diffusion.num_timesteps,
+           "evals_per_s": samples * diffusion.num_timesteps / sec}
+    if rank == 0:
+        assert n == samples and torch.isfinite(mean).all() and torch.isfinite(var).all()
+        out["mean_voxel_std"] = float(var.clamp_min(0).sqrt().mean())
+    return out
 
 
 def main():
@@ -258,11 +405,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--conv-path", type=int, default=0, help="0 auto, 1 force SIMT, 2 force tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra legs of the JSON line: library_bar, c4 (z-slab volume) and c5 (ensemble)")
+    ap.add_argument("--half", default="bf16", choices=["bf16", "fp16", "bf16_strict"], help="16-bit mode of the torso")
     ap.add_argument("--shape", default="", help="override Z,H,W (debug only; invalidates the metric)")
+    ap.add_argument("--c4-shape", default="640,192,192", help="Z,H,W of the whole-body volume of the c4 leg")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (ddpm3d_set_option), repeatable")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
-                    help="c2 (default, the driver's metric): one 96^3 patch per GPU; c4: ONE 640x192x192 volume "
-                         "sharded as z-slabs over the GPUs (strong scaling; extra measurement, BASELINE config 4)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -282,8 +430,6 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    if args.workload == "c4":
-        return run_c4(args, rank, world, dev)
     shape = PATCH
     if args.shape:
         z, h, w = (int(v) for v in args.shape.split(","))
@@ -294,6 +440,7 @@ def main():
     sd = synth_weights(model._specs)
     model.load_state_dict(sd)
     model.to(dev)
+    model.set_half_dtype(args.half)
     model.convert_to_fp16()
     model.eval()
     if args.conv_path:
@@ -367,15 +514,7 @@ def main():
     roofline = None
     breakdown = {}
     if rank == 0:
-        model.set_option("profile", 1)
-        model._sample_loop(diffusion, x_T, kw, None, 1, True, n_steps=2)
-        recs = model.profile_read()
-        model.set_option("profile", 0)
-        for kind, t_ms, work in recs:
-            b = breakdown.setdefault(kind, {"ms": 0.0, "work": 0.0, "launches": 0})
-            b["ms"] += t_ms / 2
-            b["work"] += work / 2
-            b["launches"] += 0.5
+        breakdown = profile_breakdown(model, lambda: model._sample_loop(diffusion, x_T, kw, None, 1, True, n_steps=2), 2)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -386,14 +525,14 @@ def main():
         dom = "conv_tcgen05" if breakdown.get("conv_tcgen05", {}).get("ms", 0) > 0 else "conv_simt"
         d = breakdown[dom]
         achieved = d["work"] / (d["ms"] * 1e-3) / 1e12
-        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (96^3 128->128 convolution, 782.8 GFLOP,
-        # algorithmic 226 MB in + 226 MB out + 0.9 MB weights) from the ncu --set full capture in
-        # profiles/r1k_conv_tc_ncu_full.txt; only meaningful for the default shape
-        traffic = 227427584 + 183572480 if (dom == "conv_tcgen05" and shape == PATCH) else None
         roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": traffic,
-                    "traffic_note": "DRAM bytes of the dominant launch (96^3 128->128 conv) from profiles/r1k_conv_tc_ncu_full.txt; "
-                                    "achieved/frac are over all 70 conv launches of the step",
+                    "frac": achieved / peak_tf,
+                    "traffic": DOMINANT_LAUNCH_DRAM_BYTES if (dom == "conv_tcgen05" and shape == PATCH) else None,
+                    "traffic_note": "not measured in this run: DRAM bytes (read + write) of the dominant launch (96^3 128->128 "
+                                    "3x3x3 conv, 782.8 GFLOP, algorithmic 453 MB) from the ncu --set full capture in "
+                                    + DOMINANT_LAUNCH_PROFILE + "; achieved / frac are over all conv launches of the step",
+                    "work_note": "algorithmic flops 2*M*Cout*(27*Cin + Cskip) of every tcgen05 conv launch; the unit-weight K "
+                                 "block of folded identity skips is NOT counted",
                     "peak_source": which,
                     "share_of_step": d["ms"] / sum(b["ms"] for b in breakdown.values()),
                     "launches_per_step": d["launches"]}
@@ -405,13 +544,26 @@ def main():
                 b["gbps"] = b["work"] / (b["ms"] * 1e-3) / 1e9
                 b["frac_of_hbm"] = b["gbps"] / hbm
 
+    # ---- extra legs: library bar (rank 0), c4 z-slab volume and c5 ensemble (all ranks) -----------
+    extras = {}
+    if not args.no_extras and shape == PATCH:
+        if rank == 0:
+            extras["library_bar"] = library_bar(dev, sd)
+            extras["library_bar"]["native_ms_per_eval"] = ms / K
+            extras["library_bar"]["speedup"] = extras["library_bar"]["ms_per_eval"] / (ms / K)
+            torch.cuda.empty_cache()
+        barrier()
+        z4, h4, w4 = (int(v) for v in args.c4_shape.split(","))
+        extras["c4"] = c4_leg(model, diffusion, sd, rank, world, dev, (1, 1, z4, h4, w4))
+        extras["c5"] = c5_leg(model, sd, rank, world, dev)
+
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sd32 = {k: v.float() for k, v in sd.items()}
-        v, desc = cpu_baseline_sample(sd32, threads, z_slab=8 if threads < 32 else 16)
-        cpu = {"value": v, "unit": "evals/s", "cores": threads, "kind": "port", "sample": desc}
+        ref = CpuReference(threads)
+        sec, desc, _ = ref.timed_steps(0, 1, budget_s=30.0)
+        cpu = {"value": 1.0 / sec, "unit": "evals/s", "cores": threads, "kind": ref.kind, "sample": desc}
 
     if rank == 0:
         n = world
@@ -420,22 +572,27 @@ def main():
         nbytes = 4 * shape[2] * shape[3] * shape[4]
         line = {
             "metric": "unet_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": n, "steps": K, "warmup": Wm,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic",
-            "config": {"workload": "C2: paper-default 3D UNet (128ch, 2 res blocks, mult 1-1-2-3-4), one "
-                                   f"{shape[2]}x{shape[3]}x{shape[4]} low-dose-conditioned patch per GPU, one DDPM reverse step "
-                                   "(UNet eval + posterior update) per bench step",
-                       "l2": "per-step working set (>1 GB of activations + 414 MB of weights) exceeds the 126 MB L2",
-                       "weights": "random-init, all tensors non-zero", "parallelism": f"dp{n} (independent patches)"},
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16": "bf16", "fp16": "fp16", "bf16_strict": "bf16"}[args.half], "data": "synthetic",
+            "config": dict(C2_CONFIG,
+                           l2="per-step working set (>1 GB of activations + 414 MB of weights) exceeds the 126 MB L2",
+                           weights="random-init, all tensors non-zero", parallelism=f"dp{n} (independent patches)",
+                           storage="bf16 tensor-core operands (weights, GroupNorm outputs); block inputs / outputs fp16; "
+                                   "GroupNorm statistics, embeddings, head and sampler update fp32"
+                           if args.half == "bf16" else args.half),
             "volumes_per_min": value * 60.0 / (PATCHES_PER_VOLUME * 1000),
             "tflops_per_gpu": flops_per_eval * K / (ms * 1e-3) / 1e12,
-            "e2e": {"value": e2e_v, "unit": "evals/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes},
+            "e2e": {"value": e2e_v, "unit": "evals/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes,
+                    "note": "diffusion.p_sample per step; x_t and low_res are uploaded from pinned host memory and the "
+                            "sample is read back every step; the same host x_T is uploaded each step, so step i+1's "
+                            "upload may overlap step i's compute (throughput, not latency)"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": roofline,
             "cpu_baseline": cpu,
             "kernel_breakdown_ms_per_step": breakdown,
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
