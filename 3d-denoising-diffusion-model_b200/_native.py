@@ -72,6 +72,7 @@ SIGNATURES = {
     "ddpm3d_k_conv3d": (_I, [_I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "ddpm3d_k_probe_rowshift": (_I, [_P, _I, _P, _I, _I, _P, _P]),
     "ddpm3d_k_groupnorm": (_I, [_I, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "ddpm3d_k_conv3d_gn": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ddpm3d_k_timestep_embedding": (_I, [_P, _P, _P, _I, _I, _P]),
     "ddpm3d_k_attention": (_I, [_I, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ddpm3d_k_attention_window": (_I, [_I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

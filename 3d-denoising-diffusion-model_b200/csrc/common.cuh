@@ -166,14 +166,26 @@ template <> struct Vec<f16> {
   }
 };
 
-// accurate expf: the GN/SiLU kernels are HBM-bound, the extra ALU is hidden
+// accurate expf + IEEE division: fp32 outputs (fp32 mode, the head's input)
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
-// 16-bit outputs: ex2.approx + fast division (<= 4 ulp fp32, far below the 2^-9 / 2^-12 output rounding).
-// Two SFU ops per element: at 16 SFU lanes/clk/SM this caps the GroupNorm apply pass near 4.5 TB/s under the
-// power-capped clock.  The one-SFU form h + h*tanh.approx(h), h = x/2, was measured 8 % faster on that pass but its
-// 2^-11 error is a BIAS (same sign for all positive activations) that the next convolution sums coherently: eps
-// max-rel of the shipped network went 9.4e-3 -> 1.08e-2, across the 1e-2 line, so it is not used.
-__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kNegLog2e = -1.4426950408889634f;
+// 16-bit outputs: v * rcp(1 + ex2(-v log2 e)) with the two raw SFU instructions (<= 3 ulp fp32, far below the 2^-9 /
+// 2^-12 output rounding; unbiased): FMUL + MUFU + FADD + MUFU + FMUL.  (__expf / __fdividef compile to the same two
+// MUFUs plus a range check of three more instructions per element, which made the GroupNorm apply pass issue-bound.)
+// The one-SFU form h + h*tanh.approx(h), h = v/2, was measured 8 % faster on that pass but its 2^-11 error is a BIAS
+// (same sign for all positive activations) that the next convolution sums coherently, so it is not used.
+__device__ __forceinline__ float silu_fast2(float v, float v2) { return v * rcp_approx(1.0f + ex2_approx(v2)); }
+__device__ __forceinline__ float silu_fast(float v) { return silu_fast2(v, v * kNegLog2e); }
 template <typename T> __device__ __forceinline__ float silu_t(float v) { return sizeof(T) == 2 ? silu_fast(v) : silu_f(v); }
 
 }  // namespace ddpm3d

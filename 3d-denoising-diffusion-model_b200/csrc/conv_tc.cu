@@ -45,6 +45,7 @@ struct TcParams {
   int nk;            // total k-steps
   int taps;          // 27 or 1
   int zoff;          // halo planes in front of the main source (z-slab sharding)
+  int stride;        // (1, s, s) stride of the main source (Downsample conv, unet.py:129-133); extra sources have none
   int bw, bh, bz;    // brick (one 128-row MMA tile)
   int pw, ph, pz;    // offset of the second brick of a CTA tile (MT == 2): exactly one is non-zero
   int nWt, nHt, nZt, nNt;  // CTA tiles per dimension (a CTA tile = MT bricks)
@@ -207,9 +208,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (e < p.chunks[1]) { map = &mapA1; c0 = e * BK; }
             else { map = &mapA2; c0 = (e - p.chunks[1]) * BK; }
           }
+          const int st = kk < p.n_main_steps ? p.stride : 1;  // input voxel = stride * output voxel + tap offset
 #pragma unroll
           for (int j = 0; j < MT; ++j)
-            tma_load_5d(a_dst + j * A_BYTES, map, full_bar(stage), c0, w0 + j * p.pw + dw, h0 + j * p.ph + dh,
+            tma_load_5d(a_dst + j * A_BYTES, map, full_bar(stage), c0, (w0 + j * p.pw) * st + dw, (h0 + j * p.ph) * st + dh,
                         z0 + j * p.pz + dz, b);
           if (CL == 1) {
             tma_load_2d(b_dst, &mapW, full_bar(stage), kk * BK, n0);
@@ -321,12 +323,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
           continue;
         }
-        float v[32];
+        float v[32], bv[32];
         if (valid) {
           const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b4 = __ldg(bp + j);
+            bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
             v[4 * j] = __uint_as_float(r[4 * j]) + b4.x;
             v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
             v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
@@ -361,15 +364,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          for (int j = 0; j < 32; ++j) { v[j] = 0.f; bv[j] = 0.f; }
         }
         if (p.chsum) {
           // column sums over the warp's 32 rows through a padded smem transpose (conflict-free both ways):
-          // lane = row writes its 32 values, lane = channel reads its column and adds in row order
+          // lane = row writes its 32 values, lane = channel reads its column and adds in row order.
+          // The sums are taken over (x - bias) (see the strip kernel's epilogue)
           float* tr = cs_tr + sub * (32 * 33);
           __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j];
+          for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j] - bv[j];
           __syncwarp();
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
@@ -635,9 +639,12 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          x[j] = ((vmask >> j) & 1u) ? __uint_as_float(r[j]) + bias_co : 0.f;
-          ts += x[j];
-          tq = fmaf(x[j], x[j], tq);
+          // channel sums are taken over (x - bias) = the raw accumulator: a large bias (|mean| >> std) does not cancel
+          // in the fp32 sums; the GroupNorm finalize folds the bias back in fp64
+          const float a = ((vmask >> j) & 1u) ? __uint_as_float(r[j]) : 0.f;
+          x[j] = ((vmask >> j) & 1u) ? a + bias_co : 0.f;
+          ts += a;
+          tq = fmaf(a, a, tq);
         }
         float v[32];
 #pragma unroll
@@ -1110,7 +1117,8 @@ size_t conv_tc_scratch_bytes(const ConvArgs& a0) {
 }
 
 bool conv_tc_eligible(const ConvArgs& a) {
-  if (!is_half_dt(a.dt) || !is_half_dt(a.io_dt()) || a.out_planar_f32 || a.stride_hw != 1) return false;
+  if (!is_half_dt(a.dt) || !is_half_dt(a.io_dt()) || a.out_planar_f32) return false;
+  if (a.stride_hw != 1 && !(a.stride_hw == 2 && a.taps == 27 && a.in_zpad == 0)) return false;
   if (a.dt == DDPM3D_FP16 && a.io_dt() != DDPM3D_FP16) return false;  // built: bf16/bf16, bf16/fp16, fp16/fp16
   if (a.taps != 27 && a.taps != 1) return false;
   if (a.main.C % BK != 0 || a.Cout % 64 != 0) return false;
@@ -1142,6 +1150,7 @@ int conv_tc(ConvArgs& a, cudaStream_t s) {
   p.chunks[0] = a.main.C / BK;
   p.taps = a.taps;
   p.zoff = a.in_zpad;
+  p.stride = a.stride_hw;
   p.n_main_steps = a.taps * p.chunks[0];
   p.nk = p.n_main_steps;
   int Ktot = a.taps * a.main.C;
@@ -1176,7 +1185,8 @@ int conv_tc(ConvArgs& a, cudaStream_t s) {
 
   const CUtensorMapDataType tdt = tmap_dtype(a.dt), tdt_io = tmap_dtype(a.io_dt());
   CUtensorMap maps[3];
-  DD_TRY(make_act_map(&maps[0], tdt, a.main.ptr, a.B, a.Z + 2 * a.in_zpad, a.Ho, a.Wo, a.main.C, p.bw, p.bh, p.bz));
+  DD_TRY(make_act_map(&maps[0], tdt, a.main.ptr, a.B, a.Z + 2 * a.in_zpad, a.Ho * a.stride_hw, a.Wo * a.stride_hw, a.main.C, p.bw,
+                      p.bh, p.bz, a.stride_hw));
   maps[1] = maps[0];
   maps[2] = maps[0];
   for (int e = 0; e < a.n_extra; ++e)

@@ -81,13 +81,18 @@ int gn_chunks(int64_t rows) {
 }
 
 // thread -> (row lane r, channel vector v); every thread keeps its channel vector for the whole kernel,
-// so a warp always touches whole rows (>= 64 contiguous bytes) and no index arithmetic sits in the loop
+// so a warp always touches whole rows (>= 64 contiguous bytes) and no index arithmetic sits in the loop.
+// Cancellation-safe: a thread accumulates sum(x - p) and sum((x - p)^2) in fp32 around a per-thread, per-channel pivot
+// p (the first value it reads), so the running sums stay O(std) however large |mean| / std is; the pivot is folded back
+// in fp64 (sum x = s + n p, sum x^2 = q + 2 p s + n p^2) and everything downstream (smem reduction, per-chunk partials,
+// finalize) is fp64.  GroupNorm of a tensor with mean / std = 1000 is as accurate as with mean 0
+// (tests/test_gpu_kernels.py::test_groupnorm_large_mean).
 template <typename T>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int C1,
                                                        int rows, int n_chunks, const float* __restrict__ pre_add,
-                                                       int64_t pre_stride, float* __restrict__ partials) {
+                                                       int64_t pre_stride, double* __restrict__ partials) {
   constexpr int N = Vec<T>::N;
-  extern __shared__ float sm[];  // [rpi][Ctot][2]
+  extern __shared__ double smd[];  // [rpi][Ctot][2]
   const int Ctot = C0 + C1;
   const int nvec0 = C0 / N, nvec = Ctot / N;
   const int rpi = blockDim.x / nvec;
@@ -107,14 +112,25 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ s0,
     for (int i = 0; i < N; ++i) add[i] = pre_add[(int64_t)b * pre_stride + v * N + i];
   }
 
-  float s[N], q[N];
+  float s[N], q[N], piv[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  for (int i = 0; i < N; ++i) { s[i] = 0.f; q[i] = 0.f; piv[i] = 0.f; }
+  int n = 0;
   // Row blocks of U*rpi rows are dealt round-robin to the chunks, so at any moment the whole grid streams one
   // narrow window of the tensor (DRAM page / TLB locality on multi-GB tensors); each chunk still sums its rows
   // in a fixed order.
   constexpr int U = 8;  // independent 16-byte loads in flight per thread
   const int RB = U * rpi;
+  {
+    const int row0 = chunk * RB + r;  // the first row this thread will read (if any): its values are the pivots
+    if (row0 < rows) {
+      Vec<T> a;
+      a.load(base + (int64_t)row0 * Csrc);
+      a.unpack(piv);
+#pragma unroll
+      for (int i = 0; i < N; ++i) piv[i] += add[i];
+    }
+  }
   for (int rb0 = chunk * RB; rb0 < rows; rb0 += n_chunks * RB) {
     const int row = rb0 + r;
     if (rb0 + RB <= rows) {
@@ -126,8 +142,9 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ s0,
         float f[N];
         a[u].unpack(f);
 #pragma unroll
-        for (int i = 0; i < N; ++i) { const float x = f[i] + add[i]; s[i] += x; q[i] = fmaf(x, x, q[i]); }
+        for (int i = 0; i < N; ++i) { const float x = (f[i] + add[i]) - piv[i]; s[i] += x; q[i] = fmaf(x, x, q[i]); }
       }
+      n += U;
     } else {
       for (int rr = row; rr < rows; rr += rpi) {
         Vec<T> a;
@@ -135,27 +152,32 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ s0,
         float f[N];
         a.unpack(f);
 #pragma unroll
-        for (int i = 0; i < N; ++i) { const float x = f[i] + add[i]; s[i] += x; q[i] = fmaf(x, x, q[i]); }
+        for (int i = 0; i < N; ++i) { const float x = (f[i] + add[i]) - piv[i]; s[i] += x; q[i] = fmaf(x, x, q[i]); }
+        ++n;
       }
     }
   }
-  float* mine = sm + ((int64_t)r * Ctot + v * N) * 2;
+  double* mine = smd + ((int64_t)r * Ctot + v * N) * 2;
 #pragma unroll
-  for (int i = 0; i < N; ++i) { mine[2 * i] = s[i]; mine[2 * i + 1] = q[i]; }
+  for (int i = 0; i < N; ++i) {
+    const double p = (double)piv[i], sd = (double)s[i];
+    mine[2 * i] = sd + (double)n * p;
+    mine[2 * i + 1] = (double)q[i] + 2.0 * p * sd + (double)n * p * p;
+  }
   __syncthreads();
   // group g sums its channels over the rpi row-lanes in a fixed order (deterministic)
   const int gpc = Ctot / 32;
   if (threadIdx.x < 64) {
     const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
-    float acc = 0.f;
+    double acc = 0.0;
     for (int rr = 0; rr < rpi; ++rr)
-      for (int c = g * gpc; c < (g + 1) * gpc; ++c) acc += sm[((int64_t)rr * Ctot + c) * 2 + which];
+      for (int c = g * gpc; c < (g + 1) * gpc; ++c) acc += smd[((int64_t)rr * Ctot + c) * 2 + which];
     partials[(((int64_t)b * 32 + g) * 2 + which) * n_chunks + chunk] = acc;
   }
 }
 
 // partials: [B][32 groups][2][n_chunks]
-__global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restrict__ partials, int n_chunks, int Ctot,
+__global__ void __launch_bounds__(1024) gn_finalize_kernel(const double* __restrict__ partials, int n_chunks, int Ctot,
                                                            double inv_count, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, const float* __restrict__ film,
                                                            int64_t film_stride, const float* __restrict__ pre_add,
@@ -163,12 +185,12 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restri
   __shared__ float s_mean[32], s_rstd[32];
   const int b = blockIdx.x;
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 1024 threads: one warp per group
-  const float* ps = partials + (((int64_t)b * 32 + g) * 2) * n_chunks;
-  const float* pq = ps + n_chunks;
+  const double* ps = partials + (((int64_t)b * 32 + g) * 2) * n_chunks;
+  const double* pq = ps + n_chunks;
   double s = 0.0, q = 0.0;
   for (int c = lane; c < n_chunks; c += 32) {  // coalesced; fixed order -> deterministic
-    s += (double)ps[c];
-    q += (double)pq[c];
+    s += ps[c];
+    q += pq[c];
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -203,16 +225,16 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restri
 }
 
 // z-slab sharding: this rank's fp64 sums [B][32][2] from its partials (fixed order)
-__global__ void __launch_bounds__(1024) gn_reduce_local_kernel(const float* __restrict__ partials, int n_chunks,
+__global__ void __launch_bounds__(1024) gn_reduce_local_kernel(const double* __restrict__ partials, int n_chunks,
                                                                double* __restrict__ sums) {
   const int b = blockIdx.x;
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* ps = partials + (((int64_t)b * 32 + g) * 2) * n_chunks;
-  const float* pq = ps + n_chunks;
+  const double* ps = partials + (((int64_t)b * 32 + g) * 2) * n_chunks;
+  const double* pq = ps + n_chunks;
   double s = 0.0, q = 0.0;
   for (int c = lane; c < n_chunks; c += 32) {
-    s += (double)ps[c];
-    q += (double)pq[c];
+    s += ps[c];
+    q += pq[c];
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -267,23 +289,27 @@ __global__ void __launch_bounds__(1024) gn_finalize_multi_kernel(const double* _
   }
 }
 
-// finalize from per-CTA channel sums written by the convolution epilogues: chsum_s[B][P][C_s][2].
-// grid (32 groups, B), 128 threads; fixed reduction order -> deterministic.
-__global__ void __launch_bounds__(128) gn_finalize_chsum_kernel(const float* __restrict__ cs0, const float* __restrict__ cs1,
-                                                                int C0, int C1, int P, double inv_count,
-                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                const float* __restrict__ film, int64_t film_stride,
-                                                                float* __restrict__ ab) {
-  __shared__ double sh[2][128];
-  const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+// Group sums [sum x, sum x^2] of group g of batch element b from the per-CTA channel sums written by the convolution
+// epilogues: cs_s[B][P][C_s][2] hold sums of (x - bias_s[c]) and its square (P = one slot per CTA); the bias is folded
+// back in fp64: sum x = D1 + n b, sum x^2 = D2 + 2 b D1 + n b^2 with n = voxels per batch element.  128 threads, fixed
+// reduction order -> deterministic.  Result in sh[0][0], sh[1][0] (valid for every thread after the call).
+__device__ __forceinline__ void chsum_group_sums(const float* __restrict__ cs0, const float* __restrict__ cs1,
+                                                 const float* __restrict__ bias0, const float* __restrict__ bias1, int C0,
+                                                 int C1, int P, double n_vox, int g, int b, double (*sh)[128]) {
+  const int tid = threadIdx.x;
   const int Ctot = C0 + C1, gpc = Ctot / 32;
   const int n = P * gpc;  // (slot, channel-in-group) pairs of this group
   double s = 0.0, q = 0.0;
   for (int i = tid; i < n; i += 128) {
     const int slot = i / gpc, c = g * gpc + i % gpc;
-    const float* src = c < C0 ? cs0 + (((int64_t)b * P + slot) * C0 + c) * 2 : cs1 + (((int64_t)b * P + slot) * C1 + (c - C0)) * 2;
-    s += (double)src[0];
-    q += (double)src[1];
+    const bool first = c < C0;
+    const float* src = first ? cs0 + (((int64_t)b * P + slot) * C0 + c) * 2 : cs1 + (((int64_t)b * P + slot) * C1 + (c - C0)) * 2;
+    const float* bias = first ? bias0 : bias1;
+    const double bc = bias ? (double)bias[first ? c : c - C0] : 0.0;
+    const double d1 = (double)src[0], d2 = (double)src[1];
+    s += d1;
+    q += d2 + 2.0 * bc * d1;
+    if (slot == 0) { s += n_vox * bc; q += n_vox * bc * bc; }
   }
   sh[0][tid] = s;
   sh[1][tid] = q;
@@ -292,6 +318,19 @@ __global__ void __launch_bounds__(128) gn_finalize_chsum_kernel(const float* __r
     if (tid < o) { sh[0][tid] += sh[0][tid + o]; sh[1][tid] += sh[1][tid + o]; }
     __syncthreads();
   }
+}
+
+// finalize from the conv epilogues' channel sums.  grid (32 groups, B), 128 threads.
+__global__ void __launch_bounds__(128) gn_finalize_chsum_kernel(const float* __restrict__ cs0, const float* __restrict__ cs1,
+                                                                const float* __restrict__ bias0, const float* __restrict__ bias1,
+                                                                int C0, int C1, int P, double n_vox, double inv_count,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                const float* __restrict__ film, int64_t film_stride,
+                                                                float* __restrict__ ab) {
+  __shared__ double sh[2][128];
+  const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int Ctot = C0 + C1, gpc = Ctot / 32;
+  chsum_group_sums(cs0, cs1, bias0, bias1, C0, C1, P, n_vox, g, b, sh);
   const double mean = sh[0][0] * inv_count;
   double var = sh[1][0] * inv_count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -326,11 +365,14 @@ __device__ __forceinline__ void gn_put(TO* dst, const float* y) {
 
 // grid (blocks, B); thread -> (row lane, channel vector); the per-(b, c) affine lives in registers.
 // Iteration space: output rows for NONE / POOL, input rows for UP.
+// The loads of row block i+1 are issued before block i is computed and stored (register double buffer): without it
+// all warps of an SM moved through their load / compute / store phases together and the pass reached 4.3 TB/s.
 template <typename T, typename TO, int MODE, bool SILU>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int C1, int Z,
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int C1, int Z,
                                                        int H, int W, int rows_per_block, const float* __restrict__ ab,
                                                        TO* __restrict__ out, int out_zpad) {
   constexpr int N = Vec<T>::N;
+  constexpr bool FAST = SILU && sizeof(TO) == 2;  // two-MUFU SiLU with a pre-scaled second affine
   const int Ctot = C0 + C1;
   const int nvec0 = C0 / N, nvec = Ctot / N;
   const int rpi = blockDim.x / nvec;
@@ -357,82 +399,98 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0,
       Bv[k] = b4.x; Bv[k + 1] = b4.y; Bv[k + 2] = b4.z; Bv[k + 3] = b4.w;
     }
   }
+  auto act = [&](const float* f, float* y) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float t = fmaf(f[k], A[k], Bv[k]);
+      if (FAST) y[k] = silu_fast(t);
+      else y[k] = SILU ? silu_f(t) : t;
+    }
+  };
   // row blocks are dealt round-robin to the CTAs (see gn_stats_kernel)
   if (MODE == RS_NONE) {
     constexpr int U = 4;
     const int RB = U * rpi;
-    for (int rb0 = blockIdx.x * RB; rb0 < rows_it; rb0 += gridDim.x * RB) {
+    const int step = gridDim.x * RB;
+    int rb0 = blockIdx.x * RB;
+    Vec<T> cur[U], nxt[U];
+    if (rb0 + RB <= rows_it) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) cur[u].load(base + (int64_t)(rb0 + r + u * rpi) * Csrc);
+    }
+    for (; rb0 < rows_it; rb0 += step) {
       const int row = rb0 + r;
       if (rb0 + RB <= rows_it) {
-        Vec<T> a[U];
+        const int nb0 = rb0 + step;
+        if (nb0 + RB <= rows_it) {  // prefetch the next full block
 #pragma unroll
-        for (int u = 0; u < U; ++u) a[u].load(base + (int64_t)(row + u * rpi) * Csrc);
+          for (int u = 0; u < U; ++u) nxt[u].load(base + (int64_t)(nb0 + r + u * rpi) * Csrc);
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           float f[N], y[N];
-          a[u].unpack(f);
-#pragma unroll
-          for (int k = 0; k < N; ++k) {
-            const float t = fmaf(f[k], A[k], Bv[k]);
-            y[k] = SILU ? silu_t<TO>(t) : t;
-          }
+          cur[u].unpack(f);
+          act(f, y);
           gn_put<T, TO, N>(obase + (int64_t)(row + u * rpi) * Ctot, y);
         }
-      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+      } else {  // ragged last block
         for (int rr = row; rr < rows_it; rr += rpi) {
           Vec<T> a;
           a.load(base + (int64_t)rr * Csrc);
           float f[N], y[N];
           a.unpack(f);
-#pragma unroll
-          for (int k = 0; k < N; ++k) {
-            const float t = fmaf(f[k], A[k], Bv[k]);
-            y[k] = SILU ? silu_t<TO>(t) : t;
-          }
+          act(f, y);
           gn_put<T, TO, N>(obase + (int64_t)rr * Ctot, y);
         }
       }
     }
   } else if (MODE == RS_POOL) {
-    for (int row = blockIdx.x * rpi + r; row < rows_it; row += gridDim.x * rpi) {
+    auto load4 = [&](int row, Vec<T>* a) {
       const int wo = row % Wo;
       const int t1 = row / Wo;
       const int ho = t1 % Ho;
       const int z = t1 / Ho;
       const int in_row = (z * H + 2 * ho) * W + 2 * wo;
-      Vec<T> a[4];
       a[0].load(base + (int64_t)in_row * Csrc);
       a[1].load(base + (int64_t)(in_row + 1) * Csrc);
       a[2].load(base + (int64_t)(in_row + W) * Csrc);
       a[3].load(base + (int64_t)(in_row + W + 1) * Csrc);
+    };
+    const int step = gridDim.x * rpi;
+    int row = blockIdx.x * rpi + r;
+    Vec<T> cur[4], nxt[4];
+    if (row < rows_it) load4(row, cur);
+    for (; row < rows_it; row += step) {
+      if (row + step < rows_it) load4(row + step, nxt);
       float y[N];
 #pragma unroll
       for (int k = 0; k < N; ++k) y[k] = 0.f;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        float f[N];
-        a[u].unpack(f);
+        float f[N], t[N];
+        cur[u].unpack(f);
+        act(f, t);
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-          const float t = fmaf(f[k], A[k], Bv[k]);
-          y[k] += SILU ? silu_t<TO>(t) : t;
-        }
+        for (int k = 0; k < N; ++k) y[k] += t[k];
       }
 #pragma unroll
       for (int k = 0; k < N; ++k) y[k] *= 0.25f;
       gn_put<T, TO, N>(obase + (int64_t)row * Ctot, y);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
     }
   } else {  // RS_UP: one input row -> four output rows
-    for (int row = blockIdx.x * rpi + r; row < rows_it; row += gridDim.x * rpi) {
-      Vec<T> a;
-      a.load(base + (int64_t)row * Csrc);
+    const int step = gridDim.x * rpi;
+    int row = blockIdx.x * rpi + r;
+    Vec<T> cur, nxt;
+    if (row < rows_it) cur.load(base + (int64_t)row * Csrc);
+    for (; row < rows_it; row += step) {
+      if (row + step < rows_it) nxt.load(base + (int64_t)(row + step) * Csrc);
       float f[N], y[N];
-      a.unpack(f);
-#pragma unroll
-      for (int k = 0; k < N; ++k) {
-        const float t = fmaf(f[k], A[k], Bv[k]);
-        y[k] = SILU ? silu_t<TO>(t) : t;
-      }
+      cur.unpack(f);
+      act(f, y);
       const int w = row % W;
       const int t1 = row / W;
       const int h = t1 % H;
@@ -442,6 +500,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0,
       gn_put<T, TO, N>(obase + (o0 + 1) * Ctot, y);
       gn_put<T, TO, N>(obase + (o0 + 2 * W) * Ctot, y);
       gn_put<T, TO, N>(obase + (o0 + 2 * W + 1) * Ctot, y);
+      cur = nxt;
     }
   }
 }
@@ -495,7 +554,8 @@ static int gn_stats_launch(const GnArgs& a, cudaStream_t s) {
   DD_CHECK(threads <= 256 && threads >= 64, DDPM3D_ERR_ARG, "groupnorm: unsupported channel count");
   const int64_t rows = (int64_t)a.Z * a.H * a.W;
   DD_CHECK(rows * 4 < ((int64_t)1 << 31), DDPM3D_ERR_ARG, "groupnorm: more than 2^29 voxels per batch element");
-  const size_t smem = (size_t)rpi * Ctot * 2 * sizeof(float);
+  const size_t smem = (size_t)rpi * Ctot * 2 * sizeof(double);
+  DD_CHECK(smem <= 48 * 1024, DDPM3D_ERR_ARG, "groupnorm: too many channels for the statistics kernel");
   dim3 grid(a.n_chunks, a.B);
   gn_stats_kernel<T><<<grid, threads, smem, s>>>((const T*)a.src[0], (const T*)a.src[1], a.C[0], a.C[1], (int)rows, a.n_chunks,
                                                  a.pre_add, a.pre_stride, a.partials);
@@ -549,34 +609,21 @@ int gn_forward_chsum(const GnArgs& a, cudaStream_t s) {
   const int Ctot = a.C[0] + a.C[1];
   DD_CHECK(a.chsum[0] && (a.C[1] == 0 || a.chsum[1]) && !a.pre_add, DDPM3D_ERR_STATE, "groupnorm: channel sums missing");
   const double inv_count = 1.0 / ((double)a.Z * a.H * a.W * (Ctot / 32));
-  gn_finalize_chsum_kernel<<<dim3(32, a.B), 128, 0, s>>>(a.chsum[0], a.chsum[1], a.C[0], a.C[1], chsum_slots(), inv_count, a.gamma,
-                                                         a.beta, a.film, a.film_stride, a.ab);
+  gn_finalize_chsum_kernel<<<dim3(32, a.B), 128, 0, s>>>(a.chsum[0], a.chsum[1], a.chsum_bias[0], a.chsum_bias[1], a.C[0], a.C[1],
+                                                         chsum_slots(), (double)a.Z * a.H * a.W, inv_count, a.gamma, a.beta,
+                                                         a.film, a.film_stride, a.ab);
   DD_CUDA(cudaGetLastError());
   return gn_apply_any(a, s);
 }
 
 // z-slab sharding with fused statistics: this rank's fp64 group sums [B][32][2] from the conv epilogues' channel sums
-__global__ void __launch_bounds__(128) gn_chsum_local_kernel(const float* __restrict__ cs0, const float* __restrict__ cs1, int C0,
-                                                             int C1, int P, double* __restrict__ sums) {
+__global__ void __launch_bounds__(128) gn_chsum_local_kernel(const float* __restrict__ cs0, const float* __restrict__ cs1,
+                                                             const float* __restrict__ bias0, const float* __restrict__ bias1,
+                                                             int C0, int C1, int P, double n_vox, double* __restrict__ sums) {
   __shared__ double sh[2][128];
-  const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  const int Ctot = C0 + C1, gpc = Ctot / 32;
-  const int n = P * gpc;
-  double s = 0.0, q = 0.0;
-  for (int i = tid; i < n; i += 128) {
-    const int slot = i / gpc, c = g * gpc + i % gpc;
-    const float* src = c < C0 ? cs0 + (((int64_t)b * P + slot) * C0 + c) * 2 : cs1 + (((int64_t)b * P + slot) * C1 + (c - C0)) * 2;
-    s += (double)src[0];
-    q += (double)src[1];
-  }
-  sh[0][tid] = s;
-  sh[1][tid] = q;
-  __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (tid < o) { sh[0][tid] += sh[0][tid + o]; sh[1][tid] += sh[1][tid + o]; }
-    __syncthreads();
-  }
-  if (tid == 0) {
+  const int g = blockIdx.x, b = blockIdx.y;
+  chsum_group_sums(cs0, cs1, bias0, bias1, C0, C1, P, n_vox, g, b, sh);
+  if (threadIdx.x == 0) {
     sums[((int64_t)b * 32 + g) * 2] = sh[0][0];
     sums[((int64_t)b * 32 + g) * 2 + 1] = sh[1][0];
   }
@@ -585,7 +632,8 @@ __global__ void __launch_bounds__(128) gn_chsum_local_kernel(const float* __rest
 int gn_chsum_local(const GnArgs& a, double* sums, cudaStream_t s) {
   DD_TRY(gn_check(a));
   DD_CHECK(a.chsum[0] && (a.C[1] == 0 || a.chsum[1]), DDPM3D_ERR_STATE, "groupnorm: channel sums missing");
-  gn_chsum_local_kernel<<<dim3(32, a.B), 128, 0, s>>>(a.chsum[0], a.chsum[1], a.C[0], a.C[1], chsum_slots(), sums);
+  gn_chsum_local_kernel<<<dim3(32, a.B), 128, 0, s>>>(a.chsum[0], a.chsum[1], a.chsum_bias[0], a.chsum_bias[1], a.C[0], a.C[1],
+                                                      chsum_slots(), (double)a.Z * a.H * a.W, sums);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }

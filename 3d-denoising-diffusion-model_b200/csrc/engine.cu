@@ -62,6 +62,7 @@ struct Act {
   void* p = nullptr;
   int C = 0, H = 0, W = 0;
   float* chsum = nullptr;  // per-CTA channel sums of this tensor from the producing conv's epilogue (or NULL)
+  const float* cs_bias = nullptr;  // that conv's bias: the sums are over (x - bias)
 };
 
 struct Arena {
@@ -559,7 +560,7 @@ struct Run {
     g.Z = Z;
     const int Ctot = g.C[0] + g.C[1];
     g.n_chunks = gn_chunks((int64_t)Z * g.H * g.W);
-    g.partials = (float*)arena.alloc((size_t)B * g.n_chunks * 64 * sizeof(float));
+    g.partials = (double*)arena.alloc((size_t)B * g.n_chunks * 64 * sizeof(double));
     g.ab = (float*)arena.alloc((size_t)B * 2 * Ctot * sizeof(float));
     double* sums = nullptr;
     double* gathered = nullptr;
@@ -625,7 +626,7 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   g.out_zpad = R.zp;
   g.dt = dts;
   g.dt_out = dt;
-  for (int i = 0; i < nsrc; ++i) { g.src[i] = src[i].p; g.C[i] = src[i].C; g.chsum[i] = src[i].chsum; }
+  for (int i = 0; i < nsrc; ++i) { g.src[i] = src[i].p; g.C[i] = src[i].C; g.chsum[i] = src[i].chsum; g.chsum_bias[i] = src[i].cs_bias; }
   g.H = H; g.W = W;
   g.gamma = L.gn1_g; g.beta = L.gn1_b;
   g.silu = 1;
@@ -652,6 +653,7 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   g2.dt_out = dt;
   g2.src[0] = h2; g2.C[0] = L.cout;
   g2.chsum[0] = c.chsum_written ? c.chsum_out : nullptr;
+  g2.chsum_bias[0] = L.c1.bias;
   g2.H = Ho; g2.W = Wo;
   g2.gamma = L.gn2_g; g2.beta = L.gn2_b;
   if (ctx->cfg.use_scale_shift_norm) { g2.film = R.emb_out ? R.emb_out + L.emb_off : nullptr; g2.film_stride = ctx->emb_rows_total; }
@@ -683,6 +685,7 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   c2.chsum_out = out_cs;
   DD_TRY(R.conv(c2));
   out->chsum = c2.chsum_written ? out_cs : nullptr;
+  out->cs_bias = L.c2.bias;
   R.arena.off = mark;
   return DDPM3D_OK;
 }
@@ -801,7 +804,6 @@ int run_block(Run& R, const std::vector<Layer>& blk, const Act* src, int nsrc, A
 // SuperResModel_noatt.forward (unet.py:1687-1694) + UNetModel_noatt.forward (unet.py:1015-1044)
 int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, const float* t, const int64_t* y, float* out,
                  int H, int W) {
-  const int dt = ctx->dt;
   const int B = R.B, Z = R.Z;
   // time_embed + every emb_layers Linear (unet.py:1029-1033, 199-205)
   float* emb_silu = (float*)R.arena.alloc((size_t)B * ctx->ted * sizeof(float));
@@ -865,6 +867,7 @@ int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, cons
   GnArgs g{};
   g.out_zpad = R.zp;
   g.chsum[0] = h.chsum;
+  g.chsum_bias[0] = h.cs_bias;
   g.dt = ctx->dts; g.src[0] = h.p; g.C[0] = h.C; g.H = H; g.W = W; g.gamma = ctx->out_gn_g; g.beta = ctx->out_gn_b; g.silu = 1;
   g.out = hn; g.out_f32 = 1;
   DD_TRY(R.gn(g));
@@ -1507,13 +1510,36 @@ int ddpm3d_k_groupnorm(int dtype, const void* in, const float* gamma, const floa
   g.dt = dtype; g.src[0] = in; g.C[0] = C; g.B = B; g.Z = Z; g.H = H; g.W = W; g.gamma = gamma; g.beta = beta;
   g.film = film; g.film_stride = 2 * (int64_t)C; g.silu = silu; g.resample = resample; g.out = out;
   g.n_chunks = gn_chunks((int64_t)Z * H * W);
-  const size_t pb = (size_t)B * g.n_chunks * 64 * sizeof(float), ab = (size_t)B * 2 * C * sizeof(float);
+  const size_t pb = (size_t)B * g.n_chunks * 64 * sizeof(double), ab = (size_t)B * 2 * C * sizeof(float);
   void* scratch = nullptr;
   DD_TRY(g_scratch.get(pb + ab + 256, &scratch));
-  g.partials = (float*)scratch;
+  g.partials = (double*)scratch;
   g.ab = (float*)((char*)scratch + ((pb + 255) & ~size_t(255)));
   int n = 0;
   return gn_forward(g, (cudaStream_t)stream, &n);
+}
+
+int ddpm3d_k_conv3d_gn(int dtype, const void* in, const void* w, const float* bias, const float* gamma, const float* beta,
+                       void* conv_out, void* gn_out, int B, int Z, int H, int W, int Cin, int Cout, void* stream) {
+  DD_CHECK(in && w && bias && gamma && beta && conv_out && gn_out, DDPM3D_ERR_ARG, "k_conv3d_gn: null argument");
+  ConvArgs a{};
+  a.dt = dtype; a.main = {in, Cin}; a.taps = 27; a.w = w; a.bias = bias;
+  a.out = conv_out; a.B = B; a.Z = Z; a.Ho = H; a.Wo = W; a.Cout = Cout;
+  DD_CHECK(is_half_dt(dtype) && conv_tc_eligible(a), DDPM3D_ERR_ARG, "k_conv3d_gn: shape not eligible for the tcgen05 path");
+  GnArgs g{};
+  g.dt = dtype; g.src[0] = conv_out; g.C[0] = Cout; g.B = B; g.Z = Z; g.H = H; g.W = W; g.gamma = gamma; g.beta = beta;
+  g.silu = 0; g.out = gn_out;
+  const size_t cs = (size_t)B * chsum_slots() * Cout * 2 * sizeof(float), ab = (size_t)B * 2 * Cout * sizeof(float);
+  void* scratch = nullptr;
+  DD_TRY(g_scratch.get(cs + ab + 512, &scratch));
+  a.chsum_out = (float*)scratch;
+  g.ab = (float*)((char*)scratch + ((cs + 255) & ~size_t(255)));
+  a.splitk_allowed = 0;  // stream-K layers do not produce channel sums
+  DD_TRY(conv_tc(a, (cudaStream_t)stream));
+  DD_CHECK(a.chsum_written, DDPM3D_ERR_STATE, "k_conv3d_gn: this shape does not produce epilogue channel sums");
+  g.chsum[0] = a.chsum_out;
+  g.chsum_bias[0] = bias;
+  return gn_forward_chsum(g, (cudaStream_t)stream);
 }
 
 int ddpm3d_k_timestep_embedding(const float* t, const float* freqs, float* out, int B, int dim, void* stream) {

@@ -41,7 +41,8 @@ struct ConvArgs {
   int B = 0, Z = 0, Ho = 0, Wo = 0, Cout = 0;  // output geometry; input H/W = Ho*stride
   // Optional (tcgen05 path only): per-channel [sum, sum of squares] of the OUTPUT, accumulated from the fp32
   // accumulators in the epilogue, one partial per CTA: chsum_out[B][chsum_slots()][Cout][2].  The consuming
-  // GroupNorm then skips its statistics pass over the tensor.  chsum_written is set by the launcher.
+  // GroupNorm then skips its statistics pass over the tensor.  chsum_written is set by the launcher.  The sums are
+  // taken over (x - bias[c]), i.e. over the accumulators: pass the same `bias` to GnArgs::chsum_bias.
   float* chsum_out = nullptr;
   int chsum_written = 0;
   // split-K scratch for layers with too few tiles to fill the GPU (fp32 partial tiles); see conv_tc_scratch_bytes
@@ -94,8 +95,10 @@ struct GnArgs {
   // per-source channel sums produced by the preceding convolutions' epilogues (see ConvArgs::chsum_out); when
   // every source has them the statistics pass is skipped
   const float* chsum[2] = {nullptr, nullptr};
+  // the sums are over (x - bias_c) of the producing convolution (no cancellation when a bias dominates): its bias [C_s]
+  const float* chsum_bias[2] = {nullptr, nullptr};
   // scratch (owned by the caller / workspace)
-  float* partials = nullptr;                // [B][n_chunks][32][2]
+  double* partials = nullptr;               // [B][32][2][n_chunks] fp64 (pivoted fp32 sums folded back in fp64)
   float* ab = nullptr;                      // [B][2][Ctot]
   int n_chunks = 0;
 };

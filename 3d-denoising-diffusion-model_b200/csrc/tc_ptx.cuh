@@ -157,15 +157,18 @@ inline CUtensorMapDataType tmap_dtype(int dt) {
 }
 
 // channels-last activation [B][Z][H][W][C] -> 5-D map, box {64, bw, bh, bz, 1}
+// stride_hw > 1 (Downsample conv, stride (1,s,s)): the box traverses bw*s x bh*s input voxels with element strides
+// (s, s) and still delivers bw x bh rows
 int make_act_map(CUtensorMap* map, CUtensorMapDataType dtype, const void* ptr, int B, int Z, int H, int W, int C, int bw, int bh,
-                 int bz) {
+                 int bz, int stride_hw = 1) {
   EncodeTiledFn enc = get_encode();
   DD_CHECK(enc != nullptr, DDPM3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Z, (cuuint64_t)B};
   const cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
                                  (cuuint64_t)Z * H * W * C * 2};
-  const cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bz, 1};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const cuuint32_t sh = (cuuint32_t)stride_hw;
+  const cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)bw * sh, (cuuint32_t)bh * sh, (cuuint32_t)bz, 1};
+  const cuuint32_t estr[5] = {1, sh, sh, 1, 1};
   const CUresult r = enc(map, dtype, 5, const_cast<void*>(ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -229,7 +229,7 @@ int ddpm3d_profile_read(ddpm3d_ctx* ctx, ddpm3d_prof_record* out, int cap);
 /* 3x3x3 (taps=27) or 1x1x1 (taps=1) "same" convolution, stride (1,s,s) (nn.py:22-32; call sites
  * unet.py:185,211,219,222).  w: [Cout][taps*Cin] with k = tap*Cin + ci, tap = (dz*3+dh)*3+dw;
  * bias fp32 [Cout]; residual (optional, [B][Z][Ho][Wo][Cout]) is added in the epilogue.
- * path: 1 SIMT, 2 tcgen05 (bf16 / fp16, Cin%64==0, Cout%64==0, s==1), 3 / 4 the Cin==2 stem kernels
+ * path: 1 SIMT, 2 tcgen05 (bf16 / fp16, Cin%64==0, Cout%64==0; s==2 through element-strided TMA boxes), 3 / 4 the Cin==2 stem kernels
  * (3: tcgen05 tile per 128 voxels in the 16-bit modes, 4: CUDA cores). */
 int ddpm3d_k_conv3d(int dtype, int path, const void* in, const void* w, const float* bias, const void* residual,
                     void* out, int B, int Z, int H, int W, int Cin, int Cout, int taps, int stride_hw, void* stream);
@@ -244,6 +244,12 @@ int ddpm3d_k_probe_rowshift(const void* a, int rows, const void* ident, int shif
  * resample 0 none, 1 pool, 2 upsample.  gamma/beta fp32 [C]; film fp32 [B][2C] (scale then shift) or NULL. */
 int ddpm3d_k_groupnorm(int dtype, const void* in, const float* gamma, const float* beta, const float* film,
                        int silu, int resample, void* out, int B, int Z, int H, int W, int C, void* stream);
+
+/* The fused statistics path of a ResBlock (unet.py:245-247: conv -> GroupNorm32): the tcgen05 convolution accumulates
+ * per-channel sums of its own output in the epilogue and GroupNorm (no FiLM, no SiLU) normalises from them without a
+ * statistics pass.  conv_out / gn_out: [B][Z][H][W][Cout] of `dtype` (16-bit).  Unit-test entry point. */
+int ddpm3d_k_conv3d_gn(int dtype, const void* in, const void* w, const float* bias, const float* gamma, const float* beta,
+                       void* conv_out, void* gn_out, int B, int Z, int H, int W, int Cin, int Cout, void* stream);
 
 /* timestep_embedding (nn.py:103-121): t fp32 [B] -> out fp32 [B][dim] (cos block first).  freqs: device fp32
  * [dim/2] host-computed table (see ddpm3d_set_timestep_freqs) or NULL to evaluate exp() on the device. */

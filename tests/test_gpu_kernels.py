@@ -73,6 +73,67 @@ def test_groupnorm_film_silu(dt, C, shape, silu, film, resample):
     assert max_rel(from_cl(out), ref) <= tol
 
 
+@pytest.mark.parametrize("ratio", [100.0, 1000.0])
+@pytest.mark.parametrize("C,shape", [(128, (1, 8, 24, 24)), (64, (2, 3, 6, 10)), (384, (1, 96, 12, 12))])
+def test_groupnorm_large_mean(ratio, C, shape):
+    """|mean| / std = 100 and 1000 per channel (a checkpoint whose activations sit far from zero): E[x^2] - E[x]^2 from
+    fp32 sums would cancel (at 1000 the fp32 variance is pure rounding noise).  The statistics kernel sums around a
+    per-thread pivot and folds it back in fp64, so the result is as accurate as for zero-mean data: compared with
+    F.group_norm evaluated in fp64 on the same fp32 input."""
+    B, Z, H, W = shape
+    g = torch.Generator().manual_seed(C)
+    sign = 1.0 if C != 64 else -1.0
+    mean_c = sign * (ratio + 0.2 * torch.randn(C, generator=g))  # every channel of a group sits near +-ratio
+    x = torch.randn((B, C, Z, H, W), generator=g) + mean_c[None, :, None, None, None]
+    gamma = 1 + 0.1 * torch.randn(C, generator=g)
+    beta = 0.1 * torch.randn(C, generator=g)
+    ref = F.group_norm(x.double(), 32, gamma.double(), beta.double(), 1e-5)
+    out = torch.empty((B, Z, H, W, C), device=DEV)
+    xd, gd_, bd = to_cl(x), gamma.to(DEV), beta.to(DEV)
+    N.check(N.lib().ddpm3d_k_groupnorm(N.FP32, N.ptr(xd), N.ptr(gd_), N.ptr(bd), None, 0, 0, N.ptr(out), B, Z, H, W, C, stream()))
+    torch.cuda.synchronize()
+    # the normalised values are O(1); what remains is the fp32 rounding of the per-channel affine y = x A + B at
+    # |x A| ~ ratio: a few ratio * 2^-24 (E[x^2] - E[x]^2 from fp32 sums would be off by O(1) at ratio = 1000)
+    err = float((from_cl(out).double() - ref).abs().max())
+    print(f"groupnorm, |mean|/std = {ratio:.0f}, C = {C}: max abs error {err:.2e}")
+    assert err <= 4e-7 * ratio
+
+
+@pytest.mark.parametrize("dt", [N.BF16, N.FP16])
+@pytest.mark.parametrize("bias_scale", [0.0, 100.0])
+def test_conv_epilogue_statistics_with_dominant_bias(dt, bias_scale):
+    """unet.py:245-247 conv -> GroupNorm32 on the fused path: the tcgen05 conv's epilogue accumulates the channel sums
+    of its output and GroupNorm normalises from them.  With a bias of ~100 on every channel of a unit-variance signal
+    (|mean| / std = 100) the sums are taken over (x - bias), so nothing cancels: the GroupNorm result equals F.group_norm (fp64) of the
+    conv output the kernel itself stored, to one rounding of the 16-bit result."""
+    B, Z, H, W, Cin, Cout = 1, 8, 24, 24, 64, 128
+    g = torch.Generator().manual_seed(5)
+    tdt = TDT[dt]
+    x = torch.randn((B, Cin, Z, H, W), generator=g).to(tdt).float()
+    w = (torch.randn((Cout, Cin, 3, 3, 3), generator=g) / np.sqrt(Cin * 27)).to(tdt).float()
+    b = torch.randn(Cout, generator=g) * 0.1 + bias_scale  # every channel of a group sits near +bias_scale: mean / std ~ 100
+    gamma = 1 + 0.1 * torch.randn(Cout, generator=g)
+    beta = 0.1 * torch.randn(Cout, generator=g)
+    conv_out = torch.empty((B, Z, H, W, Cout), device=DEV, dtype=tdt)
+    gn_out = torch.empty_like(conv_out)
+    xd, wd, bd, gd_, btd = to_cl(x, tdt), pack_weight(w, tdt), b.to(DEV), gamma.to(DEV), beta.to(DEV)
+    N.check(N.lib().ddpm3d_k_conv3d_gn(dt, N.ptr(xd), N.ptr(wd), N.ptr(bd), N.ptr(gd_), N.ptr(btd), N.ptr(conv_out),
+                                       N.ptr(gn_out), B, Z, H, W, Cin, Cout, stream()))
+    torch.cuda.synchronize()
+    assert max_rel(from_cl(conv_out), F.conv3d(x, w, b, padding=1)) <= ROUND_TOL[dt]
+    # the statistics describe the fp32 accumulators, the normalisation is applied to their 16-bit rounding: with a
+    # dominant bias that rounding (2^-9 / 2^-12 of |x| ~ 150) is what limits the result, not the sums -- so the
+    # reference normalises the stored tensor with statistics of the fp32 conv result
+    y = F.conv3d(x.double(), w.double(), b.double(), padding=1)
+    yg = y.reshape(B, 32, -1)
+    mean = yg.mean(-1).repeat_interleave(Cout // 32, 1)[:, :, None, None, None]
+    rstd = (yg.var(-1, unbiased=False) + 1e-5).rsqrt().repeat_interleave(Cout // 32, 1)[:, :, None, None, None]
+    ref = (from_cl(conv_out).double() - mean) * rstd * gamma.double()[None, :, None, None, None] + beta.double()[None, :, None, None, None]
+    err = float((from_cl(gn_out).double() - ref).abs().max() / ref.abs().max())
+    print(f"conv -> GroupNorm from epilogue sums, bias scale {bias_scale}: max-rel {err:.2e}")
+    assert err <= ROUND_TOL[dt]
+
+
 @pytest.mark.parametrize("dt", [N.FP32, N.BF16, N.FP16])
 @pytest.mark.parametrize("Cin,Cout,shape,taps,stride,res", [
     (2, 32, (1, 4, 8, 8), 27, 1, False), (32, 32, (2, 3, 8, 6), 27, 1, True), (64, 2, (1, 4, 8, 8), 27, 1, False),

@@ -64,6 +64,26 @@ def test_conv3d_tcgen05(Cin, Cout, shape, taps, res, dt):
     assert frac_equal >= (0.98 if dt == N.BF16 else 0.90), frac_equal
 
 
+@pytest.mark.parametrize("Cin,Cout,shape", [(64, 64, (1, 4, 16, 16)), (128, 128, (2, 5, 24, 24)), (256, 256, (1, 9, 12, 20)),
+                                            (128, 128, (1, 24, 96, 96)), (64, 128, (1, 3, 10, 6))])
+@pytest.mark.parametrize("dt", [N.BF16, N.FP16])
+def test_strided_downsample_conv_tcgen05(Cin, Cout, shape, dt):
+    """Downsample(use_conv=True) = Conv3d(C, C, 3, stride=(1,2,2), padding=1) (unet.py:113-140; the factory default
+    resblock_updown=False) on the tcgen05 kernel: the A operand is a TMA box with element strides (2, 2) on (W, H)."""
+    B, Z, H, W = shape
+    tdt = TDT[dt]
+    g = torch.Generator().manual_seed(Cin + Cout + H)
+    x = torch.randn((B, Cin, Z, H, W), generator=g).to(tdt).float()
+    w = (torch.randn((Cout, Cin, 3, 3, 3), generator=g) / np.sqrt(Cin * 27)).to(tdt).float()
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv3d(x, w, b, stride=(1, 2, 2), padding=1)
+    args = (to_cl(x, tdt), pack_weight(w, tdt), b.to(DEV), None, B, Z, H, W, Cin, Cout, 27, 2)
+    tc = conv3d(dt, 2, *args)
+    simt = conv3d(dt, 1, *args)
+    assert max_rel(from_cl(tc), ref) <= ROUND_TOL[dt]
+    assert max_rel(tc.float().cpu(), simt.float().cpu()) <= 1.5 * ROUND_TOL[dt]
+
+
 def test_ineligible_shapes_are_rejected():
     x = torch.zeros((1, 2, 4, 4, 32), device=DEV, dtype=torch.bfloat16)
     w = torch.zeros((64, 27 * 32), device=DEV, dtype=torch.bfloat16)
