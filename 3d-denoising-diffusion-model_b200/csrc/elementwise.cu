@@ -604,6 +604,24 @@ int gn_forward(const GnArgs& a, cudaStream_t s, int* launches) {
   return DDPM3D_OK;
 }
 
+// statistics + per-(b, c) affine only (a.ab); the consumer applies it itself (the fused head, head_tc.cu)
+int gn_finalize_only(const GnArgs& a, cudaStream_t s) {
+  DD_TRY(gn_check(a));
+  const int Ctot = a.C[0] + a.C[1];
+  const double inv_count = 1.0 / ((double)a.Z * a.H * a.W * (Ctot / 32));
+  if (!a.pre_add && a.chsum[0] && (a.C[1] == 0 || a.chsum[1])) {
+    gn_finalize_chsum_kernel<<<dim3(32, a.B), 128, 0, s>>>(a.chsum[0], a.chsum[1], a.chsum_bias[0], a.chsum_bias[1], a.C[0], a.C[1],
+                                                           chsum_slots(), (double)a.Z * a.H * a.W, inv_count, a.gamma, a.beta,
+                                                           a.film, a.film_stride, a.ab);
+  } else {
+    DD_TRY(gn_stats_any(a, s));
+    gn_finalize_kernel<<<a.B, 1024, 0, s>>>(a.partials, a.n_chunks, Ctot, inv_count, a.gamma, a.beta, a.film, a.film_stride,
+                                            a.pre_add, a.pre_stride, a.ab);
+  }
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
 int gn_forward_chsum(const GnArgs& a, cudaStream_t s) {
   DD_TRY(gn_check(a));
   const int Ctot = a.C[0] + a.C[1];

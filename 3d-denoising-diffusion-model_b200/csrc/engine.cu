@@ -175,7 +175,8 @@ struct ddpm3d_ctx {
   float* d_img = nullptr;
   size_t img_cap = 0;
   // options
-  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 1, fold_identity = 1, stem_tc = 1, head_v2 = 1;
+  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 1, fold_identity = 1, stem_tc = 1, head_v2 = 1,
+      head_tc = 1;
   float* splitk_buf = nullptr;  // fp32 partial tiles of split-K convolutions (sized by the dry run)
   size_t splitk_cap = 0, splitk_need = 0;
   cudaStream_t cap_stream = nullptr;
@@ -555,6 +556,22 @@ struct Run {
     return r;
   }
 
+  // statistics + affine only (g.ab); no apply pass
+  int gn_stats(GnArgs& g) {
+    g.B = B;
+    g.Z = Z;
+    const int Ctot = g.C[0] + g.C[1];
+    g.n_chunks = gn_chunks((int64_t)Z * g.H * g.W);
+    g.partials = (double*)arena.alloc((size_t)B * g.n_chunks * 64 * sizeof(double));
+    g.ab = (float*)arena.alloc((size_t)B * 2 * Ctot * sizeof(float));
+    launches += 2;
+    if (arena.dry) return DDPM3D_OK;
+    prof_begin(3, 0.0);
+    const int r = gn_finalize_only(g, s);
+    prof_end();
+    return r;
+  }
+
   int gn(GnArgs& g) {
     g.B = B;
     g.Z = Z;
@@ -863,6 +880,24 @@ int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, cons
   }
   DD_CHECK(h.H == H && h.W == W && h.C == ctx->out_norm_ch, DDPM3D_ERR_STATE, "internal: output geometry mismatch");
   // h.type(x.dtype); out = GN32 -> SiLU -> conv (fp32)                 unet.py:1043-1044
+  if (ctx->head_tc && is_half_dt(ctx->dts) && !R.zp && ctx->conv_path != 1 &&
+      conv_head_tc_eligible(ctx->dts, h.C, ctx->cfg.out_channels)) {
+    // 16-bit modes: one kernel applies the GroupNorm affine + SiLU while staging and runs the conv on tcgen05
+    GnArgs g{};
+    g.chsum[0] = h.chsum;
+    g.chsum_bias[0] = h.cs_bias;
+    g.dt = ctx->dts; g.src[0] = h.p; g.C[0] = h.C; g.H = H; g.W = W; g.gamma = ctx->out_gn_g; g.beta = ctx->out_gn_b; g.silu = 1;
+    DD_TRY(R.gn_stats(g));
+    ++R.launches;
+    if (!R.arena.dry) {
+      R.prof_begin(9, 2.0 * B * Z * H * W * (double)ctx->cfg.out_channels * 27.0 * h.C);
+      const int r = conv_head_tc(ctx->dts, h.p, g.ab, (const float*)ctx->out_conv.w, ctx->out_conv.bias, out, B, Z, H, W, h.C,
+                                 ctx->cfg.out_channels, R.s);
+      R.prof_end();
+      DD_TRY(r);
+    }
+    return DDPM3D_OK;
+  }
   float* hn = (float*)R.arena.alloc(R.conv_in_bytes(H, W, h.C, sizeof(float)));
   GnArgs g{};
   g.out_zpad = R.zp;
@@ -1430,6 +1465,7 @@ int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value) {
   else if (n == "fold_identity") ctx->fold_identity = value != 0;
   else if (n == "stem_tc") ctx->stem_tc = value != 0;
   else if (n == "head_v2") ctx->head_v2 = value != 0;
+  else if (n == "head_tc") ctx->head_tc = value != 0;
   else { set_error("unknown option: " + n); return DDPM3D_ERR_ARG; }
   // cached graphs bake the options in
   if (ctx->device >= 0) {

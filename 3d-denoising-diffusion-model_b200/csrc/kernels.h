@@ -110,6 +110,15 @@ int gn_chsum_local(const GnArgs& a, double* sums, cudaStream_t s);  // same, fro
 int gn_finalize_apply(const GnArgs& a, cudaStream_t s);
 // statistics from the producers' channel sums: finalize + apply only (one read + one write of the tensor)
 int gn_forward_chsum(const GnArgs& a, cudaStream_t s);
+// statistics (from the channel sums when present, else a pass over the tensor) + the per-(b, c) affine a.ab, no apply
+int gn_finalize_only(const GnArgs& a, cudaStream_t s);
+
+// ---- the fused head (head_tc.cu): GroupNorm apply -> SiLU -> Conv3d(C -> 1|2) on tcgen05, 16-bit modes ------------
+// x: the last block output [B][Z][H][W][C] (dt_src); ab: [B][2][C] from gn_finalize_only; w: fp32 [Cout][27*C];
+// out: planar fp32 (B, Cout, Z, H, W)
+bool conv_head_tc_eligible(int dt_src, int C, int Cout);
+int conv_head_tc(int dt_src, const void* x, const float* ab, const float* w, const float* bias, float* out, int B, int Z, int H,
+                 int W, int C, int Cout, cudaStream_t s);
 
 // plain resample (Upsample(use_conv=True) front half, unet.py:100-105)
 int resample_hw(int dt, const void* in, void* out, int B, int Z, int H, int W, int C, int mode, cudaStream_t s);

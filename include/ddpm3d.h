@@ -211,7 +211,10 @@ int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total);
  * "cluster" (0/1, default 0): 2-CTA clusters multicast the weight tile (neutral);
  * "fold_identity" (0/1, default 1): identity skips enter the second conv of a ResBlock as a unit-weight 1x1x1 source;
  * "stem_tc" (0/1, default 1): the Cin == 2 stem runs as one tcgen05 tile per 128 voxels in the 16-bit modes;
- * "head_v2" (0/1, default 1): the fp32 head conv uses 32x16x4 bricks with cp.async double-buffered channel stages. */
+ * "head_v2" (0/1, default 1): the fp32 head conv uses 32x16x4 bricks with cp.async double-buffered channel stages;
+ * "head_tc" (0/1, default 1): 16-bit modes with 64 / 128 model channels: out.0 GroupNorm apply + SiLU + out.2 conv as one
+ * tcgen05 kernel (the contraction over channels once per voxel, the 27 taps as a shifted sum); 0 = GroupNorm pass writing
+ * fp32 + the CUDA-core head. */
 int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value);
 /* Kernel launches enqueued by this ctx since creation. */
 int64_t ddpm3d_launch_count(const ddpm3d_ctx* ctx);

@@ -22,11 +22,17 @@ from gpu_util import DEV, max_rel  # noqa: E402
 # at 5e-3; "bf16_strict" (every tensor bf16, the round-1 design) measures 1.2 .. 2.5e-2 and keeps its 3e-2 bound.
 TOL = {False: 1e-4, True: 1e-2, "fp16": 5e-3, "bf16_strict": 3e-2}
 # The toy networks on which the default bf16 mode does NOT reach 1e-2, by name, with what was measured on B200 and the
-# bound asserted instead (everything else, including the shipped architecture on the slab, 7.7e-3, and on the full
-# 96^3 patch, 6.6e-3, is asserted at 1e-2).  tests/test_rounding_floor.py shows on the CPU oracle why no bf16-operand
-# design can get there: rounding ONLY the conv weights to bf16 already costs 1.0e-2 on C1.
+# bound asserted instead.  Everything with >= 64 channels without attention -- the shipped architecture on the slab
+# (7.7e-3) and on the full 96^3 patch (6.6e-3), `wide` (7.4e-3), the smoke network (7e-3), the other model classes
+# (6.0 .. 7.2e-3) -- and `plainconv` (6.2e-3) is asserted at 1e-2.  The 32-channel toys sit AT the line (0.9 .. 1.25e-2;
+# the max over voxels moves by +-15 % with any change of summation order), so the whole family is listed.
+# tests/test_rounding_floor.py shows on the CPU oracle why no bf16-operand design can do better: rounding ONLY the conv
+# weights to bf16 already costs 1.0e-2 on C1.
 BF16_ABOVE_1E2 = {
+    "tiny": dict(measured=0.90e-2, bound=1.5e-2),           # 32 channels
     "tiny_b2": dict(measured=1.22e-2, bound=1.5e-2),        # 32 channels, batch 2
+    "attn": dict(measured=0.93e-2, bound=1.5e-2),           # 32 channels, attention
+    "classcond": dict(measured=1.07e-2, bound=1.5e-2),      # 32 channels, class-conditional
     "c1_first_eps": dict(measured=1.72e-2, bound=2.2e-2),   # BASELINE configs[0]: 32 channels, 32^3
     "attn64": dict(measured=1.07e-2, bound=1.3e-2),         # 64 channels, six attention blocks (qkv, P and PV operands bf16)
 }

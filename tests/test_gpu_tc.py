@@ -128,7 +128,31 @@ def test_fused_groupnorm_statistics_agree_with_the_separate_pass():
     assert max_rel(outs[1], outs[0]) <= 3e-3
 
 
-@pytest.mark.parametrize("opts", [dict(strip=1, fold_identity=1), dict(fold_identity=1), dict(strip=1), dict(cluster=1), dict(stem_tc=0)])
+@pytest.mark.parametrize("half", [True, "fp16", "bf16_strict"])
+@pytest.mark.parametrize("shape,learn_sigma,ch", [((1, 1, 7, 16, 32), True, 64), ((2, 1, 3, 48, 16), False, 64),
+                                                  ((1, 1, 1, 16, 16), True, 64), ((1, 1, 5, 32, 32), True, 128)])
+def test_fused_head_matches_the_unfused_head(half, shape, learn_sigma, ch):
+    """out.0 GroupNorm -> SiLU -> out.2 conv (unet.py:993-997, 1043-1044): the single tcgen05 kernel (GroupNorm affine
+    applied while staging, contraction over channels once per voxel, taps as a shifted sum; fp16 operands) against
+    the GroupNorm pass + fp32 CUDA-core head.  Ragged tiles, z-ranges with clipped halos, batch 2, one output channel."""
+    over = dict(large_size=16, small_size=16, num_channels=ch, num_res_blocks=1, num_head_channels=64,
+                learn_sigma=learn_sigma, timestep_respacing="10")
+    low, x, _ = synth_inputs(shape, 0)
+    t = torch.tensor([400] * shape[0], device=DEV)
+    outs = {}
+    for fused in (1, 0):
+        model, _, _, _ = build(over, seed=12, fp16=half)
+        model.set_option("head_tc", fused)
+        model.set_option("profile", 1)
+        outs[fused] = model(x.to(DEV), t, low_res=low.to(DEV)).cpu()
+        n_small = [k for k, _, _ in model.profile_read()].count("conv_small")
+        assert n_small == 2  # stem + head, either way
+    err = max_rel(outs[1], outs[0])
+    print(f"fused vs unfused head, mode {half}, shape {shape}: max-rel {err:.2e}")
+    assert err <= 1e-3  # fp16 rounding of hn and of the head weights, fp32 accumulation
+
+
+@pytest.mark.parametrize("opts", [dict(strip=1, fold_identity=1), dict(fold_identity=1), dict(strip=1), dict(cluster=1), dict(stem_tc=0), dict(head_tc=0)])
 def test_c2_architecture_with_kernel_options(opts):
     """The optional kernel variants (strip staging with swapped MMA operands, identity skips folded into the
     accumulation as unit-weight 1x1x1 sources, weight multicast in 2-CTA clusters) on the shipped network:
