@@ -1,6 +1,7 @@
 #include "comm.h"
 
 #include <dlfcn.h>
+#include <stdint.h>
 #include <string.h>
 
 #include <mutex>
@@ -89,6 +90,7 @@ int comm_init(SlabComm* c, const void* id128, int rank, int world) {
 }
 
 void comm_destroy(SlabComm* c) {
+  comm_peer_destroy(c);
   if (c->comm && api().ok) api().CommDestroy((NcclComm)c->comm);
   c->comm = nullptr;
   c->world = 1;
@@ -135,5 +137,180 @@ int comm_allgather_slabs(const SlabComm& c, const void* send, void* recv, int B,
   DD_NCCL(api().GroupEnd());
   return DDPM3D_OK;
 }
+
+
+// =================================================================================================================
+// peer path: CUDA IPC mappings + flag kernels
+// =================================================================================================================
+namespace {
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// a protocol bug (or a dead peer) must surface as a launch failure, never as a hung GPU: give up after ~4 s
+__device__ __forceinline__ void spin_until(const uint32_t* flag, uint32_t seq, int what) {
+  const long long t0 = clock64();
+  while ((int32_t)(ld_acquire_sys(flag) - seq) < 0) {
+    if (clock64() - t0 > 8000000000LL) {
+      printf("ddpm3d slab: peer flag %d timed out waiting for sequence %u (have %u)\n", what, seq, ld_acquire_sys(flag));
+      __trap();
+    }
+  }
+}
+
+// flags: mine; up / down: the neighbours' flag arrays (NULL at the volume ends)
+__global__ void halo_pre_kernel(uint32_t* flags, uint32_t* up, uint32_t* down, uint32_t seq) {
+  if (threadIdx.x != 0) return;
+  __threadfence_system();
+  if (up) st_release_sys(up + SLAB_F_CONSUMED_DOWN, seq - 1);   // I am its lower neighbour
+  if (down) st_release_sys(down + SLAB_F_CONSUMED_UP, seq - 1);
+  if (up) spin_until(flags + SLAB_F_CONSUMED_UP, seq - 1, SLAB_F_CONSUMED_UP);
+  if (down) spin_until(flags + SLAB_F_CONSUMED_DOWN, seq - 1, SLAB_F_CONSUMED_DOWN);
+}
+__global__ void halo_post_kernel(uint32_t* flags, uint32_t* up, uint32_t* down, uint32_t seq) {
+  if (threadIdx.x != 0) return;
+  __threadfence_system();  // (the producing kernel has completed: its peer stores are performed; this orders the flag after them)
+  if (up) st_release_sys(up + SLAB_F_READY_DOWN, seq);
+  if (down) st_release_sys(down + SLAB_F_READY_UP, seq);
+  if (up) spin_until(flags + SLAB_F_READY_UP, seq, SLAB_F_READY_UP);
+  if (down) spin_until(flags + SLAB_F_READY_DOWN, seq, SLAB_F_READY_DOWN);
+}
+
+struct PushArgs {
+  void* box[SLAB_MAX_RANKS];
+  int world, rank, count;
+  uint32_t seq;
+};
+// one block per destination rank: copy the sums, fence, raise the flag
+__global__ void stats_push_kernel(const double* __restrict__ sums, PushArgs a) {
+  const int r = blockIdx.x;
+  double* dst = reinterpret_cast<double*>((char*)a.box[r] + SLAB_FLAGS_BYTES) +
+                ((size_t)(a.seq & 1u) * SLAB_MAX_RANKS + a.rank) * SLAB_GATHER_DOUBLES;
+  for (int i = threadIdx.x; i < a.count; i += blockDim.x) dst[i] = sums[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) st_release_sys(reinterpret_cast<uint32_t*>(a.box[r]) + SLAB_F_STATS + a.rank, a.seq);
+}
+
+int allgather_bytes(SlabComm* c, const void* host_in, void* host_out, size_t bytes, cudaStream_t s) {
+  char* stage = (char*)c->ipc_stage;  // [bytes | world * bytes]
+  DD_CUDA(cudaMemcpyAsync(stage, host_in, bytes, cudaMemcpyHostToDevice, s));
+  DD_NCCL(api().AllGather(stage, stage + 256, bytes, NCCL_INT8, (NcclComm)c->comm, s));
+  DD_CUDA(cudaMemcpyAsync(host_out, stage + 256, bytes * c->world, cudaMemcpyDeviceToHost, s));
+  DD_CUDA(cudaStreamSynchronize(s));
+  return DDPM3D_OK;
+}
+
+}  // namespace
+
+int comm_peer_init(SlabComm* c) {
+  DD_CHECK(c->comm && c->world <= SLAB_MAX_RANKS, DDPM3D_ERR_STATE, "peer path: communicator missing or too many ranks");
+  comm_peer_destroy(c);
+  DD_CUDA(cudaMalloc(&c->ipc_stage, 256 + 64 * SLAB_MAX_RANKS));
+  DD_CUDA(cudaMalloc(&c->mailbox, slab_mailbox_bytes()));
+  DD_CUDA(cudaMemset(c->mailbox, 0, slab_mailbox_bytes()));
+  DD_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t mine;
+  DD_CUDA(cudaIpcGetMemHandle(&mine, c->mailbox));
+  unsigned char all[64 * SLAB_MAX_RANKS];
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  DD_TRY(allgather_bytes(c, &mine, all, 64, nullptr));
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) { c->peer_mailbox[r] = c->mailbox; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, all + 64 * r, 64);
+    const cudaError_t e = cudaIpcOpenMemHandle(&c->peer_mailbox[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {  // no peer access between these devices: stay on the NCCL path
+      cudaGetLastError();
+      for (int q = 0; q < r; ++q)
+        if (q != c->rank && c->peer_mailbox[q]) cudaIpcCloseMemHandle(c->peer_mailbox[q]);
+      memset(c->peer_mailbox, 0, sizeof(c->peer_mailbox));
+      c->p2p = false;
+      return DDPM3D_OK;
+    }
+  }
+  c->p2p = true;
+  c->halo_seq = c->stats_seq = 0;
+  return DDPM3D_OK;
+}
+
+int comm_peer_sync_ws(SlabComm* c, void* ws, cudaStream_t s) {
+  if (!c->p2p) return DDPM3D_OK;
+  cudaIpcMemHandle_t mine;
+  DD_CUDA(cudaIpcGetMemHandle(&mine, ws));
+  unsigned char all[64 * SLAB_MAX_RANKS];
+  DD_TRY(allgather_bytes(c, &mine, all, 64, s));
+  const int nb[2] = {c->rank - 1, c->rank + 1};
+  for (int d = 0; d < 2; ++d) {
+    if (nb[d] < 0 || nb[d] >= c->world) continue;
+    const unsigned char* h = all + 64 * nb[d];
+    if (c->peer_ws_open[d] && memcmp(h, c->peer_ws_handle[d], 64) == 0) continue;
+    if (c->peer_ws_open[d]) {
+      cudaIpcCloseMemHandle(c->peer_ws[d]);
+      c->peer_ws_open[d] = false;
+      c->peer_ws[d] = nullptr;
+    }
+    cudaIpcMemHandle_t hh;
+    memcpy(&hh, h, 64);
+    void* p = nullptr;
+    DD_CUDA(cudaIpcOpenMemHandle(&p, hh, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_ws[d] = (char*)p;
+    c->peer_ws_open[d] = true;
+    memcpy(c->peer_ws_handle[d], h, 64);
+  }
+  return DDPM3D_OK;
+}
+
+void comm_peer_destroy(SlabComm* c) {
+  for (int d = 0; d < 2; ++d) {
+    if (c->peer_ws_open[d]) cudaIpcCloseMemHandle(c->peer_ws[d]);
+    c->peer_ws_open[d] = false;
+    c->peer_ws[d] = nullptr;
+  }
+  for (int r = 0; r < SLAB_MAX_RANKS; ++r) {
+    if (c->peer_mailbox[r] && c->peer_mailbox[r] != c->mailbox) cudaIpcCloseMemHandle(c->peer_mailbox[r]);
+    c->peer_mailbox[r] = nullptr;
+  }
+  if (c->mailbox) cudaFree(c->mailbox);
+  if (c->ipc_stage) cudaFree(c->ipc_stage);
+  c->mailbox = c->ipc_stage = nullptr;
+  c->p2p = false;
+}
+
+int comm_halo_pre(const SlabComm& c, uint32_t seq, cudaStream_t s) {
+  uint32_t* up = c.rank > 0 ? (uint32_t*)c.peer_mailbox[c.rank - 1] : nullptr;
+  uint32_t* down = c.rank + 1 < c.world ? (uint32_t*)c.peer_mailbox[c.rank + 1] : nullptr;
+  halo_pre_kernel<<<1, 32, 0, s>>>((uint32_t*)c.mailbox, up, down, seq);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
+int comm_halo_post(const SlabComm& c, uint32_t seq, cudaStream_t s) {
+  uint32_t* up = c.rank > 0 ? (uint32_t*)c.peer_mailbox[c.rank - 1] : nullptr;
+  uint32_t* down = c.rank + 1 < c.world ? (uint32_t*)c.peer_mailbox[c.rank + 1] : nullptr;
+  halo_post_kernel<<<1, 32, 0, s>>>((uint32_t*)c.mailbox, up, down, seq);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
+int comm_stats_push(const SlabComm& c, const double* sums, int count, uint32_t seq, cudaStream_t s) {
+  DD_CHECK(count <= SLAB_GATHER_DOUBLES, DDPM3D_ERR_ARG, "peer path: statistics record too large (batch > 8)");
+  PushArgs a{};
+  for (int r = 0; r < c.world; ++r) a.box[r] = c.peer_mailbox[r];
+  a.world = c.world; a.rank = c.rank; a.count = count; a.seq = seq;
+  stats_push_kernel<<<c.world, 64, 0, s>>>(sums, a);
+  DD_CUDA(cudaGetLastError());
+  return DDPM3D_OK;
+}
+
+const double* comm_stats_slot(const SlabComm& c, uint32_t seq) {
+  return reinterpret_cast<const double*>((const char*)c.mailbox + SLAB_FLAGS_BYTES) + (size_t)(seq & 1u) * SLAB_MAX_RANKS * SLAB_GATHER_DOUBLES;
+}
+const uint32_t* comm_stats_flags(const SlabComm& c) { return reinterpret_cast<const uint32_t*>(c.mailbox) + SLAB_F_STATS; }
 
 }  // namespace ddpm3d

@@ -9,27 +9,38 @@ namespace ddpm3d {
 // =================================================================================================
 template <typename T>
 __global__ void pack_input_kernel(const float* __restrict__ x, const float* __restrict__ low, T* __restrict__ out, int64_t n,
-                                  int64_t per_b, int64_t pad_vox) {
+                                  int64_t per_b, int64_t pad_vox, T* __restrict__ peer_lo, T* __restrict__ peer_hi) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     const int64_t b = pad_vox ? i / per_b : 0;
     const int64_t o = i + (2 * b + 1) * pad_vox;  // skip the leading halo planes of batches 0..b
-    out[2 * o] = from_f32<T>(x[i]);
-    out[2 * o + 1] = from_f32<T>(low[i]);
+    const T vx = from_f32<T>(x[i]), vl = from_f32<T>(low[i]);
+    out[2 * o] = vx;
+    out[2 * o + 1] = vl;
+    if (pad_vox) {  // peer path (one halo plane): first / last plane -> the neighbours' trailing / leading halo plane
+      const int64_t sp = i - b * per_b, bo = b * (per_b + 2 * pad_vox);
+      if (peer_lo && sp < pad_vox) { peer_lo[2 * (bo + sp)] = vx; peer_lo[2 * (bo + sp) + 1] = vl; }
+      if (peer_hi && sp >= per_b - pad_vox) {
+        const int64_t q = bo + sp - (per_b - pad_vox);
+        peer_hi[2 * q] = vx;
+        peer_hi[2 * q + 1] = vl;
+      }
+    }
   }
 }
 
-int pack_input(int dt, const float* x, const float* low, void* out, int B, int Z, int64_t plane, int out_zpad, cudaStream_t s) {
+int pack_input(int dt, const float* x, const float* low, void* out, int B, int Z, int64_t plane, int out_zpad, cudaStream_t s,
+               void* peer_lo, void* peer_hi) {
   const int64_t n = (int64_t)B * Z * plane, per_b = (int64_t)Z * plane, pad_vox = (int64_t)out_zpad * plane;
   const int threads = 256;
   const int blocks = (int)std::min<int64_t>(ceil_div(n, threads), sm_count() * 16);
   if (dt == DDPM3D_BF16)
-    pack_input_kernel<bf16><<<blocks, threads, 0, s>>>(x, low, (bf16*)out, n, per_b, pad_vox);
+    pack_input_kernel<bf16><<<blocks, threads, 0, s>>>(x, low, (bf16*)out, n, per_b, pad_vox, (bf16*)peer_lo, (bf16*)peer_hi);
   else if (dt == DDPM3D_FP16)
-    pack_input_kernel<f16><<<blocks, threads, 0, s>>>(x, low, (f16*)out, n, per_b, pad_vox);
+    pack_input_kernel<f16><<<blocks, threads, 0, s>>>(x, low, (f16*)out, n, per_b, pad_vox, (f16*)peer_lo, (f16*)peer_hi);
   else
-    pack_input_kernel<float><<<blocks, threads, 0, s>>>(x, low, (float*)out, n, per_b, pad_vox);
+    pack_input_kernel<float><<<blocks, threads, 0, s>>>(x, low, (float*)out, n, per_b, pad_vox, (float*)peer_lo, (float*)peer_hi);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }
@@ -248,18 +259,33 @@ __global__ void __launch_bounds__(1024) gn_reduce_local_kernel(const double* __r
 }
 
 // finalize from the all-gathered per-rank sums: gathered[world][B][32][2], summed in rank order
-__global__ void __launch_bounds__(1024) gn_finalize_multi_kernel(const double* __restrict__ gathered, int world, int B, int Ctot,
-                                                                 double inv_count, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(1024) gn_finalize_multi_kernel(const double* gathered, int world, int B, int Ctot,
+                                                                 int64_t rank_stride, const uint32_t* __restrict__ flags,
+                                                                 uint32_t seq, double inv_count, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, const float* __restrict__ film,
                                                                  int64_t film_stride, const float* __restrict__ pre_add,
                                                                  int64_t pre_stride, float* __restrict__ ab) {
   __shared__ float s_mean[32], s_rstd[32];
   const int b = blockIdx.x;
+  if (flags) {  // peer path: every rank stores its sums into this rank's mailbox and then raises flags[rank] to seq
+    if (threadIdx.x < world) {
+      const long long t0 = clock64();
+      uint32_t v;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+        if (clock64() - t0 > 8000000000LL) {
+          printf("ddpm3d slab: statistics of rank %d did not arrive (sequence %u, have %u)\n", (int)threadIdx.x, seq, v);
+          __trap();
+        }
+      } while ((int32_t)(v - seq) < 0);
+    }
+    __syncthreads();
+  }
   if (threadIdx.x < 32) {
     const int g = threadIdx.x;
     double s = 0.0, q = 0.0;
     for (int r = 0; r < world; ++r) {
-      const double* p = gathered + (((int64_t)r * B + b) * 32 + g) * 2;
+      const double* p = gathered + (int64_t)r * rank_stride + ((int64_t)b * 32 + g) * 2;
       s += p[0];
       q += p[1];
     }
@@ -370,9 +396,10 @@ __device__ __forceinline__ void gn_put(TO* dst, const float* y) {
 template <typename T, typename TO, int MODE, bool SILU>
 __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int C1, int Z,
                                                        int H, int W, int rows_per_block, const float* __restrict__ ab,
-                                                       TO* __restrict__ out, int out_zpad) {
+                                                       TO* __restrict__ out, int out_zpad, TO* __restrict__ peer_lo,
+                                                       TO* __restrict__ peer_hi) {
   constexpr int N = Vec<T>::N;
-  constexpr bool FAST = SILU && sizeof(TO) == 2;  // two-MUFU SiLU with a pre-scaled second affine
+  constexpr bool FAST = SILU && sizeof(TO) == 2;  // two-MUFU SiLU
   const int Ctot = C0 + C1;
   const int nvec0 = C0 / N, nvec = Ctot / N;
   const int rpi = blockDim.x / nvec;
@@ -387,7 +414,18 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const T* __restrict__ 
   if (v < nvec0) { base = s0 + (int64_t)b * rows_in * C0 + v * N; Csrc = C0; }
   else { base = s1 + (int64_t)b * rows_in * C1 + (v - nvec0) * N; Csrc = C1; }
   const int plane_out = rows_out / Z;
+  const int64_t obstride = (int64_t)(Z + 2 * out_zpad) * plane_out * Ctot;
   TO* obase = out + ((int64_t)b * (Z + 2 * out_zpad) + out_zpad) * plane_out * Ctot + v * N;
+  // z-slab sharding over peer-mapped memory: the first / last plane of this slab is also stored straight into the
+  // trailing halo plane of the upper neighbour (peer_lo) / the leading halo plane of the lower one (peer_hi)
+  TO* plo = peer_lo ? peer_lo + (int64_t)b * obstride + v * N : nullptr;
+  TO* phi = peer_hi ? peer_hi + (int64_t)b * obstride + v * N : nullptr;
+  const int last_plane0 = rows_out - plane_out;
+  auto put = [&](int orow, const float* y) {
+    gn_put<T, TO, N>(obase + (int64_t)orow * Ctot, y);
+    if (plo && orow < plane_out) gn_put<T, TO, N>(plo + (int64_t)orow * Ctot, y);
+    if (phi && orow >= last_plane0) gn_put<T, TO, N>(phi + (int64_t)(orow - last_plane0) * Ctot, y);
+  };
   float A[N], Bv[N];
   {
     const float* pa = ab + (int64_t)b * 2 * Ctot + v * N;
@@ -431,7 +469,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const T* __restrict__ 
           float f[N], y[N];
           cur[u].unpack(f);
           act(f, y);
-          gn_put<T, TO, N>(obase + (int64_t)(row + u * rpi) * Ctot, y);
+          put(row + u * rpi, y);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) cur[u] = nxt[u];
@@ -442,7 +480,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const T* __restrict__ 
           float f[N], y[N];
           a.unpack(f);
           act(f, y);
-          gn_put<T, TO, N>(obase + (int64_t)rr * Ctot, y);
+          put(rr, y);
         }
       }
     }
@@ -477,7 +515,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const T* __restrict__ 
       }
 #pragma unroll
       for (int k = 0; k < N; ++k) y[k] *= 0.25f;
-      gn_put<T, TO, N>(obase + (int64_t)row * Ctot, y);
+      put(row, y);
 #pragma unroll
       for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
     }
@@ -495,11 +533,11 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const T* __restrict__ 
       const int t1 = row / W;
       const int h = t1 % H;
       const int z = t1 / H;
-      const int64_t o0 = ((int64_t)(z * 2 * H + 2 * h)) * (2 * W) + 2 * w;
-      gn_put<T, TO, N>(obase + o0 * Ctot, y);
-      gn_put<T, TO, N>(obase + (o0 + 1) * Ctot, y);
-      gn_put<T, TO, N>(obase + (o0 + 2 * W) * Ctot, y);
-      gn_put<T, TO, N>(obase + (o0 + 2 * W + 1) * Ctot, y);
+      const int o0 = (z * 2 * H + 2 * h) * (2 * W) + 2 * w;
+      put(o0, y);
+      put(o0 + 1, y);
+      put(o0 + 2 * W, y);
+      put(o0 + 2 * W + 1, y);
       cur = nxt;
     }
   }
@@ -529,7 +567,8 @@ static int gn_apply_launch(const GnArgs& a, cudaStream_t s) {
   const T* s0 = (const T*)a.src[0];
   const T* s1 = (const T*)a.src[1];
 #define GN_LAUNCH(MODE, SILU) \
-  gn_apply_kernel<T, TO, MODE, SILU><<<grid, threads, 0, s>>>(s0, s1, a.C[0], a.C[1], a.Z, a.H, a.W, rows_per_block, a.ab, (TO*)a.out, a.out_zpad)
+  gn_apply_kernel<T, TO, MODE, SILU><<<grid, threads, 0, s>>>(s0, s1, a.C[0], a.C[1], a.Z, a.H, a.W, rows_per_block, a.ab, (TO*)a.out, a.out_zpad, \
+                                                              (TO*)a.peer_halo[0], (TO*)a.peer_halo[1])
   if (a.silu) {
     if (a.resample == RS_NONE) GN_LAUNCH(RS_NONE, true);
     else if (a.resample == RS_POOL) GN_LAUNCH(RS_POOL, true);
@@ -667,7 +706,8 @@ int gn_stats_local(const GnArgs& a, double* sums, cudaStream_t s) {
 int gn_finalize_apply(const GnArgs& a, cudaStream_t s) {
   const int Ctot = a.C[0] + a.C[1];
   DD_CHECK(a.gathered != nullptr && a.world >= 1, DDPM3D_ERR_STATE, "groupnorm: gathered statistics missing");
-  gn_finalize_multi_kernel<<<a.B, 1024, 0, s>>>(a.gathered, a.world, a.B, Ctot, a.inv_count_global, a.gamma, a.beta, a.film,
+  gn_finalize_multi_kernel<<<a.B, 1024, 0, s>>>(a.gathered, a.world, a.B, Ctot, a.gather_stride ? a.gather_stride : (int64_t)a.B * 64,
+                                                a.gather_flags, a.gather_seq, a.inv_count_global, a.gamma, a.beta, a.film,
                                                 a.film_stride, a.pre_add, a.pre_stride, a.ab);
   DD_CUDA(cudaGetLastError());
   return gn_apply_any(a, s);

@@ -176,7 +176,7 @@ struct ddpm3d_ctx {
   size_t img_cap = 0;
   // options
   int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 1, fold_identity = 1, stem_tc = 1, head_v2 = 1,
-      head_tc = 1;
+      head_tc = 1, slab_p2p = 1;
   float* splitk_buf = nullptr;  // fp32 partial tiles of split-K convolutions (sized by the dry run)
   size_t splitk_cap = 0, splitk_need = 0;
   cudaStream_t cap_stream = nullptr;
@@ -496,9 +496,56 @@ struct Run {
   // a tensor a 3x3x3 conv will read: carries the halo planes in z-slab mode
   size_t conv_in_bytes(int H, int W, int C, size_t esz) const { return (size_t)B * (Z + 2 * zp) * H * W * C * esz; }
 
-  // after a conv-input tensor has been produced: fetch the neighbours' boundary planes
+  // z-slab sharding over peer-mapped memory (comm.cu "peer path"): equal slabs, mailboxes and both neighbours' workspaces
+  // mapped.  The producing kernel then stores its boundary planes into the neighbours' halo planes itself.
+  bool p2p() const {
+    const SlabComm& c = ctx->slab;
+    return zp && ctx->slab_p2p && c.halo_p2p() && c.z_total == c.world * Z && c.z_begin == c.rank * Z;
+  }
+  // the same tensor in the workspace of the upper (dir 0) / lower (dir 1) neighbour (identical arena layout)
+  char* peer_ptr(int dir, const void* t) const {
+    const SlabComm& c = ctx->slab;
+    const int nb = dir == 0 ? c.rank - 1 : c.rank + 1;
+    if (nb < 0 || nb >= c.world) return nullptr;
+    return c.peer_ws[dir] + ((const char*)t - ctx->ws);
+  }
+  // before a kernel that stores into the neighbours' halo planes of tensor `t` ([B][Z+2][plane_bytes]): handshake
+  // (everything up to the previous exchange has been consumed everywhere), zero the planes at the volume's ends
+  int halo_begin(void* t, size_t plane_bytes, void** peer_lo, void** peer_hi) {
+    SlabComm& c = ctx->slab;
+    launches += 1;
+    *peer_lo = *peer_hi = nullptr;
+    if (arena.dry) return DDPM3D_OK;
+    prof_begin(10, 0.0);
+    const uint32_t seq = ++c.halo_seq;
+    int r = comm_halo_pre(c, seq, s);
+    prof_end();
+    DD_TRY(r);
+    const size_t bstride = (size_t)(Z + 2) * plane_bytes;
+    for (int b = 0; b < B; ++b) {
+      if (c.rank == 0) DD_CUDA(cudaMemsetAsync((char*)t + b * bstride, 0, plane_bytes, s));
+      if (c.rank + 1 == c.world) DD_CUDA(cudaMemsetAsync((char*)t + b * bstride + (size_t)(Z + 1) * plane_bytes, 0, plane_bytes, s));
+    }
+    if (char* up = peer_ptr(0, t)) *peer_lo = up + (size_t)(Z + 1) * plane_bytes;  // its trailing halo plane
+    if (char* dn = peer_ptr(1, t)) *peer_hi = dn;                                  // its leading halo plane
+    return DDPM3D_OK;
+  }
+  int halo_end(double bytes) {
+    launches += 1;
+    if (arena.dry) return DDPM3D_OK;
+    prof_begin(10, bytes);
+    const int r = comm_halo_post(ctx->slab, ctx->slab.halo_seq, s);
+    prof_end();
+    return r;
+  }
+
+  // after a conv-input tensor has been produced: fetch the neighbours' boundary planes (NCCL path; on the peer path the
+  // producing kernel has already stored them)
   int halo(void* t, int H, int W, int C, size_t esz) {
-    if (!zp) return DDPM3D_OK;
+    if (!zp || p2p()) return DDPM3D_OK;
+    return halo_nccl(t, H, W, C, esz);
+  }
+  int halo_nccl(void* t, int H, int W, int C, size_t esz) {
     launches += 1;
     if (arena.dry) return DDPM3D_OK;
     prof_begin(10, (double)B * 2 * H * W * C * esz);
@@ -585,6 +632,7 @@ struct Run {
       sums = (double*)arena.alloc((size_t)B * 64 * sizeof(double));
       gathered = (double*)arena.alloc((size_t)ctx->slab.world * B * 64 * sizeof(double));
       launches += 2;
+      if (arena.dry && g.out_zpad && p2p()) launches += 2;  // (the live path counts them in halo_begin / halo_end)
     }
     launches += 3;
     if (arena.dry) return DDPM3D_OK;
@@ -597,20 +645,42 @@ struct Run {
     int r;
     if (fused) {
       r = gn_forward_chsum(g, s);
-    } else if (zp) {  // z-slab sharding: statistics span all ranks (fp64 sums all-gathered, summed in rank order)
+    } else if (zp) {  // z-slab sharding: statistics span all ranks (fp64 sums exchanged, summed in rank order)
       r = have_cs ? gn_chsum_local(g, sums, s) : gn_stats_local(g, sums, s);
+      const bool peer = p2p() && B * 64 <= SLAB_GATHER_DOUBLES;
       if (r == DDPM3D_OK) {
         prof_end();
         prof_begin(11, (double)ctx->slab.world * B * 64 * sizeof(double));
-        r = comm_allgather_f64(ctx->slab, sums, gathered, (size_t)B * 64, s);
+        if (peer) {  // every rank stores its sums into every mailbox; the finalize kernel waits for the flags
+          const uint32_t seq = ++ctx->slab.stats_seq;
+          r = comm_stats_push(ctx->slab, sums, B * 64, seq, s);
+          g.gathered = comm_stats_slot(ctx->slab, seq);
+          g.gather_stride = SLAB_GATHER_DOUBLES;
+          g.gather_flags = comm_stats_flags(ctx->slab);
+          g.gather_seq = seq;
+        } else {
+          r = comm_allgather_f64(ctx->slab, sums, gathered, (size_t)B * 64, s);
+          g.gathered = gathered;
+        }
         prof_end();
-        prof_begin(4, 0.0);
+      }
+      void *peer_lo = nullptr, *peer_hi = nullptr;
+      const bool peer_halo = r == DDPM3D_OK && g.out_zpad && p2p();
+      if (peer_halo) {
+        const int Ho = g.resample == RS_POOL ? g.H / 2 : (g.resample == RS_UP ? 2 * g.H : g.H);
+        const int Wo = g.resample == RS_POOL ? g.W / 2 : (g.resample == RS_UP ? 2 * g.W : g.W);
+        r = halo_begin(g.out, (size_t)Ho * Wo * Ctot * (size_t)out_b, &peer_lo, &peer_hi);
+        g.peer_halo[0] = peer_lo;
+        g.peer_halo[1] = peer_hi;
       }
       if (r == DDPM3D_OK) {
-        g.gathered = gathered;
+        prof_begin(4, 0.0);
         g.world = ctx->slab.world;
         g.inv_count_global = 1.0 / ((double)ctx->slab.z_total * g.H * g.W * (Ctot / 32));
         r = gn_finalize_apply(g, s);
+        prof_end();
+        if (peer_halo && r == DDPM3D_OK) r = halo_end(2.0 * B * g.H * g.W * Ctot * out_b * scale);
+        return r;
       }
     } else {
       int dummy = 0;
@@ -851,13 +921,18 @@ int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, cons
   if (!R.arena.dry) {
     DD_CHECK((low != nullptr) == (ctx->cfg.unconditional == 0), DDPM3D_ERR_ARG,
              "low_res must be given to a conditional model and only to it (unet.py:1687-1694)");
+    void *peer_lo = nullptr, *peer_hi = nullptr;
+    const bool peer = R.p2p() && Cx == 1 && low;
+    if (peer) DD_TRY(R.halo_begin(h.p, (size_t)H * W * Cstem * ctx->esz, &peer_lo, &peer_hi));
     R.prof_begin(8, (double)B * Z * H * W * Cstem * (4.0 + ctx->esz));
-    const int r = Cx == 1 && low ? pack_input(ctx->dts, x, low, h.p, B, Z, (int64_t)H * W, R.zp, R.s)
+    const int r = Cx == 1 && low ? pack_input(ctx->dts, x, low, h.p, B, Z, (int64_t)H * W, R.zp, R.s, peer_lo, peer_hi)
                                  : pack_input_planar(ctx->dts, x, low, Cx, h.p, B, Z, (int64_t)H * W, R.zp, R.s);
     R.prof_end();
     DD_TRY(r);
+    if (peer) DD_TRY(R.halo_end((double)B * 2 * H * W * Cstem * ctx->esz));
+    else if (R.p2p()) DD_TRY(R.halo_nccl(h.p, H, W, Cstem, ctx->esz));
   }
-  DD_TRY(R.halo(h.p, H, W, Cstem, ctx->esz));
+  if (!R.p2p()) DD_TRY(R.halo(h.p, H, W, Cstem, ctx->esz));
   std::vector<Act> skips;
   for (auto& blk : ctx->input_blocks) {
     Act o;
@@ -967,6 +1042,13 @@ int ensure_workspace(ddpm3d_ctx* ctx, int B, int Z, int H, int W) {
     ctx->ws_cap = (size_t)need;
   }
   return DDPM3D_OK;
+}
+
+// z-slab sharding over peer-mapped memory: (re)map the neighbours' workspaces.  Collective over the slab ranks: every
+// rank reaches it at the start of every sharded call (same call sequence on all ranks).
+int sync_peers(ddpm3d_ctx* ctx, cudaStream_t s) {
+  if (!ctx->slab.active() || !ctx->slab.p2p || !ctx->slab_p2p) return DDPM3D_OK;
+  return comm_peer_sync_ws(&ctx->slab, ctx->ws, s);
 }
 
 int forward_launch(ddpm3d_ctx* ctx, const float* x, const float* low, const float* t, const int64_t* y, float* out, int B,
@@ -1239,6 +1321,7 @@ int ddpm3d_unet_forward(ddpm3d_ctx* ctx, const float* x, const float* low_res, c
   DD_CUDA(cudaSetDevice(ctx->device));
   DD_TRY(ensure_workspace(ctx, B, Z, H, W));
   cudaStream_t s = (cudaStream_t)stream;
+  DD_TRY(sync_peers(ctx, s));
   GraphKey key{};
   key.kind = 0; key.B = B; key.Z = Z; key.H = H; key.W = W;
   key.p[0] = x; key.p[1] = low_res; key.p[2] = t; key.p[3] = y; key.p[4] = out; key.p[5] = s;
@@ -1317,6 +1400,7 @@ int ddpm3d_p_sample(ddpm3d_ctx* ctx, const float* x, const float* low_res, const
   DD_TRY(ensure_workspace(ctx, B, Z, H, W));
   DD_TRY(ensure_loop_buffers(ctx, B, n));
   cudaStream_t s = (cudaStream_t)stream;
+  DD_TRY(sync_peers(ctx, s));
   // the step index is data (device counter), so one graph serves every step
   DD_TRY(step_set_k(ctx->d_counter, ctx->d_tmodel, ctx->d_table, B, step_index, 0, s));
   ctx->launches += 1;
@@ -1349,6 +1433,7 @@ int ddpm3d_p_sample_t(ddpm3d_ctx* ctx, const float* x, const float* low_res, con
   DD_TRY(ensure_workspace(ctx, B, Z, H, W));
   DD_TRY(ensure_loop_buffers(ctx, B, n));
   cudaStream_t s = (cudaStream_t)stream;
+  DD_TRY(sync_peers(ctx, s));
   GraphKey key{};
   key.kind = 3; key.B = B; key.Z = Z; key.H = H; key.W = W;
   key.p[0] = x; key.p[1] = low_res; key.p[2] = y; key.p[3] = noise; key.p[4] = sample; key.p[5] = pred_xstart; key.p[6] = s;
@@ -1380,6 +1465,7 @@ int ddpm3d_sample_loop(ddpm3d_ctx* ctx, const float* x_T, const float* low_res, 
   DD_TRY(ensure_loop_buffers(ctx, B, n));
   if (n_steps <= 0 || n_steps > ctx->T) n_steps = ctx->T;
   cudaStream_t s = (cudaStream_t)stream;
+  DD_TRY(sync_peers(ctx, s));
   float* img = ctx->d_img;
   DD_CUDA(cudaMemcpyAsync(img, x_T, (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, s));
   DD_TRY(step_set_k(ctx->d_counter, ctx->d_tmodel, ctx->d_table, B, ctx->T - 1, 0, s));
@@ -1426,7 +1512,10 @@ int ddpm3d_set_comm(ddpm3d_ctx* ctx, const void* id128, int rank, int world) {
   for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
   ctx->graphs.clear();
   ctx->graph_launches.clear();
-  return comm_init(&ctx->slab, id128, rank, world);
+  DD_TRY(comm_init(&ctx->slab, id128, rank, world));
+  // mailboxes for the peer path (CUDA IPC over NVLink); without peer access between the devices the NCCL path stays
+  if (world > 1 && ctx->slab_p2p) DD_TRY(comm_peer_init(&ctx->slab));
+  return DDPM3D_OK;
 }
 
 int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total) {
@@ -1466,6 +1555,7 @@ int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value) {
   else if (n == "stem_tc") ctx->stem_tc = value != 0;
   else if (n == "head_v2") ctx->head_v2 = value != 0;
   else if (n == "head_tc") ctx->head_tc = value != 0;
+  else if (n == "slab_p2p") ctx->slab_p2p = value != 0;
   else { set_error("unknown option: " + n); return DDPM3D_ERR_ARG; }
   // cached graphs bake the options in
   if (ctx->device >= 0) {

@@ -92,6 +92,14 @@ struct GnArgs {
   const double* gathered = nullptr;
   int world = 1;
   double inv_count_global = 0.0;
+  // peer path: gathered is this rank's mailbox slot (rank stride gather_stride doubles); the finalize kernel first waits
+  // until gather_flags[r] >= gather_seq for every rank r
+  int64_t gather_stride = 0;
+  const uint32_t* gather_flags = nullptr;
+  uint32_t gather_seq = 0;
+  // peer path: base (batch 0) of the upper neighbour's trailing halo plane / the lower neighbour's leading halo plane of
+  // the tensor that corresponds to `out` (same layout), or NULL
+  void* peer_halo[2] = {nullptr, nullptr};
   // per-source channel sums produced by the preceding convolutions' epilogues (see ConvArgs::chsum_out); when
   // every source has them the statistics pass is skipped
   const float* chsum[2] = {nullptr, nullptr};
@@ -126,7 +134,8 @@ int resample_hw(int dt, const void* in, void* out, int B, int Z, int H, int W, i
 // ---- network input / embedding -----------------------------------------------------------------
 // cat([x, low_res], 1) + cast (unet.py:1690-1693,1035): two fp32 (B,1,Z,H,W) -> [B][Z][H][W][2]
 // out_zpad: halo planes on each side of Z in `out` ([B][Z+2p][H][W][2]); plane = H*W voxels
-int pack_input(int dt, const float* x, const float* low, void* out, int B, int Z, int64_t plane, int out_zpad, cudaStream_t s);
+int pack_input(int dt, const float* x, const float* low, void* out, int B, int Z, int64_t plane, int out_zpad, cudaStream_t s,
+               void* peer_lo = nullptr, void* peer_hi = nullptr);
 int pack_input_planar(int dt, const float* x, const float* low, int Cx, void* out, int B, int Z, int64_t plane, int out_zpad,
                       cudaStream_t s);
 

@@ -212,6 +212,9 @@ int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total);
  * "fold_identity" (0/1, default 1): identity skips enter the second conv of a ResBlock as a unit-weight 1x1x1 source;
  * "stem_tc" (0/1, default 1): the Cin == 2 stem runs as one tcgen05 tile per 128 voxels in the 16-bit modes;
  * "head_v2" (0/1, default 1): the fp32 head conv uses 32x16x4 bricks with cp.async double-buffered channel stages;
+ * "slab_p2p" (0/1, default 1; set before ddpm3d_set_comm): z-slab sharding exchanges halo planes and GroupNorm sums through
+ * peer-mapped memory (CUDA IPC over NVLink: the producing kernels store into the neighbours' halo planes, sequence-numbered
+ * flags order the accesses) instead of NCCL send/recv and all-gather; needs equal slabs and peer access, else NCCL is used;
  * "head_tc" (0/1, default 1): 16-bit modes with 64 / 128 model channels: out.0 GroupNorm apply + SiLU + out.2 conv as one
  * tcgen05 kernel (the contraction over channels once per voxel, the 27 taps as a shifted sum); 0 = GroupNorm pass writing
  * fp32 + the CUDA-core head. */
