@@ -164,16 +164,19 @@ __device__ __forceinline__ void spin_until(const uint32_t* flag, uint32_t seq, i
 }
 
 // flags: mine; up / down: the neighbours' flag arrays (NULL at the volume ends)
-__global__ void halo_pre_kernel(uint32_t* flags, uint32_t* up, uint32_t* down, uint32_t seq) {
+__global__ void halo_pre_kernel(uint32_t* flags, uint32_t* up, uint32_t* down) {
   if (threadIdx.x != 0) return;
+  const uint32_t seq = flags[SLAB_F_HALO_SEQ] + 1;
+  flags[SLAB_F_HALO_SEQ] = seq;
   __threadfence_system();
   if (up) st_release_sys(up + SLAB_F_CONSUMED_DOWN, seq - 1);   // I am its lower neighbour
   if (down) st_release_sys(down + SLAB_F_CONSUMED_UP, seq - 1);
   if (up) spin_until(flags + SLAB_F_CONSUMED_UP, seq - 1, SLAB_F_CONSUMED_UP);
   if (down) spin_until(flags + SLAB_F_CONSUMED_DOWN, seq - 1, SLAB_F_CONSUMED_DOWN);
 }
-__global__ void halo_post_kernel(uint32_t* flags, uint32_t* up, uint32_t* down, uint32_t seq) {
+__global__ void halo_post_kernel(uint32_t* flags, uint32_t* up, uint32_t* down) {
   if (threadIdx.x != 0) return;
+  const uint32_t seq = flags[SLAB_F_HALO_SEQ];
   __threadfence_system();  // (the producing kernel has completed: its peer stores are performed; this orders the flag after them)
   if (up) st_release_sys(up + SLAB_F_READY_DOWN, seq);
   if (down) st_release_sys(down + SLAB_F_READY_UP, seq);
@@ -184,17 +187,20 @@ __global__ void halo_post_kernel(uint32_t* flags, uint32_t* up, uint32_t* down, 
 struct PushArgs {
   void* box[SLAB_MAX_RANKS];
   int world, rank, count;
-  uint32_t seq;
 };
-// one block per destination rank: copy the sums, fence, raise the flag
-__global__ void stats_push_kernel(const double* __restrict__ sums, PushArgs a) {
-  const int r = blockIdx.x;
-  double* dst = reinterpret_cast<double*>((char*)a.box[r] + SLAB_FLAGS_BYTES) +
-                ((size_t)(a.seq & 1u) * SLAB_MAX_RANKS + a.rank) * SLAB_GATHER_DOUBLES;
-  for (int i = threadIdx.x; i < a.count; i += blockDim.x) dst[i] = sums[i];
+// one block: copy the sums into every rank's slot, fence, raise this rank's flag everywhere
+__global__ void __launch_bounds__(256) stats_push_kernel(const double* __restrict__ sums, PushArgs a) {
+  uint32_t* mine = reinterpret_cast<uint32_t*>(a.box[a.rank]);
+  const uint32_t seq = mine[SLAB_F_STATS_SEQ] + 1;
+  for (int r = 0; r < a.world; ++r) {
+    double* dst = reinterpret_cast<double*>((char*)a.box[r] + SLAB_FLAGS_BYTES) +
+                  ((size_t)(seq & 1u) * SLAB_MAX_RANKS + a.rank) * SLAB_GATHER_DOUBLES;
+    for (int i = threadIdx.x; i < a.count; i += blockDim.x) dst[i] = sums[i];
+  }
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) st_release_sys(reinterpret_cast<uint32_t*>(a.box[r]) + SLAB_F_STATS + a.rank, a.seq);
+  if ((int)threadIdx.x < a.world) st_release_sys(reinterpret_cast<uint32_t*>(a.box[threadIdx.x]) + SLAB_F_STATS + a.rank, seq);
+  if (threadIdx.x == 0) mine[SLAB_F_STATS_SEQ] = seq;
 }
 
 int allgather_bytes(SlabComm* c, const void* host_in, void* host_out, size_t bytes, cudaStream_t s) {
@@ -235,11 +241,11 @@ int comm_peer_init(SlabComm* c) {
     }
   }
   c->p2p = true;
-  c->halo_seq = c->stats_seq = 0;
   return DDPM3D_OK;
 }
 
-int comm_peer_sync_ws(SlabComm* c, void* ws, cudaStream_t s) {
+int comm_peer_sync_ws(SlabComm* c, void* ws, cudaStream_t s, bool* changed) {
+  *changed = false;
   if (!c->p2p) return DDPM3D_OK;
   cudaIpcMemHandle_t mine;
   DD_CUDA(cudaIpcGetMemHandle(&mine, ws));
@@ -250,6 +256,7 @@ int comm_peer_sync_ws(SlabComm* c, void* ws, cudaStream_t s) {
     if (nb[d] < 0 || nb[d] >= c->world) continue;
     const unsigned char* h = all + 64 * nb[d];
     if (c->peer_ws_open[d] && memcmp(h, c->peer_ws_handle[d], 64) == 0) continue;
+    *changed = true;
     if (c->peer_ws_open[d]) {
       cudaIpcCloseMemHandle(c->peer_ws[d]);
       c->peer_ws_open[d] = false;
@@ -282,35 +289,34 @@ void comm_peer_destroy(SlabComm* c) {
   c->p2p = false;
 }
 
-int comm_halo_pre(const SlabComm& c, uint32_t seq, cudaStream_t s) {
+int comm_halo_pre(const SlabComm& c, cudaStream_t s) {
   uint32_t* up = c.rank > 0 ? (uint32_t*)c.peer_mailbox[c.rank - 1] : nullptr;
   uint32_t* down = c.rank + 1 < c.world ? (uint32_t*)c.peer_mailbox[c.rank + 1] : nullptr;
-  halo_pre_kernel<<<1, 32, 0, s>>>((uint32_t*)c.mailbox, up, down, seq);
+  halo_pre_kernel<<<1, 32, 0, s>>>((uint32_t*)c.mailbox, up, down);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }
 
-int comm_halo_post(const SlabComm& c, uint32_t seq, cudaStream_t s) {
+int comm_halo_post(const SlabComm& c, cudaStream_t s) {
   uint32_t* up = c.rank > 0 ? (uint32_t*)c.peer_mailbox[c.rank - 1] : nullptr;
   uint32_t* down = c.rank + 1 < c.world ? (uint32_t*)c.peer_mailbox[c.rank + 1] : nullptr;
-  halo_post_kernel<<<1, 32, 0, s>>>((uint32_t*)c.mailbox, up, down, seq);
+  halo_post_kernel<<<1, 32, 0, s>>>((uint32_t*)c.mailbox, up, down);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }
 
-int comm_stats_push(const SlabComm& c, const double* sums, int count, uint32_t seq, cudaStream_t s) {
+int comm_stats_push(const SlabComm& c, const double* sums, int count, cudaStream_t s) {
   DD_CHECK(count <= SLAB_GATHER_DOUBLES, DDPM3D_ERR_ARG, "peer path: statistics record too large (batch > 8)");
   PushArgs a{};
   for (int r = 0; r < c.world; ++r) a.box[r] = c.peer_mailbox[r];
-  a.world = c.world; a.rank = c.rank; a.count = count; a.seq = seq;
-  stats_push_kernel<<<c.world, 64, 0, s>>>(sums, a);
+  a.world = c.world; a.rank = c.rank; a.count = count;
+  stats_push_kernel<<<1, 256, 0, s>>>(sums, a);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }
 
-const double* comm_stats_slot(const SlabComm& c, uint32_t seq) {
-  return reinterpret_cast<const double*>((const char*)c.mailbox + SLAB_FLAGS_BYTES) + (size_t)(seq & 1u) * SLAB_MAX_RANKS * SLAB_GATHER_DOUBLES;
-}
+const double* comm_stats_slots(const SlabComm& c) { return reinterpret_cast<const double*>((const char*)c.mailbox + SLAB_FLAGS_BYTES); }
 const uint32_t* comm_stats_flags(const SlabComm& c) { return reinterpret_cast<const uint32_t*>(c.mailbox) + SLAB_F_STATS; }
+const uint32_t* comm_stats_seq(const SlabComm& c) { return reinterpret_cast<const uint32_t*>(c.mailbox) + SLAB_F_STATS_SEQ; }
 
 }  // namespace ddpm3d

@@ -31,12 +31,14 @@ struct SlabComm {
   unsigned char peer_ws_handle[2][64] = {};
   bool peer_ws_open[2] = {false, false};
   void* ipc_stage = nullptr;               // device staging for the handle all-gather
-  uint32_t halo_seq = 0, stats_seq = 0;    // identical on every rank (same call sequence)
+  // the exchange sequence numbers live in the mailbox (device side, incremented by the flag kernels themselves), so a
+  // sharded step can be captured in a CUDA graph and replayed
   bool halo_p2p() const { return p2p && (rank == 0 || peer_ws[0]) && (rank + 1 == world || peer_ws[1]); }
 };
 // mailbox layout
 constexpr size_t SLAB_FLAGS_BYTES = 4096;
 constexpr int SLAB_F_READY_UP = 0, SLAB_F_READY_DOWN = 1, SLAB_F_CONSUMED_UP = 2, SLAB_F_CONSUMED_DOWN = 3, SLAB_F_STATS = 8;
+constexpr int SLAB_F_HALO_SEQ = 64, SLAB_F_STATS_SEQ = 65;  // local counters (never written by peers)
 inline size_t slab_mailbox_bytes() { return SLAB_FLAGS_BYTES + (size_t)2 * SLAB_MAX_RANKS * SLAB_GATHER_DOUBLES * sizeof(double); }
 
 int comm_unique_id(void* out128);
@@ -55,19 +57,20 @@ int comm_allgather_slabs(const SlabComm& c, const void* send, void* recv, int B,
 // collective (every rank of the communicator): allocate + exchange + map the mailboxes
 int comm_peer_init(SlabComm* c);
 // collective: make sure the z-neighbours' workspaces (`ws`, same size on every rank) are mapped; re-maps after a
-// re-allocation anywhere.  Synchronises the stream.
-int comm_peer_sync_ws(SlabComm* c, void* ws, cudaStream_t s);
+// re-allocation anywhere (*changed is set: captured graphs hold the old addresses).  Synchronises the stream.
+int comm_peer_sync_ws(SlabComm* c, void* ws, cudaStream_t s, bool* changed);
 void comm_peer_destroy(SlabComm* c);
-// halo handshake, one-thread kernels.  pre: tell the neighbours that every halo up to seq - 1 has been consumed (all
-// earlier kernels of this stream are done) and wait until they have consumed theirs -- after it this rank may store
-// into their halo planes.  post: tell the neighbours that the boundary planes of exchange `seq` are in their halo
-// planes and wait for theirs.
-int comm_halo_pre(const SlabComm& c, uint32_t seq, cudaStream_t s);
-int comm_halo_post(const SlabComm& c, uint32_t seq, cudaStream_t s);
-// statistics: store `count` doubles into slot [seq & 1][rank] of every rank's mailbox and raise this rank's flag there;
-// the finalize kernel waits for all `world` flags (comm_stats_slot / comm_stats_flags give it the addresses)
-int comm_stats_push(const SlabComm& c, const double* sums, int count, uint32_t seq, cudaStream_t s);
-const double* comm_stats_slot(const SlabComm& c, uint32_t seq);
-const uint32_t* comm_stats_flags(const SlabComm& c);
+// halo handshake, one-thread kernels.  pre: start exchange seq = ++halo_seq; tell the neighbours that every halo up to
+// seq - 1 has been consumed (all earlier kernels of this stream are done) and wait until they have consumed theirs --
+// after it this rank may store into their halo planes.  post: tell the neighbours that the boundary planes of exchange
+// seq are in their halo planes and wait for theirs.
+int comm_halo_pre(const SlabComm& c, cudaStream_t s);
+int comm_halo_post(const SlabComm& c, cudaStream_t s);
+// statistics: seq = ++stats_seq; store `count` doubles into slot [seq & 1][rank] of every rank's mailbox and raise this
+// rank's flag there.  The finalize kernel reads stats_seq, waits for all `world` flags and sums the slots.
+int comm_stats_push(const SlabComm& c, const double* sums, int count, cudaStream_t s);
+const double* comm_stats_slots(const SlabComm& c);        // [2][SLAB_MAX_RANKS][SLAB_GATHER_DOUBLES]
+const uint32_t* comm_stats_flags(const SlabComm& c);      // [world]
+const uint32_t* comm_stats_seq(const SlabComm& c);
 
 }  // namespace ddpm3d

@@ -261,13 +261,16 @@ __global__ void __launch_bounds__(1024) gn_reduce_local_kernel(const double* __r
 // finalize from the all-gathered per-rank sums: gathered[world][B][32][2], summed in rank order
 __global__ void __launch_bounds__(1024) gn_finalize_multi_kernel(const double* gathered, int world, int B, int Ctot,
                                                                  int64_t rank_stride, const uint32_t* __restrict__ flags,
-                                                                 uint32_t seq, double inv_count, const float* __restrict__ gamma,
+                                                                 const uint32_t* __restrict__ seq_ptr, int64_t parity_stride,
+                                                                 double inv_count, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, const float* __restrict__ film,
                                                                  int64_t film_stride, const float* __restrict__ pre_add,
                                                                  int64_t pre_stride, float* __restrict__ ab) {
   __shared__ float s_mean[32], s_rstd[32];
   const int b = blockIdx.x;
   if (flags) {  // peer path: every rank stores its sums into this rank's mailbox and then raises flags[rank] to seq
+    const uint32_t seq = *seq_ptr;  // incremented by this rank's push kernel (earlier in the stream)
+    gathered += (int64_t)(seq & 1u) * parity_stride;
     if (threadIdx.x < world) {
       const long long t0 = clock64();
       uint32_t v;
@@ -707,7 +710,7 @@ int gn_finalize_apply(const GnArgs& a, cudaStream_t s) {
   const int Ctot = a.C[0] + a.C[1];
   DD_CHECK(a.gathered != nullptr && a.world >= 1, DDPM3D_ERR_STATE, "groupnorm: gathered statistics missing");
   gn_finalize_multi_kernel<<<a.B, 1024, 0, s>>>(a.gathered, a.world, a.B, Ctot, a.gather_stride ? a.gather_stride : (int64_t)a.B * 64,
-                                                a.gather_flags, a.gather_seq, a.inv_count_global, a.gamma, a.beta, a.film,
+                                                a.gather_flags, a.gather_seq, a.gather_parity_stride, a.inv_count_global, a.gamma, a.beta, a.film,
                                                 a.film_stride, a.pre_add, a.pre_stride, a.ab);
   DD_CUDA(cudaGetLastError());
   return gn_apply_any(a, s);

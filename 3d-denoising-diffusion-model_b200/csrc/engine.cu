@@ -517,8 +517,7 @@ struct Run {
     *peer_lo = *peer_hi = nullptr;
     if (arena.dry) return DDPM3D_OK;
     prof_begin(10, 0.0);
-    const uint32_t seq = ++c.halo_seq;
-    int r = comm_halo_pre(c, seq, s);
+    int r = comm_halo_pre(c, s);
     prof_end();
     DD_TRY(r);
     const size_t bstride = (size_t)(Z + 2) * plane_bytes;
@@ -534,7 +533,7 @@ struct Run {
     launches += 1;
     if (arena.dry) return DDPM3D_OK;
     prof_begin(10, bytes);
-    const int r = comm_halo_post(ctx->slab, ctx->slab.halo_seq, s);
+    const int r = comm_halo_post(ctx->slab, s);
     prof_end();
     return r;
   }
@@ -652,12 +651,12 @@ struct Run {
         prof_end();
         prof_begin(11, (double)ctx->slab.world * B * 64 * sizeof(double));
         if (peer) {  // every rank stores its sums into every mailbox; the finalize kernel waits for the flags
-          const uint32_t seq = ++ctx->slab.stats_seq;
-          r = comm_stats_push(ctx->slab, sums, B * 64, seq, s);
-          g.gathered = comm_stats_slot(ctx->slab, seq);
+          r = comm_stats_push(ctx->slab, sums, B * 64, s);
+          g.gathered = comm_stats_slots(ctx->slab);
           g.gather_stride = SLAB_GATHER_DOUBLES;
+          g.gather_parity_stride = (int64_t)SLAB_MAX_RANKS * SLAB_GATHER_DOUBLES;
           g.gather_flags = comm_stats_flags(ctx->slab);
-          g.gather_seq = seq;
+          g.gather_seq = comm_stats_seq(ctx->slab);
         } else {
           r = comm_allgather_f64(ctx->slab, sums, gathered, (size_t)B * 64, s);
           g.gathered = gathered;
@@ -1048,7 +1047,33 @@ int ensure_workspace(ddpm3d_ctx* ctx, int B, int Z, int H, int W) {
 // rank reaches it at the start of every sharded call (same call sequence on all ranks).
 int sync_peers(ddpm3d_ctx* ctx, cudaStream_t s) {
   if (!ctx->slab.active() || !ctx->slab.p2p || !ctx->slab_p2p) return DDPM3D_OK;
-  return comm_peer_sync_ws(&ctx->slab, ctx->ws, s);
+  bool changed = false;
+  DD_TRY(comm_peer_sync_ws(&ctx->slab, ctx->ws, s, &changed));
+  if (changed) {  // captured graphs hold the old peer addresses
+    for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+    ctx->graphs.clear();
+    ctx->graph_launches.clear();
+  }
+  return DDPM3D_OK;
+}
+
+// A sharded call may be captured in a CUDA graph when nothing in it goes through NCCL: peer path, equal slabs, no
+// attention blocks (their K/V all-gather is an ncclAllGather)
+bool slab_capturable(const ddpm3d_ctx* ctx, int B, int Z) {
+  const SlabComm& c = ctx->slab;
+  if (!ctx->slab_p2p || !c.halo_p2p() || c.z_total != c.world * Z || c.z_begin != c.rank * Z || B * 64 > SLAB_GATHER_DOUBLES) return false;
+  if (ctx->cfg.in_channels != 1 || ctx->cfg.unconditional) return false;  // (the planar pack kernel exchanges through NCCL)
+  auto has_attn = [](const std::vector<Layer>& blk) {
+    for (const Layer& L : blk)
+      if (L.kind == L_ATTN) return true;
+    return false;
+  };
+  for (auto& blk : ctx->input_blocks)
+    if (has_attn(blk)) return false;
+  if (has_attn(ctx->middle)) return false;
+  for (auto& blk : ctx->output_blocks)
+    if (has_attn(blk)) return false;
+  return true;
 }
 
 int forward_launch(ddpm3d_ctx* ctx, const float* x, const float* low, const float* t, const int64_t* y, float* out, int B,
@@ -1066,8 +1091,11 @@ int forward_launch(ddpm3d_ctx* ctx, const float* x, const float* low, const floa
 
 // Runs `body` (which enqueues work on `s`) either directly or through a cached CUDA graph.
 template <typename F>
-int run_graphed(ddpm3d_ctx* ctx, const GraphKey& key, cudaStream_t s, F&& body) {
-  if (!ctx->use_graph || ctx->profile || ctx->slab.active()) {  // NCCL calls are issued eagerly, in rank-identical order
+int run_graphed(ddpm3d_ctx* ctx, const GraphKey& key0, cudaStream_t s, F&& body) {
+  GraphKey key = key0;  // a sharded step bakes the slab position and the peer addresses in
+  if (ctx->slab.active()) key.i[2] = ((int64_t)1 << 62) | ((int64_t)ctx->slab.z_begin << 31) | (int64_t)ctx->slab.z_total;
+  // NCCL calls are issued eagerly, in rank-identical order; the peer path has none and replays like any other step
+  if (!ctx->use_graph || ctx->profile || (ctx->slab.active() && !slab_capturable(ctx, key.B, key.Z))) {
     int n = 0;
     DD_TRY(body(s, &n));
     ctx->launches += n;

@@ -92,11 +92,11 @@ struct GnArgs {
   const double* gathered = nullptr;
   int world = 1;
   double inv_count_global = 0.0;
-  // peer path: gathered is this rank's mailbox slot (rank stride gather_stride doubles); the finalize kernel first waits
-  // until gather_flags[r] >= gather_seq for every rank r
-  int64_t gather_stride = 0;
+  // peer path: gathered is this rank's mailbox (rank stride gather_stride doubles); the finalize kernel first waits
+  // until gather_flags[r] >= *gather_seq for every rank r
+  int64_t gather_stride = 0, gather_parity_stride = 0;  // `gathered` holds two such slots, selected by (*gather_seq & 1)
   const uint32_t* gather_flags = nullptr;
-  uint32_t gather_seq = 0;
+  const uint32_t* gather_seq = nullptr;                 // device counter, incremented by the push kernel
   // peer path: base (batch 0) of the upper neighbour's trailing halo plane / the lower neighbour's leading halo plane of
   // the tensor that corresponds to `out` (same layout), or NULL
   void* peer_halo[2] = {nullptr, nullptr};
