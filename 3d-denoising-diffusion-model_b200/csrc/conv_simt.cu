@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(SimtParams p) {
         const int kk = k - p.kbeg[s];
         const int C = p.C[s];
         int tap, ci;
-        if (s == 0 && p.taps == 27) { tap = kk / C; ci = kk - tap * C; } else { tap = 13; ci = kk; }
+        if (s == 0 && p.taps > 1) { tap = kk / C; ci = kk - tap * C; if (p.taps == 9) tap += 9; } else { tap = 13; ci = kk; }
         const int dz = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
         const int st = s == 0 ? p.stride : 1;
         const int Hs = s == 0 ? p.Hin : p.Ho, Ws = s == 0 ? p.Win : p.Wo;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(SimtParams p) {
           const int kk = k - p.kbeg[s];
           const int C = p.C[s];
           int tap, ci;
-          if (s == 0 && p.taps == 27) { tap = kk / C; ci = kk - tap * C; } else { tap = 13; ci = kk; }
+          if (s == 0 && p.taps > 1) { tap = kk / C; ci = kk - tap * C; if (p.taps == 9) tap += 9; } else { tap = 13; ci = kk; }
           const int dz = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
           const int st = s == 0 ? p.stride : 1;
           const int Hs = s == 0 ? p.Hin : p.Ho, Ws = s == 0 ? p.Win : p.Wo;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(SimtParams p) {
 }  // namespace
 
 int conv_simt(const ConvArgs& a, cudaStream_t s) {
-  DD_CHECK(a.taps == 27 || a.taps == 1, DDPM3D_ERR_ARG, "conv: taps must be 27 or 1");
+  DD_CHECK(a.taps == 27 || a.taps == 9 || a.taps == 1, DDPM3D_ERR_ARG, "conv: taps must be 27, 9 (3x3 in the plane, dims = 2) or 1");
   DD_CHECK(a.stride_hw == 1 || a.stride_hw == 2, DDPM3D_ERR_ARG, "conv: stride_hw must be 1 or 2");
   DD_CHECK(a.n_extra >= 0 && a.n_extra <= 2, DDPM3D_ERR_ARG, "conv: at most two extra sources");
   SimtParams p{};

@@ -199,8 +199,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           const CUtensorMap* map;
           int c0, dz = 0, dh = 0, dw = 0;
           if (kk < p.n_main_steps) {
-            const int tap = p.taps == 27 ? kk / p.chunks[0] : 13;
-            c0 = (kk - (p.taps == 27 ? tap * p.chunks[0] : 0)) * BK;
+            int tap = p.taps > 1 ? kk / p.chunks[0] : 13;
+            c0 = (kk - (p.taps > 1 ? tap * p.chunks[0] : 0)) * BK;
+            if (p.taps == 9) tap += 9;  // a 3x3 kernel of a dims = 2 network: the centre z-plane of the 27-tap numbering
             dz = tap / 9 - 1 + p.zoff; dh = (tap / 3) % 3 - 1; dw = tap % 3 - 1;
             map = &mapA0;
           } else {
@@ -433,6 +434,8 @@ struct StripParams {
   int Wb, Wp, nbands, nh, tiles_per_band, nNt, num_tiles, zoff;
   int NV;            // voxels (padded-flattened positions) per tile = the MMA N: a multiple of 16, <= 256
   int nsrc, chunks[3], n_macro_main, n_macro, Cin;
+  int dz0;           // z offset of the first tap plane: -1 for 3x3x3, 0 for the 3x3 kernels of a dims = 2 network
+  int taps;          // 27 or 9
   uint32_t strip_bytes, strip_stride;  // bytes delivered per strip / smem distance between the two strip buffers
   const float* bias;
   const void* res;   // residual (applied after the transpose, voxel-major) or NULL
@@ -519,7 +522,7 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
           const uint32_t dst = smem_base + sb * p.strip_stride;
           if (m < p.n_macro_main) {
             const int dz = m / p.chunks[0], ch = m - dz * p.chunks[0];
-            tma_load_5d(dst, &mapA0, sfull(sb), ch * BK, w0 - 1, h_s, z + dz - 1 + p.zoff, b);
+            tma_load_5d(dst, &mapA0, sfull(sb), ch * BK, w0 - 1, h_s, z + dz + p.dz0 + p.zoff, b);
           } else {
             const int e = m - p.n_macro_main;
             if (e < p.chunks[1]) tma_load_5d(dst, &mapA1, sfull(sb), e * BK, w0 - 1, h_s, z, b);
@@ -544,7 +547,7 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
             kcol = dz * 9 * p.Cin + ch * BK;  // + t * Cin per in-plane tap
           } else {
             ntaps = 1;
-            kcol = 27 * p.Cin + (m - p.n_macro_main) * BK;
+            kcol = p.taps * p.Cin + (m - p.n_macro_main) * BK;
           }
           for (int t = 0; t < ntaps; ++t) {
             mbar_wait(wempty(ws), wph ^ 1);
@@ -1003,7 +1006,7 @@ struct StripPlan {
 };
 
 bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
-  if (!a.strip_allowed || !is_half_dt(a.dt) || a.taps != 27 || a.stride_hw != 1 || a.out_planar_f32) return false;
+  if (!a.strip_allowed || !is_half_dt(a.dt) || (a.taps != 27 && a.taps != 9) || a.stride_hw != 1 || a.out_planar_f32) return false;
   if (a.Cout % 128 != 0 || a.main.C % BK != 0) return false;
   for (int e = 0; e < a.n_extra; ++e)
     if (a.extra[e].C % BK != 0) return false;
@@ -1063,9 +1066,11 @@ int conv_tc_strip(ConvArgs& a, const StripPlan& plan, bool chsum, cudaStream_t s
   p.nsrc = 1 + a.n_extra;
   p.chunks[0] = a.main.C / BK;
   p.Cin = a.main.C;
-  p.n_macro_main = 3 * p.chunks[0];
+  p.taps = a.taps;
+  p.dz0 = a.taps == 27 ? -1 : 0;
+  p.n_macro_main = (a.taps == 27 ? 3 : 1) * p.chunks[0];
   p.n_macro = p.n_macro_main;
-  int Ktot = 27 * a.main.C;
+  int Ktot = a.taps * a.main.C;
   for (int e = 0; e < a.n_extra; ++e) {
     p.chunks[1 + e] = a.extra[e].C / BK;
     p.n_macro += p.chunks[1 + e];
@@ -1118,9 +1123,9 @@ size_t conv_tc_scratch_bytes(const ConvArgs& a0) {
 
 bool conv_tc_eligible(const ConvArgs& a) {
   if (!is_half_dt(a.dt) || !is_half_dt(a.io_dt()) || a.out_planar_f32) return false;
-  if (a.stride_hw != 1 && !(a.stride_hw == 2 && a.taps == 27 && a.in_zpad == 0)) return false;
+  if (a.stride_hw != 1 && !(a.stride_hw == 2 && a.taps != 1 && a.in_zpad == 0)) return false;
   if (a.dt == DDPM3D_FP16 && a.io_dt() != DDPM3D_FP16) return false;  // built: bf16/bf16, bf16/fp16, fp16/fp16
-  if (a.taps != 27 && a.taps != 1) return false;
+  if (a.taps != 27 && a.taps != 9 && a.taps != 1) return false;
   if (a.main.C % BK != 0 || a.Cout % 64 != 0) return false;
   for (int e = 0; e < a.n_extra; ++e)
     if (a.extra[e].C % BK != 0) return false;

@@ -30,6 +30,7 @@ struct DevConv {
   void* w = nullptr;      // dt [Cout][Ktot]
   float* bias = nullptr;  // [Cout]
   int Ktot = 0;
+  int taps = 27;          // 27 (Conv3d 3x3x3), 9 (Conv2d 3x3 of a dims = 2 network) or 1
 };
 
 struct Layer {
@@ -388,8 +389,10 @@ int pack_conv(ddpm3d_ctx* ctx, int dt, const std::string& wkey, const std::strin
   DD_CHECK(w && w->loaded, DDPM3D_ERR_MISSING, "missing state_dict tensor: " + wkey);
   DD_CHECK(b && b->loaded, DDPM3D_ERR_MISSING, "missing state_dict tensor: " + bkey);
   const int64_t Cout = w->shape[0], Cin = w->shape[1];
-  // dims = 2 (unet.py:396-716 with Conv2d): the images run through the same kernels as (B, C, 1, H, W) volumes
-  const bool flat2d = taps == 27 && w->shape.size() == 4;
+  // dims = 2 (unet.py:396-716 with Conv2d): the images run through the same kernels as (B, C, 1, H, W) volumes, with
+  // the 9 in-plane taps only (k = tap9 * Cin + ci)
+  if (taps == 27 && w->shape.size() == 4) taps = 9;
+  out->taps = taps;
   const Param* sw = nullptr;
   const Param* sb = nullptr;
   int64_t Cs = 0;
@@ -407,11 +410,7 @@ int pack_conv(ddpm3d_ctx* ctx, int dt, const std::string& wkey, const std::strin
   std::vector<float> packed((size_t)(Cout * Ktot), 0.f);
   for (int64_t co = 0; co < Cout; ++co) {
     float* row = packed.data() + co * Ktot;
-    if (flat2d) {  // a 3x3 kernel is the centre z-plane (taps 9..17) of a 3x3x3 kernel whose other planes are zero
-      const float* src = w->host.data() + co * Cin * 9;
-      for (int64_t ci = 0; ci < Cin; ++ci)
-        for (int t = 0; t < 9; ++t) row[(int64_t)(9 + t) * Cin + ci] = src[ci * 9 + t];
-    } else {
+    {
       const float* src = w->host.data() + co * Cin * taps;
       for (int64_t ci = 0; ci < Cin; ++ci)
         for (int t = 0; t < taps; ++t) row[(int64_t)t * Cin + ci] = src[ci * taps + t];
@@ -574,7 +573,7 @@ struct Run {
     a.B = B;
     a.Z = Z;
     if (!ctx->fuse_stats) a.chsum_out = nullptr;
-    if (a.taps == 27) a.in_zpad = zp;
+    if (a.taps != 1) a.in_zpad = zp;
     a.splitk_allowed = ctx->split_k;
     a.cluster_allowed = ctx->cluster;
     a.strip_allowed = ctx->strip;
@@ -726,7 +725,7 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   c.dt = dt;
   c.dt_io = dts;
   c.main = {h1, Cin};
-  c.taps = 27;
+  c.taps = L.c1.taps;
   c.w = L.c1.w; c.bias = L.c1.bias;
   c.out = h2; c.Ho = Ho; c.Wo = Wo; c.Cout = L.cout;
   c.chsum_out = R.alloc_chsum(L.cout);
@@ -753,7 +752,7 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   c2.dt = dt;
   c2.dt_io = dts;
   c2.main = {h3, L.cout};
-  c2.taps = 27;
+  c2.taps = L.c2.taps;
   c2.w = L.c2.w; c2.bias = L.c2.bias;
   c2.out = out->p; c2.Ho = Ho; c2.Wo = Wo; c2.Cout = L.cout;
   if (L.skip_conv) {  // skip_connection (1x1x1) folded into the same accumulation, reading the concat halves in place
@@ -766,7 +765,7 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   } else {
     c2.residual = src[0].p;
     c2.res_mode = L.down ? RES_POOL : (L.up ? RES_UP : RES_SAME);
-    if (!L.up && !L.down) c2.w_ld = 27 * L.cout + L.cout;  // skip the appended unit block
+    if (!L.up && !L.down) c2.w_ld = L.c2.taps * L.cout + L.cout;  // skip the appended unit block
   }
   c2.chsum_out = out_cs;
   DD_TRY(R.conv(c2));
@@ -862,7 +861,7 @@ int run_conv_layer(Run& R, const Layer& L, const Act& x, Act* out) {
     in = u;
   }
   ConvArgs c{};
-  c.dt = dt; c.main = {in, L.cin}; c.taps = 27; c.stride_hw = L.kind == L_UPCONV ? 1 : L.stride_hw;
+  c.dt = dt; c.main = {in, L.cin}; c.taps = L.c1.taps; c.stride_hw = L.kind == L_UPCONV ? 1 : L.stride_hw;
   c.w = L.c1.w; c.bias = L.c1.bias; c.out = out->p; c.Ho = Ho; c.Wo = Wo; c.Cout = L.cout;
   DD_TRY(R.conv(c));
   R.arena.off = mark;
@@ -954,7 +953,7 @@ int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, cons
   }
   DD_CHECK(h.H == H && h.W == W && h.C == ctx->out_norm_ch, DDPM3D_ERR_STATE, "internal: output geometry mismatch");
   // h.type(x.dtype); out = GN32 -> SiLU -> conv (fp32)                 unet.py:1043-1044
-  if (ctx->head_tc && is_half_dt(ctx->dts) && !R.zp && ctx->conv_path != 1 &&
+  if (ctx->head_tc && is_half_dt(ctx->dts) && !R.zp && ctx->conv_path != 1 && !ctx->two_d() &&
       conv_head_tc_eligible(ctx->dts, h.C, ctx->cfg.out_channels)) {
     // 16-bit modes: one kernel applies the GroupNorm affine + SiLU while staging and runs the conv on tcgen05
     GnArgs g{};
@@ -982,7 +981,7 @@ int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, cons
   DD_TRY(R.gn(g));
   DD_TRY(R.halo(hn, H, W, h.C, sizeof(float)));
   ConvArgs c{};
-  c.dt = DDPM3D_FP32; c.main = {hn, h.C}; c.taps = 27; c.w = ctx->out_conv.w; c.bias = ctx->out_conv.bias;
+  c.dt = DDPM3D_FP32; c.main = {hn, h.C}; c.taps = ctx->out_conv.taps; c.w = ctx->out_conv.w; c.bias = ctx->out_conv.bias;
   c.out = out; c.out_planar_f32 = 1; c.Ho = H; c.Wo = W; c.Cout = ctx->cfg.out_channels;
   DD_TRY(R.conv(c));
   return DDPM3D_OK;

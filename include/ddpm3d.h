@@ -232,8 +232,9 @@ int ddpm3d_profile_read(ddpm3d_ctx* ctx, ddpm3d_prof_record* out, int cap);
  * dtype: DDPM3D_FP32 (float), DDPM3D_BF16 (__nv_bfloat16) or DDPM3D_FP16 (__half) for activations and conv weights.
  * Activations are [B][Z][H][W][C] (NDHWC).  These replace the torch ops behind nn.py:17-32. */
 
-/* 3x3x3 (taps=27) or 1x1x1 (taps=1) "same" convolution, stride (1,s,s) (nn.py:22-32; call sites
- * unet.py:185,211,219,222).  w: [Cout][taps*Cin] with k = tap*Cin + ci, tap = (dz*3+dh)*3+dw;
+/* 3x3x3 (taps=27), in-plane 3x3 (taps=9: the Conv2d of a dims = 2 network on one-plane volumes) or 1x1x1 (taps=1) "same"
+ * convolution, stride (1,s,s) (nn.py:22-32; call sites unet.py:185,211,219,222).  w: [Cout][taps*Cin] with
+ * k = tap*Cin + ci, tap = (dz*3+dh)*3+dw (taps=9: tap = dh*3+dw);
  * bias fp32 [Cout]; residual (optional, [B][Z][Ho][Wo][Cout]) is added in the epilogue.
  * path: 1 SIMT, 2 tcgen05 (bf16 / fp16, Cin%64==0, Cout%64==0; s==2 through element-strided TMA boxes), 3 / 4 the Cin==2 stem kernels
  * (3: tcgen05 tile per 128 voxels in the 16-bit modes, 4: CUDA cores). */

@@ -84,6 +84,27 @@ def test_strided_downsample_conv_tcgen05(Cin, Cout, shape, dt):
     assert max_rel(tc.float().cpu(), simt.float().cpu()) <= 1.5 * ROUND_TOL[dt]
 
 
+@pytest.mark.parametrize("Cin,Cout,shape,stride", [(64, 64, (2, 1, 32, 32), 1), (128, 256, (1, 1, 64, 64), 1), (64, 128, (1, 3, 16, 24), 1),
+                                                   (128, 128, (1, 1, 32, 32), 2), (64, 128, (1, 4, 160, 192), 1)])
+@pytest.mark.parametrize("dt", [N.BF16, N.FP16])
+def test_conv2d_nine_taps(Cin, Cout, shape, stride, dt):
+    """The Conv2d layers of the dims = 2 networks (unet.py:396-716): 9 in-plane taps on one-plane volumes (Z > 1 =
+    the same 3x3 kernel on every plane), on the tcgen05 kernels (brick, strip for the last shape, element-strided
+    boxes for stride 2) and on the CUDA-core kernel, against F.conv2d."""
+    B, Z, H, W = shape
+    tdt = TDT[dt]
+    g = torch.Generator().manual_seed(Cin + Cout + W)
+    x = torch.randn((B, Cin, Z, H, W), generator=g).to(tdt).float()
+    w = (torch.randn((Cout, Cin, 3, 3), generator=g) / np.sqrt(Cin * 9)).to(tdt).float()
+    b = torch.randn(Cout, generator=g)
+    ref = torch.stack([F.conv2d(x[:, :, z], w, b, stride=stride, padding=1) for z in range(Z)], dim=2)
+    args = (to_cl(x, tdt), pack_weight(w, tdt), b.to(DEV), None, B, Z, H, W, Cin, Cout, 9, stride)
+    tc = conv3d(dt, 2, *args)
+    simt = conv3d(dt, 1, *args)
+    assert max_rel(from_cl(tc), ref) <= ROUND_TOL[dt]
+    assert max_rel(from_cl(simt), ref) <= ROUND_TOL[dt]
+
+
 def test_ineligible_shapes_are_rejected():
     x = torch.zeros((1, 2, 4, 4, 32), device=DEV, dtype=torch.bfloat16)
     w = torch.zeros((64, 27 * 32), device=DEV, dtype=torch.bfloat16)
