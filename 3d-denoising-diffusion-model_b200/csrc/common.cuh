@@ -69,6 +69,12 @@ inline int sm_count() {
   return c;
 }
 
+// programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may begin
+// before its predecessor in the stream has finished; pdl_wait() blocks until that predecessor has completed and its
+// writes are visible.  pdl_launch_dependents() in the predecessor lets the dependent grid be scheduled right away.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- scalar conversions ------------------------------------------------------------------
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }

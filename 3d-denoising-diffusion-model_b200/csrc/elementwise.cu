@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(1024) gn_finalize_kernel(const double* __restr
   __shared__ float s_mean[32], s_rstd[32];
   const int b = blockIdx.x;
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 1024 threads: one warp per group
+  pdl_launch_dependents();
   const double* ps = partials + (((int64_t)b * 32 + g) * 2) * n_chunks;
   const double* pq = ps + n_chunks;
   double s = 0.0, q = 0.0;
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(1024) gn_finalize_multi_kernel(const double* g
                                                                  int64_t pre_stride, float* __restrict__ ab) {
   __shared__ float s_mean[32], s_rstd[32];
   const int b = blockIdx.x;
+  pdl_launch_dependents();
   if (flags) {  // peer path: every rank stores its sums into this rank's mailbox and then raises flags[rank] to seq
     const uint32_t seq = *seq_ptr;  // incremented by this rank's push kernel (earlier in the stream)
     gathered += (int64_t)(seq & 1u) * parity_stride;
@@ -359,6 +361,7 @@ __global__ void __launch_bounds__(128) gn_finalize_chsum_kernel(const float* __r
   __shared__ double sh[2][128];
   const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int Ctot = C0 + C1, gpc = Ctot / 32;
+  pdl_launch_dependents();  // the apply kernel may start its prologue now; it waits for this grid before reading `ab`
   chsum_group_sums(cs0, cs1, bias0, bias1, C0, C1, P, n_vox, g, b, sh);
   const double mean = sh[0][0] * inv_count;
   double var = sh[1][0] * inv_count - mean * mean;
@@ -430,6 +433,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const T* __restrict__ 
     if (phi && orow >= last_plane0) gn_put<T, TO, N>(phi + (int64_t)(orow - last_plane0) * Ctot, y);
   };
   float A[N], Bv[N];
+  pdl_wait();  // launched with programmatic stream serialisation: everything above overlapped the finalize kernel
   {
     const float* pa = ab + (int64_t)b * 2 * Ctot + v * N;
 #pragma unroll
@@ -569,9 +573,18 @@ static int gn_apply_launch(const GnArgs& a, cudaStream_t s) {
   dim3 grid(blocks, a.B);
   const T* s0 = (const T*)a.src[0];
   const T* s1 = (const T*)a.src[1];
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // may start while the finalize kernel is still running
+  attr[0].val.programmaticStreamSerializationAllowed = a.pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
 #define GN_LAUNCH(MODE, SILU) \
-  gn_apply_kernel<T, TO, MODE, SILU><<<grid, threads, 0, s>>>(s0, s1, a.C[0], a.C[1], a.Z, a.H, a.W, rows_per_block, a.ab, (TO*)a.out, a.out_zpad, \
-                                                              (TO*)a.peer_halo[0], (TO*)a.peer_halo[1])
+  DD_CUDA(cudaLaunchKernelEx(&cfg, gn_apply_kernel<T, TO, MODE, SILU>, s0, s1, a.C[0], a.C[1], a.Z, a.H, a.W, rows_per_block, \
+                             (const float*)a.ab, (TO*)a.out, a.out_zpad, (TO*)a.peer_halo[0], (TO*)a.peer_halo[1]))
   if (a.silu) {
     if (a.resample == RS_NONE) GN_LAUNCH(RS_NONE, true);
     else if (a.resample == RS_POOL) GN_LAUNCH(RS_POOL, true);

@@ -177,7 +177,7 @@ struct ddpm3d_ctx {
   size_t img_cap = 0;
   // options
   int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 1, fold_identity = 1, stem_tc = 1, head_v2 = 1,
-      head_tc = 1, slab_p2p = 1;
+      head_tc = 1, slab_p2p = 1, pdl = 1;
   float* splitk_buf = nullptr;  // fp32 partial tiles of split-K convolutions (sized by the dry run)
   size_t splitk_cap = 0, splitk_need = 0;
   cudaStream_t cap_stream = nullptr;
@@ -559,12 +559,20 @@ struct Run {
     cudaEventCreate(&e.b);
     e.kind = kind;
     e.work = work;
-    cudaEventRecord(e.a, s);
+    prof_record(e.a);
     ctx->prof.push_back(e);
   }
   void prof_end() {
     if (!ctx->profile || arena.dry) return;
-    cudaEventRecord(ctx->prof.back().b, s);
+    prof_record(ctx->prof.back().b);
+  }
+  // profile = 2: the step is captured like any other and the brackets become event-record NODES of the graph, so the
+  // times are those of the replayed graph (no eager launch gaps between the short kernels)
+  void prof_record(cudaEvent_t e) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &st);
+    if (st == cudaStreamCaptureStatusActive) cudaEventRecordWithFlags(e, s, cudaEventRecordExternal);
+    else cudaEventRecord(e, s);
   }
 
   float* alloc_chsum(int C) { return (float*)arena.alloc((size_t)B * chsum_slots() * C * 2 * sizeof(float)); }
@@ -620,6 +628,7 @@ struct Run {
   int gn(GnArgs& g) {
     g.B = B;
     g.Z = Z;
+    g.pdl = ctx->pdl;
     const int Ctot = g.C[0] + g.C[1];
     g.n_chunks = gn_chunks((int64_t)Z * g.H * g.W);
     g.partials = (double*)arena.alloc((size_t)B * g.n_chunks * 64 * sizeof(double));
@@ -1094,7 +1103,7 @@ int run_graphed(ddpm3d_ctx* ctx, const GraphKey& key0, cudaStream_t s, F&& body)
   GraphKey key = key0;  // a sharded step bakes the slab position and the peer addresses in
   if (ctx->slab.active()) key.i[2] = ((int64_t)1 << 62) | ((int64_t)ctx->slab.z_begin << 31) | (int64_t)ctx->slab.z_total;
   // NCCL calls are issued eagerly, in rank-identical order; the peer path has none and replays like any other step
-  if (!ctx->use_graph || ctx->profile || (ctx->slab.active() && !slab_capturable(ctx, key.B, key.Z))) {
+  if (!ctx->use_graph || ctx->profile == 1 || (ctx->slab.active() && !slab_capturable(ctx, key.B, key.Z))) {
     int n = 0;
     DD_TRY(body(s, &n));
     ctx->launches += n;
@@ -1573,7 +1582,7 @@ int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value) {
   const std::string n(name);
   if (n == "cuda_graph") ctx->use_graph = value != 0;
   else if (n == "conv_path") { DD_CHECK(value >= 0 && value <= 2, DDPM3D_ERR_ARG, "conv_path must be 0, 1 or 2"); ctx->conv_path = (int)value; }
-  else if (n == "profile") ctx->profile = value != 0;
+  else if (n == "profile") { DD_CHECK(value >= 0 && value <= 2, DDPM3D_ERR_ARG, "profile must be 0, 1 or 2"); ctx->profile = (int)value; }
   else if (n == "fuse_stats") ctx->fuse_stats = value != 0;
   else if (n == "split_k") ctx->split_k = value != 0;
   else if (n == "cluster") ctx->cluster = value != 0;
@@ -1583,6 +1592,7 @@ int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value) {
   else if (n == "head_v2") ctx->head_v2 = value != 0;
   else if (n == "head_tc") ctx->head_tc = value != 0;
   else if (n == "slab_p2p") ctx->slab_p2p = value != 0;
+  else if (n == "pdl") ctx->pdl = value != 0;
   else { set_error("unknown option: " + n); return DDPM3D_ERR_ARG; }
   // cached graphs bake the options in
   if (ctx->device >= 0) {
@@ -1618,6 +1628,11 @@ int ddpm3d_profile_read(ddpm3d_ctx* ctx, ddpm3d_prof_record* out, int cap) {
     cudaEventDestroy(ctx->prof[i].b);
   }
   ctx->prof.clear();
+  if (ctx->profile == 2) {  // the captured graphs reference the events just destroyed
+    for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+    ctx->graphs.clear();
+    ctx->graph_launches.clear();
+  }
   return n;
 }
 

@@ -87,6 +87,8 @@ struct GnArgs {
   int dt_out = -1;                          // 16-bit output format when it differs from the input's (-1 = dt)
   int out_f32 = 0;
   int out_zpad = 0;                         // output tensor has this many halo planes on each side of Z (left untouched)
+  int pdl = 1;                              // the apply kernel is launched with programmatic stream serialisation (it follows
+                                            // the finalize kernel, which releases it early); 0 when another kernel sits between
   // cross-rank statistics (z-slab sharding): when gathered != NULL the finalize pass reads
   // gathered[world][B][32][2] (fp64 sums, rank order) instead of the local partials
   const double* gathered = nullptr;

@@ -12,7 +12,8 @@ UNet (BASELINE.json configs[1]): one UNet evaluation + the posterior / noise upd
              step's inputs coming from pinned host memory and the sample read back to the host,
              every step, inside the timed region.
 * `roofline`: the dominant kernel class (the 3x3x3 implicit-GEMM convolution) from a profiled pass
-             of the same step (CUDA events around every launch on the launching stream).
+             of the same step: CUDA-event pairs around every operator, recorded as nodes of the replayed
+             CUDA graph on the launching stream.
 * `cpu_baseline` / `--impl reference`: the reference's own CPU implementation (its unmodified modules staged under
              oracle/_ref by `python -m oracle.build_ref`; the oracle's restatement where that is absent) on the host
              cores: full 96^3 fp32 p_sample steps.
@@ -265,8 +266,10 @@ def library_bar(dev, sd):
     return {"ms_per_eval": e0.elapsed_time(e1) / 3, "kind": kind}
 
 
-def profile_breakdown(model, run, steps):
-    model.set_option("profile", 1)
+def profile_breakdown(model, run, steps, in_graph=False):
+    """Operator times of `run` from the library's profile mode.  in_graph: the step is captured and replayed as in the
+    timed region and the event pairs are nodes of that graph -- the records then describe ONE step (the last replay)."""
+    model.set_option("profile", 2 if in_graph else 1)
     run()
     recs = model.profile_read()
     model.set_option("profile", 0)
@@ -514,7 +517,9 @@ def main():
     roofline = None
     breakdown = {}
     if rank == 0:
-        breakdown = profile_breakdown(model, lambda: model._sample_loop(diffusion, x_T, kw, None, 1, True, n_steps=2), 2)
+        # profiled pass = the same captured step, replayed 4 times; the records are those of the last replay
+        breakdown = profile_breakdown(model, lambda: model._sample_loop(diffusion, x_T, kw, None, 1, True, n_steps=4), 1,
+                                      in_graph=True)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

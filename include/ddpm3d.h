@@ -200,7 +200,9 @@ int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total);
 /* ---- knobs and introspection ------------------------------------------------------------------ */
 /* "cuda_graph" (0/1, default 1): replay one captured graph per UNet evaluation;
  * "conv_path" (0 = auto, 1 = force the generic CUDA-core kernel everywhere, 2 = same as 0);
- * "profile" (0/1): record a CUDA-event pair around every kernel launch (disables graphs);
+ * "profile" (0/1/2): 1 = record a CUDA-event pair around every operator, launched eagerly (graphs off: the short kernels
+ * then include launch gaps); 2 = the step is captured as usual and the brackets become event-record nodes of the graph,
+ * so ddpm3d_profile_read returns the operator times of the LAST replay of the captured graph;
  * "fuse_stats" (0/1, default 1): GroupNorm statistics come from per-channel sums accumulated in the producing
  * convolution's epilogue instead of a separate pass over the tensor;
  * "split_k" (0/1, default 1): convolutions with too few tiles to fill the GPU deal their k-steps evenly to the CTAs
@@ -215,6 +217,8 @@ int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total);
  * "slab_p2p" (0/1, default 1; set before ddpm3d_set_comm): z-slab sharding exchanges halo planes and GroupNorm sums through
  * peer-mapped memory (CUDA IPC over NVLink: the producing kernels store into the neighbours' halo planes, sequence-numbered
  * flags order the accesses) instead of NCCL send/recv and all-gather; needs equal slabs and peer access, else NCCL is used;
+ * "pdl" (0/1, default 1): the GroupNorm apply kernel is launched with programmatic stream serialisation so that its
+ * prologue overlaps the finalize kernel before it (griddepcontrol.wait / launch_dependents);
  * "head_tc" (0/1, default 1): 16-bit modes with 64 / 128 model channels: out.0 GroupNorm apply + SiLU + out.2 conv as one
  * tcgen05 kernel (the contraction over channels once per voxel, the 27 taps as a shifted sum); 0 = GroupNorm pass writing
  * fp32 + the CUDA-core head. */

@@ -10,7 +10,7 @@ from ddpm3d_b200 import script_util as su
 dev = torch.device("cuda", 0)
 shape = bench.PATCH
 opts = [a for a in sys.argv[1:] if "=" in a]
-pos = [a for a in sys.argv[1:] if "=" not in a]
+pos = [a for a in sys.argv[1:] if "=" not in a and not a.startswith("--")]
 if pos:
     z, h, w = (int(v) for v in pos[0].split(","))
     shape = (1, 1, z, h, w)
@@ -25,10 +25,23 @@ x = torch.randn(shape, generator=g).to(dev); low = torch.rand(shape, generator=g
 t = torch.tensor([500.0], device=dev)
 for _ in range(2):
     model(x, t, low_res=low)
-model.set_option("profile", 1)
-model(x, t, low_res=low)
-model.profile_read()
-model(x, t, low_res=low)
+# profile = 2: the evaluation is captured as usual, the event pairs are nodes of the graph; the records are those of the
+# last replay (profile = 1, eager launches, adds ~8 us of launch gap to every short kernel)
+mode = 1 if "--eager" in sys.argv else 2
+out = torch.empty((1, 2) + tuple(shape[2:]), device=dev)
+model.set_option("profile", mode)
+if mode == 2:
+    import ctypes as C
+    from ddpm3d_b200 import _native as N
+    def fwd():  # fixed output buffer: one graph key
+        N.check(N.lib().ddpm3d_unet_forward(model._ensure_ctx(), N.ptr(x), N.ptr(low), N.ptr(t), None, N.ptr(out), 1, shape[2], shape[3],
+                                            shape[4], N.current_stream_ptr(dev)))
+    for _ in range(4):
+        fwd()
+else:
+    model(x, t, low_res=low)
+    model.profile_read()
+    model(x, t, low_res=low)
 recs = model.profile_read()
 tot = sum(r[1] for r in recs)
 print(f"total {tot:.3f} ms over {len(recs)} launches")
