@@ -40,7 +40,7 @@ class ProfRecord(C.Structure):
 
 
 PROF_KINDS = ["conv_tcgen05", "conv_simt", "gn_stats", "gn_finalize", "groupnorm", "embedding", "update",
-              "attention", "misc", "conv_small", "halo_exchange", "gn_allgather"]
+              "attention", "misc", "conv_small", "halo_exchange", "gn_allgather", "empty_bracket"]
 
 _P = C.c_void_p
 _I = C.c_int

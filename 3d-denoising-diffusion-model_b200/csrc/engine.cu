@@ -899,6 +899,9 @@ int run_block(Run& R, const std::vector<Layer>& blk, const Act* src, int nsrc, A
 int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, const float* t, const int64_t* y, float* out,
                  int H, int W) {
   const int B = R.B, Z = R.Z;
+  // profiling: an empty bracket, so the reader knows what two back-to-back event records cost in this launch mode
+  R.prof_begin(12, 0.0);
+  R.prof_end();
   // time_embed + every emb_layers Linear (unet.py:1029-1033, 199-205)
   float* emb_silu = (float*)R.arena.alloc((size_t)B * ctx->ted * sizeof(float));
   R.emb_out = (float*)R.arena.alloc((size_t)B * std::max(ctx->emb_rows_total, 1) * sizeof(float));

@@ -527,6 +527,7 @@ def main():
             pass
         peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0  # kernel timed inside a long step
         which = "measured (sustained)" if "bf16_tflops_sustained" in peaks else "fallback"
+        empty = breakdown.pop("empty_bracket", None)  # two back-to-back event-record nodes: the floor of every bracket
         dom = "conv_tcgen05" if breakdown.get("conv_tcgen05", {}).get("ms", 0) > 0 else "conv_simt"
         d = breakdown[dom]
         achieved = d["work"] / (d["ms"] * 1e-3) / 1e12
@@ -539,6 +540,9 @@ def main():
                     "work_note": "algorithmic flops 2*M*Cout*(27*Cin + Cskip) of every tcgen05 conv launch; the unit-weight K "
                                  "block of folded identity skips is NOT counted",
                     "peak_source": which,
+                    "timing": "operator brackets are event-record nodes of the replayed CUDA graph; times are NOT corrected for "
+                              "the bracket floor (event_bracket_floor_ms: an empty bracket in the same graph)",
+                    "event_bracket_floor_ms": empty["ms"] if empty else None,
                     "share_of_step": d["ms"] / sum(b["ms"] for b in breakdown.values()),
                     "launches_per_step": d["launches"]}
         hbm = peaks.get("hbm_gbs", 6650.0)

@@ -227,8 +227,8 @@ int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value);
 int64_t ddpm3d_launch_count(const ddpm3d_ctx* ctx);
 /* After a profiled call: synchronises and writes up to `cap` records; returns the record count.
  * `kind`: 0 conv-tcgen05, 1 conv-simt, 2 gn-stats, 3 gn-finalize, 4 gn-apply, 5 embedding, 6 update,
- * 7 attention, 8 pack/resample/misc, 9 conv-small (stem / head direct convolutions), 10 halo exchange (NCCL), 11 GroupNorm
- * statistics all-gather (NCCL).  `work` = algorithmic flops (conv, attention) or bytes (others). */
+ * 7 attention, 8 pack/resample/misc, 9 conv-small (stem / head direct convolutions), 10 halo exchange, 11 GroupNorm
+ * statistics exchange, 12 an empty bracket (what two back-to-back event records cost in this launch mode).  `work` = algorithmic flops (conv, attention) or bytes (others). */
 typedef struct ddpm3d_prof_record { int32_t kind; int32_t pad_; float ms; float pad2_; double work; } ddpm3d_prof_record;
 int ddpm3d_profile_read(ddpm3d_ctx* ctx, ddpm3d_prof_record* out, int cap);
 
