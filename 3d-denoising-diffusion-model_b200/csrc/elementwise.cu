@@ -634,6 +634,7 @@ static int gn_stats_any(const GnArgs& a, cudaStream_t s) {
 }
 
 static int gn_apply_any(const GnArgs& a, cudaStream_t s) {
+  if (gn_apply_stream_eligible(a)) return gn_apply_stream(a, s);
   const int dto = a.dt_out < 0 ? a.dt : a.dt_out;  // 16-bit output format (block inputs are fp16, conv operands bf16)
   if (a.dt == DDPM3D_BF16) {
     if (a.out_f32) return gn_apply_launch<bf16, float>(a, s);

@@ -177,7 +177,7 @@ struct ddpm3d_ctx {
   size_t img_cap = 0;
   // options
   int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 1, fold_identity = 1, stem_tc = 1, head_v2 = 1,
-      head_tc = 1, slab_p2p = 1, pdl = 1;
+      head_tc = 1, slab_p2p = 1, pdl = 1, gn_stream = 1, gn_stream_mb = 48;
   float* splitk_buf = nullptr;  // fp32 partial tiles of split-K convolutions (sized by the dry run)
   size_t splitk_cap = 0, splitk_need = 0;
   cudaStream_t cap_stream = nullptr;
@@ -629,6 +629,8 @@ struct Run {
     g.B = B;
     g.Z = Z;
     g.pdl = ctx->pdl;
+    g.stream_allowed = ctx->gn_stream;
+    g.stream_min_mb = ctx->gn_stream_mb;
     const int Ctot = g.C[0] + g.C[1];
     g.n_chunks = gn_chunks((int64_t)Z * g.H * g.W);
     g.partials = (double*)arena.alloc((size_t)B * g.n_chunks * 64 * sizeof(double));
@@ -1596,6 +1598,8 @@ int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value) {
   else if (n == "head_tc") ctx->head_tc = value != 0;
   else if (n == "slab_p2p") ctx->slab_p2p = value != 0;
   else if (n == "pdl") ctx->pdl = value != 0;
+  else if (n == "gn_stream") ctx->gn_stream = value != 0;
+  else if (n == "gn_stream_mb") ctx->gn_stream_mb = (int)value;
   else { set_error("unknown option: " + n); return DDPM3D_ERR_ARG; }
   // cached graphs bake the options in
   if (ctx->device >= 0) {

@@ -87,6 +87,8 @@ struct GnArgs {
   int dt_out = -1;                          // 16-bit output format when it differs from the input's (-1 = dt)
   int out_f32 = 0;
   int out_zpad = 0;                         // output tensor has this many halo planes on each side of Z (left untouched)
+  int stream_allowed = 1;                   // large tensors: the TMA streaming apply kernel (gn_stream.cu)
+  int stream_min_mb = 48;                   // ... from this many MB of input on
   int pdl = 1;                              // the apply kernel is launched with programmatic stream serialisation (it follows
                                             // the finalize kernel, which releases it early); 0 when another kernel sits between
   // cross-rank statistics (z-slab sharding): when gathered != NULL the finalize pass reads
@@ -120,6 +122,9 @@ int gn_chsum_local(const GnArgs& a, double* sums, cudaStream_t s);  // same, fro
 int gn_finalize_apply(const GnArgs& a, cudaStream_t s);
 // statistics from the producers' channel sums: finalize + apply only (one read + one write of the tensor)
 int gn_forward_chsum(const GnArgs& a, cudaStream_t s);
+// apply pass of the large tensors as a TMA streaming kernel (16-bit in / out, no resampling, channel counts % 128 == 0)
+bool gn_apply_stream_eligible(const GnArgs& a);
+int gn_apply_stream(const GnArgs& a, cudaStream_t s);
 // statistics (from the channel sums when present, else a pass over the tensor) + the per-(b, c) affine a.ab, no apply
 int gn_finalize_only(const GnArgs& a, cudaStream_t s);
 

@@ -73,6 +73,34 @@ def test_groupnorm_film_silu(dt, C, shape, silu, film, resample):
     assert max_rel(from_cl(out), ref) <= tol
 
 
+@pytest.mark.parametrize("dt", [N.BF16, N.FP16])
+@pytest.mark.parametrize("C,shape,silu,film", [(128, (1, 64, 96, 96), 1, True), (256, (1, 47, 81, 81), 1, False),
+                                               (384, (2, 30, 48, 48), 0, True)])
+def test_groupnorm_large_tensors_streaming_apply(dt, C, shape, silu, film):
+    """Tensors of >= 48 MB take the TMA streaming apply kernel (gn_stream.cu): 64-row x 128-channel tiles through a
+    shared-memory ring, rewritten in place, stored back by TMA.  Ragged last tile (rows % 64 != 0), batch 2, several
+    128-channel chunks, with and without SiLU / FiLM; same bound as the small shapes."""
+    B, Z, H, W = shape
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn((B, C, Z, H, W), generator=g) * 2 + 0.5
+    gamma = 1 + 0.1 * torch.randn(C, generator=g)
+    beta = 0.1 * torch.randn(C, generator=g)
+    fm = torch.randn((B, 2 * C), generator=g) * 0.3 if film else None
+    tdt = TDT[dt]
+    xin = x.to(tdt).float()
+    ref = F.group_norm(xin, 32, gamma, beta, 1e-5)
+    if film:
+        ref = ref * (1 + fm[:, :C, None, None, None]) + fm[:, C:, None, None, None]
+    if silu:
+        ref = F.silu(ref)
+    out = torch.empty((B, Z, H, W, C), device=DEV, dtype=tdt)
+    xd, gd_, bd = to_cl(x, tdt), gamma.to(DEV), beta.to(DEV)
+    fd = fm.to(DEV).contiguous() if film else None
+    N.check(N.lib().ddpm3d_k_groupnorm(dt, N.ptr(xd), N.ptr(gd_), N.ptr(bd), N.ptr(fd), silu, 0, N.ptr(out), B, Z, H, W, C, stream()))
+    torch.cuda.synchronize()
+    assert max_rel(from_cl(out), ref) <= ROUND_TOL[dt]
+
+
 @pytest.mark.parametrize("ratio", [100.0, 1000.0])
 @pytest.mark.parametrize("C,shape", [(128, (1, 8, 24, 24)), (64, (2, 3, 6, 10)), (384, (1, 96, 12, 12))])
 def test_groupnorm_large_mean(ratio, C, shape):
