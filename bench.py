@@ -44,8 +44,8 @@ PATCHES_PER_VOLUME = 18    # scripts/test.py:205-230 tiling of a (110,200,200) v
 C2_CONFIG = {"workload": "C2: paper-default 3D UNet (128ch, 2 res blocks, mult 1-1-2-3-4), one 96x96x96 low-dose-conditioned "
                          "patch per GPU, one DDPM reverse step (UNet eval + posterior update) per bench step"}
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch, from the committed ncu capture
-DOMINANT_LAUNCH_DRAM_BYTES = 227427584 + 183572480
-DOMINANT_LAUNCH_PROFILE = "profiles/r1k_conv_tc_ncu_full.txt"
+DOMINANT_LAUNCH_DRAM_BYTES = 454000640 + 200749568
+DOMINANT_LAUNCH_PROFILE = "profiles/r2_conv_strip_ncu_full.txt"
 C2_FLAGS = dict(
     large_size=96, small_size=96, class_cond=False, learn_sigma=True, num_channels=128, num_res_blocks=2,
     num_heads=4, num_head_channels=64, num_heads_upsample=-1, attention_resolutions="1000", dropout=0.0,
@@ -535,7 +535,8 @@ def main():
                     "frac": achieved / peak_tf,
                     "traffic": DOMINANT_LAUNCH_DRAM_BYTES if (dom == "conv_tcgen05" and shape == PATCH) else None,
                     "traffic_note": "not measured in this run: DRAM bytes (read + write) of the dominant launch (96^3 128->128 "
-                                    "3x3x3 conv, 782.8 GFLOP, algorithmic 453 MB) from the ncu --set full capture in "
+                                    "3x3x3 conv with its identity skip folded in as a second source, 782.8 GFLOP, "
+                                    "algorithmic 679 MB = two 226 MB inputs + 226 MB output) from the ncu --set full capture in "
                                     + DOMINANT_LAUNCH_PROFILE + "; achieved / frac are over all conv launches of the step",
                     "work_note": "algorithmic flops 2*M*Cout*(27*Cin + Cskip) of every tcgen05 conv launch; the unit-weight K "
                                  "block of folded identity skips is NOT counted",

@@ -58,6 +58,8 @@ def _worker(rank, world, port, q):
 
             single, diffusion = make()
             sharded, _ = make()
+            if idx == 0:  # equal slabs, peer path switched off: NCCL send/recv + all-gather (the other equal-slab cases
+                sharded.set_option("slab_p2p", 0)  # exchange through peer-mapped memory, the unequal one cannot)
             sharded.enable_slab_sharding()
             low, x_T, _ = synth_inputs(shape, 0)
             low, x_T = low.to(dev), x_T.to(dev)
