@@ -340,7 +340,8 @@ constexpr int STEM_TC_THREADS = 128;
 template <typename T>
 __global__ void __launch_bounds__(STEM_TC_THREADS)
 stem_tc_kernel(const uint32_t* __restrict__ in, const T* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
-               int Z, int H, int W, int Cout, int zp, uint32_t tmem_cols, int64_t total, int ntiles) {
+               int Z, int H, int W, int Cout, int zp, uint32_t tmem_cols, int64_t total, int ntiles, float* __restrict__ chsum,
+               int nB) {
   extern __shared__ uint8_t stem_smem_raw[];
   __shared__ uint64_t bar_storage;
   __shared__ uint32_t tmem_slot;
@@ -352,6 +353,12 @@ stem_tc_kernel(const uint32_t* __restrict__ in, const T* __restrict__ w, const f
   uint8_t* a_ptr = stem_smem_raw + (a_smem - raw);
   uint8_t* w_ptr = a_ptr + 128 * 128;
   const uint32_t bar = smem_u32(&bar_storage);
+  // GroupNorm channel sums of the output (see ConvArgs::chsum_out): per warp a [32][33] transpose scratch and
+  // [nB][Cout][2] accumulators behind the weight rows; the launcher guarantees that a tile never straddles two batch elements
+  float* cs_tr = reinterpret_cast<float*>(w_ptr + (size_t)Cout * 128) + warp * (32 * 33);
+  float* cs_acc = reinterpret_cast<float*>(w_ptr + (size_t)Cout * 128) + 4 * 32 * 33 + (size_t)warp * nB * Cout * 2;
+  if (chsum)
+    for (int i = tid & 31; i < nB * Cout * 2; i += 32) cs_acc[i] = 0.f;
 
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -437,6 +444,35 @@ stem_tc_kernel(const uint32_t* __restrict__ in, const T* __restrict__ w, const f
           *reinterpret_cast<uint4*>(op + c0 + 8 * j) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
       }
+      if (chsum) {
+        // column sums over the warp's 32 voxels of the raw accumulators (= x - bias: a dominant bias does not cancel)
+        const int lane = tid & 31;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cs_tr[lane * 33 + j] = live ? __uint_as_float(r[j]) : 0.f;
+        __syncwarp();
+        float s0 = 0.f, q0 = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          const float x0 = cs_tr[rr * 33 + lane];
+          s0 += x0;
+          q0 = fmaf(x0, x0, q0);
+        }
+        const int tb = (int)(((int64_t)tile * 128) / ((int64_t)Z * H * W));  // batch element of this tile
+        float* a2 = cs_acc + ((size_t)tb * Cout + c0 + lane) * 2;
+        a2[0] += s0;
+        a2[1] += q0;
+      }
+    }
+  }
+  if (chsum) {  // combine the four warps' accumulators in a fixed order: this CTA's slot of chsum[nB][gridDim.x][Cout][2]
+    __syncthreads();
+    const float* acc0 = reinterpret_cast<const float*>(w_ptr + (size_t)Cout * 128) + 4 * 32 * 33;
+    const int n = nB * Cout * 2;
+    for (int i = tid; i < n; i += STEM_TC_THREADS) {
+      const float t = ((acc0[i] + acc0[n + i]) + acc0[2 * n + i]) + acc0[3 * n + i];
+      const int bb = i / (Cout * 2), rem = i - bb * Cout * 2;
+      chsum[((size_t)bb * gridDim.x + blockIdx.x) * Cout * 2 + rem] = t;
     }
   }
   tc_fence_before();
@@ -452,24 +488,33 @@ bool stem_tc_eligible(const ConvArgs& a) {
          (reinterpret_cast<uintptr_t>(a.main.ptr) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 3) == 0;
 }
 
+static int stem_tc_grid(const ConvArgs& a, uint32_t* cols_out) {
+  const int64_t ntiles = ceil_div((int64_t)a.B * a.Z * a.Ho * a.Wo, 128);
+  uint32_t cols = 32;
+  while ((int)cols < a.Cout) cols *= 2;
+  const int per_sm = std::max(1, std::min(6, 512 / (int)cols));   // TMEM columns bound the co-resident CTAs
+  if (cols_out) *cols_out = cols;
+  return (int)std::min<int64_t>(ntiles, (int64_t)sm_count() * per_sm);
+}
+
 template <typename T>
-int stem_tc_launch(const ConvArgs& a, cudaStream_t s) {
+int stem_tc_launch(ConvArgs& a, cudaStream_t s) {
   const int64_t total = (int64_t)a.B * a.Z * a.Ho * a.Wo;
   const int64_t ntiles = ceil_div(total, 128);
   DD_CHECK(ntiles < ((int64_t)1 << 31), DDPM3D_ERR_ARG, "conv_stem: too many voxels");
   uint32_t cols = 32;
-  while ((int)cols < a.Cout) cols *= 2;
-  const int per_sm = std::max(1, std::min(6, 512 / (int)cols));   // TMEM columns bound the co-resident CTAs
-  const int sms = sm_count();
-  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sms * per_sm);
-  const size_t smem = 1024 + 128 * 128 + (size_t)a.Cout * 128;
+  const int grid = stem_tc_grid(a, &cols);
+  // channel sums for the consuming GroupNorm: one slot per CTA (conv_stem_chsum_slots); needs whole tiles per batch element
+  float* chsum = conv_stem_chsum_slots(a) ? a.chsum_out : nullptr;
+  const size_t smem = 1024 + 128 * 128 + (size_t)a.Cout * 128 + (chsum ? (size_t)4 * 32 * 33 * 4 + (size_t)4 * a.B * a.Cout * 2 * 4 : 0);
   static uint64_t configured = 0;
   if (first_use_on_device(&configured)) {
-    DD_CUDA(cudaFuncSetAttribute(stem_tc_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    DD_CUDA(cudaFuncSetAttribute(stem_tc_kernel<f16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    DD_CUDA(cudaFuncSetAttribute(stem_tc_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    DD_CUDA(cudaFuncSetAttribute(stem_tc_kernel<f16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   }
   stem_tc_kernel<T><<<grid, STEM_TC_THREADS, smem, s>>>((const uint32_t*)a.main.ptr, (const T*)a.w, a.bias, (T*)a.out, a.Z, a.Ho,
-                                                        a.Wo, a.Cout, a.in_zpad, cols, total, (int)ntiles);
+                                                        a.Wo, a.Cout, a.in_zpad, cols, total, (int)ntiles, chsum, a.B);
+  a.chsum_written = chsum ? 1 : 0;
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }
@@ -523,8 +568,17 @@ bool conv_stem_eligible(const ConvArgs& a) {
          a.Cout % 32 == 0 && a.Cout <= 512 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
 }
 
-int conv_stem(const ConvArgs& a, cudaStream_t s) {
+// slots (= CTAs) of the channel-sum buffer the tensor-core stem writes, chsum_out[B][slots][Cout][2]; 0 = this launch
+// produces no channel sums (CUDA-core stem, tiles that straddle batch elements, accumulators that do not fit)
+int conv_stem_chsum_slots(const ConvArgs& a) {
+  if (!conv_stem_eligible(a) || !stem_tc_eligible(a)) return 0;
+  if (((int64_t)a.Z * a.Ho * a.Wo) % 128 != 0 || a.B * a.Cout > 512) return 0;
+  return stem_tc_grid(a, nullptr);
+}
+
+int conv_stem(ConvArgs& a, cudaStream_t s) {
   DD_CHECK(conv_stem_eligible(a), DDPM3D_ERR_ARG, "conv_stem: shape not eligible");
+  a.chsum_written = 0;
   if (stem_tc_eligible(a)) return a.dt == DDPM3D_BF16 ? stem_tc_launch<bf16>(a, s) : stem_tc_launch<f16>(a, s);
   const int nWt = (int)ceil_div(a.Wo, SW_), nHt = (int)ceil_div(a.Ho, SH_), nZt = (int)ceil_div(a.Z, SZ_);
   const int grid = a.B * nZt * nHt * nWt;

@@ -22,6 +22,7 @@
 // in place (unet.py:222,254-256 and :1040-1042).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <type_traits>
 
@@ -174,6 +175,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const uint32_t tmem_base = tmem_base_slot;
   const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
   if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before any multicast can signal them
+  // programmatic dependent launch: everything above overlapped the tail of the kernel before this one (the GroupNorm
+  // apply pass).  The kernel after this one (the GroupNorm finalize) is released by the MMA warp once it has issued its
+  // last tile -- released at the start, it and the apply grid behind it would sit in griddepcontrol.wait next to the
+  // running convolution for its whole duration (measured: +3 % on the network step)
+  pdl_wait();
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -263,6 +269,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         umma_commit(tfull_bar(acc));  // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      pdl_launch_dependents();  // only the last epilogue is left: the next kernel may be scheduled (it waits for this grid)
     }
   } else {
     // ===================================== epilogue ==========================================
@@ -428,11 +435,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 // hardware).  Per 9 taps the SM now pulls one 75 KB strip + 9 x 16 KB weight tiles through L2 instead of 9 x 48 KB.
 // The ~2/Wp pad columns are computed and discarded.
 constexpr int STRIP_THREADS = 224;  // warp 0 strip producer, 1 MMA, 2-5 epilogue, 6 weight producer
+constexpr int STRIP_MAXW = 8;
 
 struct StripParams {
   int B, Z, H, W, Cout;
   int Wb, Wp, nbands, nh, tiles_per_band, nNt, num_tiles, zoff;
   int NV;            // voxels (padded-flattened positions) per tile = the MMA N: a multiple of 16, <= 256
+  int NW;            // stages of the weight ring (3 .. STRIP_MAXW): as many as fit beside the two strips.  A stage lasts
+                     // 2 NV tensor cycles, so 4 stages of a 208-position tile cover ~1700 cycles -- less than a loaded L2 round trip
   int nsrc, chunks[3], n_macro_main, n_macro, Cin;
   int dz0;           // z offset of the first tap plane: -1 for 3x3x3, 0 for the 3x3 kernels of a dims = 2 network
   int taps;          // 27 or 9
@@ -441,12 +451,12 @@ struct StripParams {
   const void* res;   // residual (applied after the transpose, voxel-major) or NULL
   int res_mode;
   void* out;
-  float* chsum;      // only without a residual (the sums are taken channel-major, before the transpose)
+  float* chsum;      // per-CTA channel sums of the output (with a residual: taken after it was added, second transpose)
   int cs_slots;
   uint32_t cs_off;
 };
 
-template <typename T, typename TS, int NB, int NW>
+template <typename T, typename TS, int NB>
 __global__ void __launch_bounds__(STRIP_THREADS, 1)
 conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW, const StripParams p) {
@@ -456,8 +466,10 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
   constexpr int TMEM_COLS = 2 * ACC_COLS;
   static_assert(TMEM_COLS == 512 || TMEM_COLS == 256, "TMEM allocation must be a power of two <= 512");
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * 2 + 2 * NW + 4];
+  constexpr int NWB = STRIP_MAXW;  // barrier slots of the weight ring (p.NW of them in use)
+  __shared__ __align__(8) uint64_t bars[2 * 2 + 2 * NWB + 4];
   __shared__ uint32_t tmem_base_slot;
+  const int NW = p.NW;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = smem_base + 2 * p.strip_stride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -465,9 +477,9 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
   auto sfull = [&](int i) { return bar0 + 8u * i; };
   auto sempty = [&](int i) { return bar0 + 8u * (2 + i); };
   auto wfull = [&](int i) { return bar0 + 8u * (4 + i); };
-  auto wempty = [&](int i) { return bar0 + 8u * (4 + NW + i); };
-  auto tfull = [&](int i) { return bar0 + 8u * (4 + 2 * NW + i); };
-  auto tempty = [&](int i) { return bar0 + 8u * (6 + 2 * NW + i); };
+  auto wempty = [&](int i) { return bar0 + 8u * (4 + NWB + i); };
+  auto tfull = [&](int i) { return bar0 + 8u * (4 + 2 * NWB + i); };
+  auto tempty = [&](int i) { return bar0 + 8u * (6 + 2 * NWB + i); };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA0);
@@ -488,6 +500,7 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // see conv_tc_kernel
 
   // tile -> (b, z, band, q0, n0)
   auto decode = [&](int tile, int& b, int& z, int& w0, int& q0, int& n0) {
@@ -602,6 +615,7 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
         umma_commit(tfull(acc));
         if (++acc == 2) { acc = 0; aph ^= 1; }
       }
+      pdl_launch_dependents();
     }
   } else {
     // ===================================== epilogue ===========================================
@@ -623,6 +637,7 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
       decode(tile, b, z, w0, q0, n0);
       const int co = n0 + sub * 32 + lane;
       const float bias_co = __ldg(p.bias + co);
+      const bool with_res = p.res_mode != RES_NONE;
       float ts = 0.f, tq = 0.f;
       mbar_wait(tfull(acc), aph);
       tc_fence_after();
@@ -646,8 +661,10 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
           // in the fp32 sums; the GroupNorm finalize folds the bias back in fp64
           const float a = ((vmask >> j) & 1u) ? __uint_as_float(r[j]) : 0.f;
           x[j] = ((vmask >> j) & 1u) ? a + bias_co : 0.f;
-          ts += a;
-          tq = fmaf(a, a, tq);
+          if (!with_res) {
+            ts += a;
+            tq = fmaf(a, a, tq);
+          }
         }
         float v[32];
 #pragma unroll
@@ -695,6 +712,25 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) w4[qq] = pack2<TS>(v[8 * i + 2 * qq], v[8 * i + 2 * qq + 1]);
             *reinterpret_cast<uint4*>(op + 8 * i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          }
+        }
+        if (p.chsum && p.res_mode != RES_NONE) {
+          // the residual was added voxel-major: transpose the final values back so that lane = channel again and take
+          // the sums over (x - bias) of what was stored (the un-rounded fp32 values, as in the other epilogues)
+#pragma unroll
+          for (int turn = 0; turn < 2; ++turn) {
+            if ((sub & 1) == turn) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) tr[lane * 33 + c] = v[c];  // [voxel][channel]
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float a = ((vmask >> j) & 1u) ? tr[j * 33 + lane] - bias_co : 0.f;
+                ts += a;
+                tq = fmaf(a, a, tq);
+              }
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + (sub >> 1)) : "memory");
           }
         }
       }
@@ -807,7 +843,7 @@ void choose_brick(int Z, int H, int W, int* bw_, int* bh_, int* bz_) {
 }
 
 template <typename T, typename TS, int MT, int BN, int NSTAGE, int CL>
-int launch_cl(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s) {
+int launch_cl(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s, bool pdl) {
   constexpr size_t stage_smem = (size_t)NSTAGE * (MT * A_BYTES + BN * BK * 2) + 1024;
   constexpr size_t smem_max = stage_smem + CS_SMEM_MAX;
   static_assert(smem_max <= 227 * 1024, "shared memory budget");
@@ -837,13 +873,15 @@ int launch_cl(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& 
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   DD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<T, TS, MT, BN, NSTAGE, CL>, maps[0], maps[1], maps[2], mapW, q));
   if (p.sk) {
     sk_fixup_kernel<TS, MT, BN><<<dim3(p.num_tiles, 8), 256, 0, s>>>(p, grid);
@@ -854,16 +892,16 @@ int launch_cl(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& 
 
 // stream-K ranges differ per CTA, so those launches cannot share weight tiles (CL = 1)
 template <typename T, typename TS, int MT, int BN, int NSTAGE>
-int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s, int cl) {
-  if (cl == 2) return launch_cl<T, TS, MT, BN, NSTAGE, 2>(maps, mapW, p, s);
-  return launch_cl<T, TS, MT, BN, NSTAGE, 1>(maps, mapW, p, s);
+int launch(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s, int cl, bool pdl) {
+  if (cl == 2) return launch_cl<T, TS, MT, BN, NSTAGE, 2>(maps, mapW, p, s, pdl);
+  return launch_cl<T, TS, MT, BN, NSTAGE, 1>(maps, mapW, p, s, pdl);
 }
 template <typename T, typename TS>
-int launch_plan(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s, int cl, int MT, int BN) {
-  if (MT == 2) return launch<T, TS, 2, 128, 4>(maps, mapW, p, s, cl);
-  if (BN == 256) return launch<T, TS, 1, 256, 4>(maps, mapW, p, s, cl);
-  if (BN == 128) return launch<T, TS, 1, 128, 6>(maps, mapW, p, s, cl);
-  return launch<T, TS, 1, 64, 8>(maps, mapW, p, s, cl);
+int launch_plan(const CUtensorMap* maps, const CUtensorMap& mapW, const TcParams& p, cudaStream_t s, int cl, int MT, int BN, bool pdl) {
+  if (MT == 2) return launch<T, TS, 2, 128, 4>(maps, mapW, p, s, cl, pdl);
+  if (BN == 256) return launch<T, TS, 1, 256, 4>(maps, mapW, p, s, cl, pdl);
+  if (BN == 128) return launch<T, TS, 1, 128, 6>(maps, mapW, p, s, cl, pdl);
+  return launch<T, TS, 1, 64, 8>(maps, mapW, p, s, cl, pdl);
 }
 
 // ---- probe (test-only): does a SWIZZLE_128B K-major operand descriptor work when its start address is an
@@ -1005,15 +1043,21 @@ struct StripPlan {
   size_t smem;
 };
 
+// strip_allowed: 0 never; 1 the large layers only (planes >= 24 wide, tiles of 192..256 positions, >= 2 tiles per SM);
+// 2 also small planes (12..23 wide: one tile of 160..256 padded-flattened positions per plane).  For those the brick
+// kernel is bound by the bytes it pulls through L2 per MMA (one 16 KB A tile per tap, no reuse) and runs stream-K with an
+// fp32 fix-up pass; the strip form computes ~20 % pad positions but moves a third of the bytes and keeps the GroupNorm
+// channel sums in the epilogue.  DDPM3D_STRIP_EFF (percent) overrides the acceptance threshold of level 2 (tuning).
 bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
   if (!a.strip_allowed || !is_half_dt(a.dt) || (a.taps != 27 && a.taps != 9) || a.stride_hw != 1 || a.out_planar_f32) return false;
   if (a.Cout % 128 != 0 || a.main.C % BK != 0) return false;
   for (int e = 0; e < a.n_extra; ++e)
     if (a.extra[e].C % BK != 0) return false;
   if (a.residual && a.res_mode == RES_UP && (a.Ho % 2 || a.Wo % 2)) return false;
+  const bool small_ok = a.strip_allowed >= 2;
   StripPlan t{};
   t.Wb = 0;
-  for (int d = std::min(a.Wo, 96); d >= 24; --d)
+  for (int d = std::min(a.Wo, 96); d >= (small_ok ? 12 : 24); --d)
     if (a.Wo % d == 0) { t.Wb = d; break; }
   if (!t.Wb) return false;
   t.Wp = t.Wb + 2;
@@ -1025,17 +1069,39 @@ bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
     const double eff = (double)a.Ho * t.Wb / ((double)tpb * nv) * (nv >= 224 ? 1.0 : 0.97);
     if (eff > best_eff + 0.015) { best_eff = eff; t.NV = nv; t.tiles_per_band = tpb; }  // prefer the longest tile
   }
-  if (best_eff < 0.88) return false;  // pad columns + ragged last tile
+  bool classic = best_eff >= 0.88;  // pad columns + ragged last tile
+  if (!classic) {
+    if (!small_ok) return false;
+    // shorter tiles: below ~160 positions the 16 KB weight tile per tap (read once per 2 NV tensor cycles) exceeds what
+    // an SM can pull through L2
+    for (int nv = 176; nv >= 160; nv -= 16) {
+      const int tpb = (int)ceil_div((int64_t)a.Ho * t.Wp, nv);
+      const double eff = (double)a.Ho * t.Wb / ((double)tpb * nv) * 0.95;
+      if (eff > best_eff + 0.015) { best_eff = eff; t.NV = nv; t.tiles_per_band = tpb; }
+    }
+  }
   t.nh = 3 + (int)ceil_div(t.NV + 1, t.Wp);
   if (t.nh > 256) return false;
   t.nNt = a.Cout / 128;
   const int64_t tiles = (int64_t)a.B * a.Z * t.nbands * t.tiles_per_band * t.nNt;
-  if (tiles < 2 * (int64_t)sm_count() || tiles >= ((int64_t)1 << 31)) return false;
+  if (tiles >= ((int64_t)1 << 31)) return false;
+  const int sms = sm_count();
+  if (tiles < 2 * (int64_t)sms) classic = false;
+  if (!classic) {
+    if (!small_ok || tiles < sms) return false;
+    // useful positions x how full the last wave is: accept from 0.60 (a 12 x 12 plane with 3 channel tiles: 0.78 x 0.97)
+    static const double thr = [] {
+      const char* e = getenv("DDPM3D_STRIP_EFF");
+      return e ? atof(e) / 100.0 : 0.60;
+    }();
+    const double wave = (double)tiles / ((double)ceil_div(tiles, sms) * sms);
+    if (best_eff * wave < thr) return false;
+  }
   t.num_tiles = (int)tiles;
   t.strip_bytes = (uint32_t)(t.nh * t.Wp * 128);
   t.strip_stride = (t.strip_bytes + 1023u) & ~1023u;
   const size_t cs = CS_TR_BYTES / 2 + (want_chsum ? (size_t)a.B * a.Cout * 2 * sizeof(float) : 0);  // the transpose scratch is always needed
-  for (int nw : {4, 3}) {
+  for (int nw = std::max(3, std::min(STRIP_MAXW, a.strip_maxw)); nw >= 3; --nw) {
     t.NW = nw;
     t.smem = (size_t)2 * t.strip_stride + (size_t)nw * 128 * BK * 2 + 1024 + cs;
     if (t.smem + 256 <= 227 * 1024) { *out = t; return true; }
@@ -1043,17 +1109,27 @@ bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
   return false;
 }
 
-template <typename T, typename TS, int NW>
-int launch_strip(const CUtensorMap* maps, const CUtensorMap& mapW, const StripParams& p, const StripPlan& plan, cudaStream_t s) {
+template <typename T, typename TS>
+int launch_strip(const CUtensorMap* maps, const CUtensorMap& mapW, const StripParams& p, const StripPlan& plan, cudaStream_t s,
+                 bool pdl) {
   static uint64_t configured = 0;
   if (first_use_on_device(&configured)) {
-    DD_CUDA(cudaFuncSetAttribute(conv_tc_strip_kernel<T, TS, 2, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_strip_kernel<T, TS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
   }
   const int grid = std::min(p.num_tiles, sm_count());
   if (p.chsum && grid < p.cs_slots)
     DD_CUDA(cudaMemsetAsync(p.chsum, 0, (size_t)p.B * p.cs_slots * p.Cout * 2 * sizeof(float), s));
-  conv_tc_strip_kernel<T, TS, 2, NW><<<grid, STRIP_THREADS, plan.smem, s>>>(maps[0], maps[1], maps[2], mapW, p);
-  DD_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(STRIP_THREADS);
+  cfg.dynamicSmemBytes = plan.smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_strip_kernel<T, TS, 2>, maps[0], maps[1], maps[2], mapW, p));
   return DDPM3D_OK;
 }
 
@@ -1063,6 +1139,7 @@ int conv_tc_strip(ConvArgs& a, const StripPlan& plan, bool chsum, cudaStream_t s
   p.Wb = plan.Wb; p.Wp = plan.Wp; p.nbands = plan.nbands; p.nh = plan.nh; p.tiles_per_band = plan.tiles_per_band;
   p.nNt = plan.nNt; p.num_tiles = plan.num_tiles; p.zoff = a.in_zpad;
   p.NV = plan.NV;
+  p.NW = plan.NW;
   p.nsrc = 1 + a.n_extra;
   p.chunks[0] = a.main.C / BK;
   p.Cin = a.main.C;
@@ -1082,7 +1159,6 @@ int conv_tc_strip(ConvArgs& a, const StripPlan& plan, bool chsum, cudaStream_t s
   p.res = a.residual;
   p.res_mode = a.residual ? a.res_mode : RES_NONE;
   p.out = a.out;
-  if (a.residual) chsum = false;
   p.chsum = chsum ? a.chsum_out : nullptr;
   p.cs_slots = chsum_slots();
   p.cs_off = (uint32_t)((size_t)2 * plan.strip_stride + (size_t)plan.NW * 128 * BK * 2 + 1024);
@@ -1096,11 +1172,10 @@ int conv_tc_strip(ConvArgs& a, const StripPlan& plan, bool chsum, cudaStream_t s
     DD_TRY(make_act_map(&maps[1 + e], tdt_io, a.extra[e].ptr, a.B, a.Z, a.Ho, a.Wo, a.extra[e].C, plan.Wp, plan.nh, 1));
   CUtensorMap mapW;
   DD_TRY(make_w_map(&mapW, tdt, a.w, a.Cout, a.w_ld ? a.w_ld : Ktot, 128));
-  if (a.dt == DDPM3D_BF16 && a.io_dt() == DDPM3D_BF16)
-    return plan.NW == 4 ? launch_strip<bf16, bf16, 4>(maps, mapW, p, plan, s) : launch_strip<bf16, bf16, 3>(maps, mapW, p, plan, s);
-  if (a.dt == DDPM3D_BF16)
-    return plan.NW == 4 ? launch_strip<bf16, f16, 4>(maps, mapW, p, plan, s) : launch_strip<bf16, f16, 3>(maps, mapW, p, plan, s);
-  return plan.NW == 4 ? launch_strip<f16, f16, 4>(maps, mapW, p, plan, s) : launch_strip<f16, f16, 3>(maps, mapW, p, plan, s);
+  const bool pdl = a.pdl != 0;
+  if (a.dt == DDPM3D_BF16 && a.io_dt() == DDPM3D_BF16) return launch_strip<bf16, bf16>(maps, mapW, p, plan, s, pdl);
+  if (a.dt == DDPM3D_BF16) return launch_strip<bf16, f16>(maps, mapW, p, plan, s, pdl);
+  return launch_strip<f16, f16>(maps, mapW, p, plan, s, pdl);
 }
 
 }  // namespace
@@ -1199,9 +1274,10 @@ int conv_tc(ConvArgs& a, cudaStream_t s) {
   CUtensorMap mapW;
   const int cl = (!p.sk && a.cluster_allowed && p.num_tiles / p.nNt >= 2 * sm_count()) ? 2 : 1;
   DD_TRY(make_w_map(&mapW, tdt, a.w, a.Cout, a.w_ld ? a.w_ld : Ktot, BN / cl));
-  if (a.dt == DDPM3D_BF16 && a.io_dt() == DDPM3D_BF16) return launch_plan<bf16, bf16>(maps, mapW, p, s, cl, MT, BN);
-  if (a.dt == DDPM3D_BF16) return launch_plan<bf16, f16>(maps, mapW, p, s, cl, MT, BN);
-  return launch_plan<f16, f16>(maps, mapW, p, s, cl, MT, BN);
+  const bool pdl = a.pdl != 0;
+  if (a.dt == DDPM3D_BF16 && a.io_dt() == DDPM3D_BF16) return launch_plan<bf16, bf16>(maps, mapW, p, s, cl, MT, BN, pdl);
+  if (a.dt == DDPM3D_BF16) return launch_plan<bf16, f16>(maps, mapW, p, s, cl, MT, BN, pdl);
+  return launch_plan<f16, f16>(maps, mapW, p, s, cl, MT, BN, pdl);
 }
 
 }  // namespace ddpm3d

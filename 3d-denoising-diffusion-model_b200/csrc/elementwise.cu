@@ -326,21 +326,39 @@ __global__ void __launch_bounds__(1024) gn_finalize_multi_kernel(const double* g
 // reduction order -> deterministic.  Result in sh[0][0], sh[1][0] (valid for every thread after the call).
 __device__ __forceinline__ void chsum_group_sums(const float* __restrict__ cs0, const float* __restrict__ cs1,
                                                  const float* __restrict__ bias0, const float* __restrict__ bias1, int C0,
-                                                 int C1, int P, double n_vox, int g, int b, double (*sh)[128]) {
+                                                 int C1, int P0, int P1, double n_vox, int g, int b, double (*sh)[128]) {
   const int tid = threadIdx.x;
   const int Ctot = C0 + C1, gpc = Ctot / 32;
-  const int n = P * gpc;  // (slot, channel-in-group) pairs of this group
+  const int n = (P0 > P1 ? P0 : P1) * gpc;  // (slot, channel-in-group) pairs of this group
   double s = 0.0, q = 0.0;
-  for (int i = tid; i < n; i += 128) {
-    const int slot = i / gpc, c = g * gpc + i % gpc;
-    const bool first = c < C0;
-    const float* src = first ? cs0 + (((int64_t)b * P + slot) * C0 + c) * 2 : cs1 + (((int64_t)b * P + slot) * C1 + (c - C0)) * 2;
-    const float* bias = first ? bias0 : bias1;
-    const double bc = bias ? (double)bias[first ? c : c - C0] : 0.0;
-    const double d1 = (double)src[0], d2 = (double)src[1];
-    s += d1;
-    q += d2 + 2.0 * bc * d1;
-    if (slot == 0) { s += n_vox * bc; q += n_vox * bc * bc; }
+  // four pairs per thread and pass, all loads issued before the first add: the pass is one L2 round trip, not four
+  // (this kernel sits between every convolution and the GroupNorm apply that follows it)
+  constexpr int U = 4;
+  for (int i0 = tid; i0 < n; i0 += 128 * U) {
+    float2 v[U];
+    float bc[U];
+    int sl[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * 128;
+      const int slot = i / gpc, c = g * gpc + i % gpc;
+      const bool first = c < C0;
+      const int P = first ? P0 : P1;
+      // the sources may have different slot counts (the stem: one per CTA)
+      const bool ok = i < n && slot < P;
+      const float* src = first ? cs0 + (((int64_t)b * P0 + slot) * C0 + c) * 2 : cs1 + (((int64_t)b * P1 + slot) * C1 + (c - C0)) * 2;
+      const float* bias = first ? bias0 : bias1;
+      v[u] = ok ? *reinterpret_cast<const float2*>(src) : make_float2(0.f, 0.f);
+      bc[u] = (ok && bias) ? bias[first ? c : c - C0] : 0.f;
+      sl[u] = ok ? slot : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double d1 = (double)v[u].x, d2 = (double)v[u].y, bcd = (double)bc[u];
+      s += d1;
+      q += d2 + 2.0 * bcd * d1;
+      if (sl[u] == 0) { s += n_vox * bcd; q += n_vox * bcd * bcd; }
+    }
   }
   sh[0][tid] = s;
   sh[1][tid] = q;
@@ -354,15 +372,16 @@ __device__ __forceinline__ void chsum_group_sums(const float* __restrict__ cs0, 
 // finalize from the conv epilogues' channel sums.  grid (32 groups, B), 128 threads.
 __global__ void __launch_bounds__(128) gn_finalize_chsum_kernel(const float* __restrict__ cs0, const float* __restrict__ cs1,
                                                                 const float* __restrict__ bias0, const float* __restrict__ bias1,
-                                                                int C0, int C1, int P, double n_vox, double inv_count,
+                                                                int C0, int C1, int P0, int P1, double n_vox, double inv_count,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 const float* __restrict__ film, int64_t film_stride,
                                                                 float* __restrict__ ab) {
   __shared__ double sh[2][128];
   const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int Ctot = C0 + C1, gpc = Ctot / 32;
+  pdl_wait();               // (pdl = 2) this grid was scheduled while the last epilogues of the producing convolution ran
   pdl_launch_dependents();  // the apply kernel may start its prologue now; it waits for this grid before reading `ab`
-  chsum_group_sums(cs0, cs1, bias0, bias1, C0, C1, P, n_vox, g, b, sh);
+  chsum_group_sums(cs0, cs1, bias0, bias1, C0, C1, P0, P1, n_vox, g, b, sh);
   const double mean = sh[0][0] * inv_count;
   double var = sh[1][0] * inv_count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -434,6 +453,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const T* __restrict__ 
   };
   float A[N], Bv[N];
   pdl_wait();  // launched with programmatic stream serialisation: everything above overlapped the finalize kernel
+  pdl_launch_dependents();  // the convolution that follows may set up (barriers, TMEM, descriptors) while this grid drains
   {
     const float* pa = ab + (int64_t)b * 2 * Ctot + v * N;
 #pragma unroll
@@ -660,15 +680,29 @@ int gn_forward(const GnArgs& a, cudaStream_t s, int* launches) {
   return DDPM3D_OK;
 }
 
+static int finalize_chsum_launch(const GnArgs& a, double inv_count, cudaStream_t s) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(32, a.B);
+  cfg.blockDim = dim3(128);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = a.pdl >= 2 ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DD_CUDA(cudaLaunchKernelEx(&cfg, gn_finalize_chsum_kernel, a.chsum[0], a.chsum[1], a.chsum_bias[0], a.chsum_bias[1], a.C[0], a.C[1],
+                             a.chsum_P[0] ? a.chsum_P[0] : chsum_slots(), a.chsum_P[1] ? a.chsum_P[1] : chsum_slots(),
+                             (double)a.Z * a.H * a.W, inv_count, a.gamma, a.beta, a.film, a.film_stride, a.ab));
+  return DDPM3D_OK;
+}
+
 // statistics + per-(b, c) affine only (a.ab); the consumer applies it itself (the fused head, head_tc.cu)
 int gn_finalize_only(const GnArgs& a, cudaStream_t s) {
   DD_TRY(gn_check(a));
   const int Ctot = a.C[0] + a.C[1];
   const double inv_count = 1.0 / ((double)a.Z * a.H * a.W * (Ctot / 32));
   if (!a.pre_add && a.chsum[0] && (a.C[1] == 0 || a.chsum[1])) {
-    gn_finalize_chsum_kernel<<<dim3(32, a.B), 128, 0, s>>>(a.chsum[0], a.chsum[1], a.chsum_bias[0], a.chsum_bias[1], a.C[0], a.C[1],
-                                                           chsum_slots(), (double)a.Z * a.H * a.W, inv_count, a.gamma, a.beta,
-                                                           a.film, a.film_stride, a.ab);
+    DD_TRY(finalize_chsum_launch(a, inv_count, s));
   } else {
     DD_TRY(gn_stats_any(a, s));
     gn_finalize_kernel<<<a.B, 1024, 0, s>>>(a.partials, a.n_chunks, Ctot, inv_count, a.gamma, a.beta, a.film, a.film_stride,
@@ -683,20 +717,17 @@ int gn_forward_chsum(const GnArgs& a, cudaStream_t s) {
   const int Ctot = a.C[0] + a.C[1];
   DD_CHECK(a.chsum[0] && (a.C[1] == 0 || a.chsum[1]) && !a.pre_add, DDPM3D_ERR_STATE, "groupnorm: channel sums missing");
   const double inv_count = 1.0 / ((double)a.Z * a.H * a.W * (Ctot / 32));
-  gn_finalize_chsum_kernel<<<dim3(32, a.B), 128, 0, s>>>(a.chsum[0], a.chsum[1], a.chsum_bias[0], a.chsum_bias[1], a.C[0], a.C[1],
-                                                         chsum_slots(), (double)a.Z * a.H * a.W, inv_count, a.gamma, a.beta,
-                                                         a.film, a.film_stride, a.ab);
-  DD_CUDA(cudaGetLastError());
+  DD_TRY(finalize_chsum_launch(a, inv_count, s));
   return gn_apply_any(a, s);
 }
 
 // z-slab sharding with fused statistics: this rank's fp64 group sums [B][32][2] from the conv epilogues' channel sums
 __global__ void __launch_bounds__(128) gn_chsum_local_kernel(const float* __restrict__ cs0, const float* __restrict__ cs1,
                                                              const float* __restrict__ bias0, const float* __restrict__ bias1,
-                                                             int C0, int C1, int P, double n_vox, double* __restrict__ sums) {
+                                                             int C0, int C1, int P0, int P1, double n_vox, double* __restrict__ sums) {
   __shared__ double sh[2][128];
   const int g = blockIdx.x, b = blockIdx.y;
-  chsum_group_sums(cs0, cs1, bias0, bias1, C0, C1, P, n_vox, g, b, sh);
+  chsum_group_sums(cs0, cs1, bias0, bias1, C0, C1, P0, P1, n_vox, g, b, sh);
   if (threadIdx.x == 0) {
     sums[((int64_t)b * 32 + g) * 2] = sh[0][0];
     sums[((int64_t)b * 32 + g) * 2 + 1] = sh[1][0];
@@ -707,7 +738,7 @@ int gn_chsum_local(const GnArgs& a, double* sums, cudaStream_t s) {
   DD_TRY(gn_check(a));
   DD_CHECK(a.chsum[0] && (a.C[1] == 0 || a.chsum[1]), DDPM3D_ERR_STATE, "groupnorm: channel sums missing");
   gn_chsum_local_kernel<<<dim3(32, a.B), 128, 0, s>>>(a.chsum[0], a.chsum[1], a.chsum_bias[0], a.chsum_bias[1], a.C[0], a.C[1],
-                                                      chsum_slots(), (double)a.Z * a.H * a.W, sums);
+                                                      a.chsum_P[0] ? a.chsum_P[0] : chsum_slots(), a.chsum_P[1] ? a.chsum_P[1] : chsum_slots(), (double)a.Z * a.H * a.W, sums);
   DD_CUDA(cudaGetLastError());
   return DDPM3D_OK;
 }
@@ -836,24 +867,37 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // one CTA per batch element: sinusoid -> Linear -> SiLU -> Linear (+label_emb) -> SiLU
-__global__ void time_embed_kernel(EmbArgs a) {
+// grid (ceil(ted / TE_ROWS), B): every CTA evaluates the sinusoid and the first Linear in full (128 x 512 weights from L2:
+// cheaper than a second launch) and TE_ROWS rows of the second Linear -- one CTA per batch element took 0.11 ms for 1.3 MB of
+// weights.  Per-row summation order (lane-strided, then the warp butterfly) is unchanged.
+constexpr int TE_ROWS = 16;
+__global__ void __launch_bounds__(512) time_embed_kernel(EmbArgs a) {
   extern __shared__ float sm[];  // e0[mc] | h1[ted]
   float* e0 = sm;
   float* h1 = sm + a.model_channels;
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const float t = a.t[b];
   for (int j = threadIdx.x; j < a.model_channels; j += blockDim.x) e0[j] = temb_value(t, j, a.model_channels, a.freqs);
   __syncthreads();
-  for (int r = warp; r < a.ted; r += nwarp) {
-    const float* w = a.w0 + (int64_t)r * a.model_channels;
-    float acc = 0.f;
-    for (int k = lane; k < a.model_channels; k += 32) acc += w[k] * e0[k];
-    acc = warp_sum(acc);
-    if (lane == 0) h1[r] = silu_f(acc + a.b0[r]);
+  // first Linear: four rows per warp and pass so that their weight loads are in flight together
+  for (int r0 = warp * 4; r0 < a.ted; r0 += nwarp * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < a.model_channels; k += 32) {
+      const float e = e0[k];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r0 + u < a.ted) acc[u] += a.w0[(int64_t)(r0 + u) * a.model_channels + k] * e;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float v = warp_sum(acc[u]);
+      if (lane == 0 && r0 + u < a.ted) h1[r0 + u] = silu_f(v + a.b0[r0 + u]);
+    }
   }
   __syncthreads();
-  for (int r = warp; r < a.ted; r += nwarp) {
+  const int r = blockIdx.x * TE_ROWS + warp;
+  if (warp < TE_ROWS && r < a.ted) {
     const float* w = a.w2 + (int64_t)r * a.ted;
     float acc = 0.f;
     for (int k = lane; k < a.ted; k += 32) acc += w[k] * h1[k];
@@ -882,7 +926,7 @@ __global__ void emb_layers_kernel(EmbArgs a) {
 
 int embedding_forward(const EmbArgs& a, cudaStream_t s, int* launches) {
   const size_t smem = (size_t)(a.model_channels + a.ted) * sizeof(float);
-  time_embed_kernel<<<a.B, 512, smem, s>>>(a);
+  time_embed_kernel<<<dim3((unsigned)ceil_div(a.ted, TE_ROWS), a.B), 512, smem, s>>>(a);
   DD_CUDA(cudaGetLastError());
   if (a.rows_total > 0) {
     const int threads = 256;

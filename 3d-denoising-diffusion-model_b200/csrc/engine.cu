@@ -63,6 +63,7 @@ struct Act {
   void* p = nullptr;
   int C = 0, H = 0, W = 0;
   float* chsum = nullptr;  // per-CTA channel sums of this tensor from the producing conv's epilogue (or NULL)
+  int cs_slots = 0;        // slots of chsum (0 = chsum_slots())
   const float* cs_bias = nullptr;  // that conv's bias: the sums are over (x - bias)
 };
 
@@ -176,8 +177,8 @@ struct ddpm3d_ctx {
   float* d_img = nullptr;
   size_t img_cap = 0;
   // options
-  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 1, fold_identity = 1, stem_tc = 1, head_v2 = 1,
-      head_tc = 1, slab_p2p = 1, pdl = 1, gn_stream = 1, gn_stream_mb = 48;
+  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 1, strip_w = 4, fold_identity = 1, stem_tc = 1, head_v2 = 1,
+      head_tc = 1, slab_p2p = 1, pdl = 2, gn_stream = 1, gn_stream_mb = 48;
   float* splitk_buf = nullptr;  // fp32 partial tiles of split-K convolutions (sized by the dry run)
   size_t splitk_cap = 0, splitk_need = 0;
   cudaStream_t cap_stream = nullptr;
@@ -585,6 +586,8 @@ struct Run {
     a.splitk_allowed = ctx->split_k;
     a.cluster_allowed = ctx->cluster;
     a.strip_allowed = ctx->strip;
+    a.strip_maxw = ctx->strip_w;
+    a.pdl = ctx->pdl >= 2;
     a.stem_tc_allowed = ctx->stem_tc;
     a.head_v2_allowed = ctx->head_v2;
     ++launches;
@@ -613,6 +616,7 @@ struct Run {
   int gn_stats(GnArgs& g) {
     g.B = B;
     g.Z = Z;
+    g.pdl = ctx->pdl;
     const int Ctot = g.C[0] + g.C[1];
     g.n_chunks = gn_chunks((int64_t)Z * g.H * g.W);
     g.partials = (double*)arena.alloc((size_t)B * g.n_chunks * 64 * sizeof(double));
@@ -628,7 +632,7 @@ struct Run {
   int gn(GnArgs& g) {
     g.B = B;
     g.Z = Z;
-    g.pdl = ctx->pdl;
+    g.pdl = ctx->pdl;  // 1: finalize -> apply; 2: also conv -> finalize and apply -> conv (the whole conv / GroupNorm chain)
     g.stream_allowed = ctx->gn_stream;
     g.stream_min_mb = ctx->gn_stream_mb;
     const int Ctot = g.C[0] + g.C[1];
@@ -722,7 +726,10 @@ int run_res(Run& R, const Layer& L, const Act* src, int nsrc, Act* out) {
   g.out_zpad = R.zp;
   g.dt = dts;
   g.dt_out = dt;
-  for (int i = 0; i < nsrc; ++i) { g.src[i] = src[i].p; g.C[i] = src[i].C; g.chsum[i] = src[i].chsum; g.chsum_bias[i] = src[i].cs_bias; }
+  for (int i = 0; i < nsrc; ++i) {
+    g.src[i] = src[i].p; g.C[i] = src[i].C;
+    g.chsum[i] = src[i].chsum; g.chsum_bias[i] = src[i].cs_bias; g.chsum_P[i] = src[i].cs_slots;
+  }
   g.H = H; g.W = W;
   g.gamma = L.gn1_g; g.beta = L.gn1_b;
   g.silu = 1;
@@ -796,6 +803,7 @@ int run_attn(Run& R, const Layer& L, const Act& x, Act* out) {
   void* n = R.arena.alloc(R.act_bytes(H, W, C));
   GnArgs g{};
   g.dt = dts; g.dt_out = dt; g.src[0] = x.p; g.C[0] = C; g.H = H; g.W = W; g.gamma = L.gn1_g; g.beta = L.gn1_b; g.silu = 0; g.out = n;
+  g.chsum[0] = x.chsum; g.chsum_bias[0] = x.cs_bias; g.chsum_P[0] = x.cs_slots;
   DD_TRY(R.gn(g));
   void* qkv = R.arena.alloc(R.act_bytes(H, W, 3 * C));
   ConvArgs c{};
@@ -859,6 +867,9 @@ int run_conv_layer(Run& R, const Layer& L, const Act& x, Act* out) {
   }
   out->C = L.cout; out->H = Ho; out->W = Wo;
   out->p = R.arena.alloc(R.act_bytes(Ho, Wo, L.cout));
+  // channel sums of the output for the GroupNorm that reads it: the tensor-core stem has one slot per CTA
+  const size_t cs_floats = (size_t)R.B * 6 * chsum_slots() * L.cout * 2;
+  float* out_cs = (float*)R.arena.alloc(cs_floats * sizeof(float));
   mark = R.arena.off;
   if (L.kind == L_UPCONV) {
     void* u = R.arena.alloc(R.act_bytes(Ho, Wo, L.cin));
@@ -874,7 +885,13 @@ int run_conv_layer(Run& R, const Layer& L, const Act& x, Act* out) {
   ConvArgs c{};
   c.dt = dt; c.main = {in, L.cin}; c.taps = L.c1.taps; c.stride_hw = L.kind == L_UPCONV ? 1 : L.stride_hw;
   c.w = L.c1.w; c.bias = L.c1.bias; c.out = out->p; c.Ho = Ho; c.Wo = Wo; c.Cout = L.cout;
+  c.chsum_out = out_cs;
   DD_TRY(R.conv(c));
+  if (c.chsum_written) {
+    out->chsum = out_cs;
+    out->cs_bias = L.c1.bias;
+    out->cs_slots = conv_stem_eligible(c) ? conv_stem_chsum_slots(c) : 0;  // (0 = one per SM: the tcgen05 conv kernels)
+  }
   R.arena.off = mark;
   return DDPM3D_OK;
 }
@@ -973,6 +990,7 @@ int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, cons
     GnArgs g{};
     g.chsum[0] = h.chsum;
     g.chsum_bias[0] = h.cs_bias;
+    g.chsum_P[0] = h.cs_slots;
     g.dt = ctx->dts; g.src[0] = h.p; g.C[0] = h.C; g.H = H; g.W = W; g.gamma = ctx->out_gn_g; g.beta = ctx->out_gn_b; g.silu = 1;
     DD_TRY(R.gn_stats(g));
     ++R.launches;
@@ -990,6 +1008,7 @@ int forward_impl(ddpm3d_ctx* ctx, Run& R, const float* x, const float* low, cons
   g.out_zpad = R.zp;
   g.chsum[0] = h.chsum;
   g.chsum_bias[0] = h.cs_bias;
+  g.chsum_P[0] = h.cs_slots;
   g.dt = ctx->dts; g.src[0] = h.p; g.C[0] = h.C; g.H = H; g.W = W; g.gamma = ctx->out_gn_g; g.beta = ctx->out_gn_b; g.silu = 1;
   g.out = hn; g.out_f32 = 1;
   DD_TRY(R.gn(g));
@@ -1591,13 +1610,14 @@ int ddpm3d_set_option(ddpm3d_ctx* ctx, const char* name, int64_t value) {
   else if (n == "fuse_stats") ctx->fuse_stats = value != 0;
   else if (n == "split_k") ctx->split_k = value != 0;
   else if (n == "cluster") ctx->cluster = value != 0;
-  else if (n == "strip") ctx->strip = value != 0;
+  else if (n == "strip") ctx->strip = value < 0 ? 0 : (value > 2 ? 2 : value);
+  else if (n == "strip_w") ctx->strip_w = value;
   else if (n == "fold_identity") ctx->fold_identity = value != 0;
   else if (n == "stem_tc") ctx->stem_tc = value != 0;
   else if (n == "head_v2") ctx->head_v2 = value != 0;
   else if (n == "head_tc") ctx->head_tc = value != 0;
   else if (n == "slab_p2p") ctx->slab_p2p = value != 0;
-  else if (n == "pdl") ctx->pdl = value != 0;
+  else if (n == "pdl") ctx->pdl = value < 0 ? 0 : value;
   else if (n == "gn_stream") ctx->gn_stream = value != 0;
   else if (n == "gn_stream_mb") ctx->gn_stream_mb = (int)value;
   else { set_error("unknown option: " + n); return DDPM3D_ERR_ARG; }
@@ -1653,8 +1673,10 @@ int ddpm3d_k_conv3d(int dtype, int path, const void* in, const void* w, const fl
   a.dt = dtype; a.main = {in, Cin}; a.taps = taps; a.stride_hw = stride_hw; a.w = w; a.bias = bias;
   a.residual = residual; a.res_mode = residual ? RES_SAME : RES_NONE;
   a.out = out; a.B = B; a.Z = Z; a.Ho = H / stride_hw; a.Wo = W / stride_hw; a.Cout = Cout;
-  if (path == 2) {
+  if (path == 2 || (path >= 5 && path <= 7)) {
     DD_CHECK(is_half_dt(dtype) && conv_tc_eligible(a), DDPM3D_ERR_ARG, "k_conv3d: shape not eligible for the tcgen05 path");
+    if (path == 5 || path == 6) a.strip_allowed = path == 5 ? 0 : 1;
+    if (path == 7) a.strip_maxw = 4;
     a.splitk_allowed = 1;
     const size_t need = conv_tc_scratch_bytes(a);
     if (need) {

@@ -53,6 +53,8 @@ gn_apply_stream_kernel(const __grid_constant__ CUtensorMap mapIn0, const __grid_
     if (threadIdx.x == GS_CONSUMERS) {
       int stage = 0;
       uint32_t ph = 0;
+      pdl_wait();  // with the whole chain programmatic, the convolution that writes the input may still be running
+      pdl_launch_dependents();
       for (int combo = 0; combo < ncombo; ++combo) {
         const int s = combo < p.chunks[0] ? 0 : 1, chunk = s ? combo - p.chunks[0] : combo;
         const CUtensorMap* map = s ? &mapIn1 : &mapIn0;

@@ -49,7 +49,11 @@ struct ConvArgs {
   float* splitk_scratch = nullptr;
   size_t splitk_bytes = 0;
   int splitk_allowed = 0;
-  int strip_allowed = 1;    // (unit-test entry point default; the engine passes its `strip` option) strip variant: A staged once per (dz, chunk), 9 in-plane taps by row-shifted descriptors
+  int strip_allowed = 2;    // (unit-test entry point default; the engine passes its `strip` option) strip variant: A staged once per (dz, chunk),
+                            // 9 in-plane taps by row-shifted descriptors.  1 = large layers only, 2 = also 12..23-wide planes
+  int strip_maxw = 8;       // strip variant: most stages of the weight ring (as many as fit beside the two strips are used)
+  int pdl = 0;              // tcgen05 kernels: launch with programmatic stream serialisation (the prologue overlaps the tail of the
+                            // kernel before; every thread executes griddepcontrol.wait before it touches global memory)
   int cluster_allowed = 1;  // 2-CTA clusters sharing the weight tile by TMA multicast (big layers)
   int head_v2_allowed = 1;  // head conv: 32x16x4 bricks, 8 voxels per thread, cp.async double-buffered channel stages
   int stem_tc_allowed = 1;  // Cin == 2 stem as one M128 x Cout x K64 tcgen05 tile per 128 voxels (16-bit modes)
@@ -59,7 +63,8 @@ inline int chsum_slots() { return sm_count(); }  // one per persistent CTA (unus
 int conv_simt(const ConvArgs& a, cudaStream_t s);
 // thin ends of the network on the CUDA cores with smem-staged halo bricks (conv_small.cu)
 bool conv_stem_eligible(const ConvArgs& a);  // Cin == 2
-int conv_stem(const ConvArgs& a, cudaStream_t s);
+int conv_stem(ConvArgs& a, cudaStream_t s);
+int conv_stem_chsum_slots(const ConvArgs& a);  // slots of chsum_out the tensor-core stem fills (0 = none)
 bool conv_head_eligible(const ConvArgs& a);  // Cout <= 2, fp32, planar output
 int conv_head(const ConvArgs& a, cudaStream_t s);
 // tcgen05 path; returns DDPM3D_ERR_ARG (without launching) when the shape is not eligible.
@@ -107,6 +112,7 @@ struct GnArgs {
   // per-source channel sums produced by the preceding convolutions' epilogues (see ConvArgs::chsum_out); when
   // every source has them the statistics pass is skipped
   const float* chsum[2] = {nullptr, nullptr};
+  int chsum_P[2] = {0, 0};                  // slots per source (0 = chsum_slots(): one per SM; the stem has one per CTA)
   // the sums are over (x - bias_c) of the producing convolution (no cancellation when a bias dominates): its bias [C_s]
   const float* chsum_bias[2] = {nullptr, nullptr};
   // scratch (owned by the caller / workspace)

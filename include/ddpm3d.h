@@ -207,9 +207,11 @@ int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total);
  * convolution's epilogue instead of a separate pass over the tensor;
  * "split_k" (0/1, default 1): convolutions with too few tiles to fill the GPU deal their k-steps evenly to the CTAs
  * (stream-K: fp32 partials, deterministic fix-up pass);
- * "strip" (0/1, default 1): large 3x3x3 layers stage the A operand once per (dz, channel chunk) and address the 9
+ * "strip" (0/1/2, default 2): 3x3x3 layers stage the A operand once per (dz, channel chunk) and address the 9
  * in-plane taps through row-shifted descriptors, with swapped MMA operands (M = channels, N = up to 256 voxels):
- * half the L2 traffic, -9 % on the network step;
+ * half the L2 traffic, -9 % on the network step.  1 = only planes >= 24 wide with >= 2 tiles per SM, 2 = also 12..23-wide
+ * planes (one tile per plane) where that beats the stream-K brick kernel; "strip_w" (3..8, default 8): most stages of its
+ * weight ring (as many as fit beside the two strips are used);
  * "cluster" (0/1, default 0): 2-CTA clusters multicast the weight tile (neutral);
  * "fold_identity" (0/1, default 1): identity skips enter the second conv of a ResBlock as a unit-weight 1x1x1 source;
  * "stem_tc" (0/1, default 1): the Cin == 2 stem runs as one tcgen05 tile per 128 voxels in the 16-bit modes;
@@ -217,8 +219,11 @@ int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total);
  * "slab_p2p" (0/1, default 1; set before ddpm3d_set_comm): z-slab sharding exchanges halo planes and GroupNorm sums through
  * peer-mapped memory (CUDA IPC over NVLink: the producing kernels store into the neighbours' halo planes, sequence-numbered
  * flags order the accesses) instead of NCCL send/recv and all-gather; needs equal slabs and peer access, else NCCL is used;
- * "pdl" (0/1, default 1): the GroupNorm apply kernel is launched with programmatic stream serialisation so that its
- * prologue overlaps the finalize kernel before it (griddepcontrol.wait / launch_dependents);
+ * "pdl" (0/1/2, default 2): programmatic dependent launch (griddepcontrol.wait / launch_dependents).  1 = the GroupNorm
+ * apply kernel may be scheduled while the finalize kernel before it runs; 2 = the whole convolution / GroupNorm chain:
+ * the finalize kernel is scheduled while the producing convolution runs, and a tcgen05 convolution sets up its barriers,
+ * TMEM and descriptors while the apply pass before it drains (every thread waits for the grid before it before touching
+ * global memory);
  * "head_tc" (0/1, default 1): 16-bit modes with 64 / 128 model channels: out.0 GroupNorm apply + SiLU + out.2 conv as one
  * tcgen05 kernel (the contraction over channels once per voxel, the 27 taps as a shifted sum); 0 = GroupNorm pass writing
  * fp32 + the CUDA-core head. */
@@ -241,7 +246,8 @@ int ddpm3d_profile_read(ddpm3d_ctx* ctx, ddpm3d_prof_record* out, int cap);
  * k = tap*Cin + ci, tap = (dz*3+dh)*3+dw (taps=9: tap = dh*3+dw);
  * bias fp32 [Cout]; residual (optional, [B][Z][Ho][Wo][Cout]) is added in the epilogue.
  * path: 1 SIMT, 2 tcgen05 (bf16 / fp16, Cin%64==0, Cout%64==0; s==2 through element-strided TMA boxes), 3 / 4 the Cin==2 stem kernels
- * (3: tcgen05 tile per 128 voxels in the 16-bit modes, 4: CUDA cores). */
+ * (3: tcgen05 tile per 128 voxels in the 16-bit modes, 4: CUDA cores), 5 / 6 tcgen05 with the strip variant off / restricted
+ * to the large layers ("strip" option levels 0 / 1), 7 the strip variant with a 4-stage weight ring. */
 int ddpm3d_k_conv3d(int dtype, int path, const void* in, const void* w, const float* bias, const void* residual,
                     void* out, int B, int Z, int H, int W, int Cin, int Cout, int taps, int stride_hw, void* stream);
 

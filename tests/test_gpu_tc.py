@@ -39,6 +39,10 @@ from test_gpu_model import TOL, build  # noqa: E402
     (128, 256, (1, 32, 48, 48), 27, True),   # two output-channel tiles
     (64, 128, (1, 4, 192, 192), 27, False),  # two 96-wide bands per plane (halo column shared between bands)
     (64, 128, (1, 12, 80, 80), 27, True),    # band width that is not a power of two
+    # strip variant on small planes ("strip" level 2): one tile of 160 / 176 padded-flattened positions per plane
+    (128, 384, (1, 64, 16, 16), 27, False),  # 16-wide planes: two 160-position tiles per plane, the second one ragged
+    (128, 128, (1, 220, 20, 12), 27, True),  # 12-wide, 20 rows: N = 160, residual
+    (192, 384, (1, 60, 12, 12), 27, True),   # 12 x 12 planes, N = 176, three channel tiles (the shipped 12^2 level)
 ])
 @pytest.mark.parametrize("dt", [N.BF16, N.FP16])
 def test_conv3d_tcgen05(Cin, Cout, shape, taps, res, dt):
@@ -57,6 +61,9 @@ def test_conv3d_tcgen05(Cin, Cout, shape, taps, res, dt):
     tc = conv3d(dt, 2, *args)
     simt = conv3d(dt, 1, *args)
     assert max_rel(from_cl(tc), ref) <= ROUND_TOL[dt]
+    # the same layer with the strip variant off (brick / stream-K kernel) and restricted to the large layers
+    for path in (5, 6):
+        assert max_rel(conv3d(dt, path, *args).float().cpu(), simt.float().cpu()) <= 1.5 * ROUND_TOL[dt]
     # same 16-bit inputs, fp32 accumulation in both: they may differ by one output rounding at most
     assert max_rel(tc.float().cpu(), simt.float().cpu()) <= 1.5 * ROUND_TOL[dt]
     frac_equal = float((tc == simt).float().mean())
@@ -149,6 +156,35 @@ def test_fused_groupnorm_statistics_agree_with_the_separate_pass():
     assert max_rel(outs[1], outs[0]) <= 3e-3
 
 
+def test_fused_statistics_on_the_shipped_architecture():
+    """The same on the shipped network with 96 x 96 planes (8 of them): here the stem's tensor-core kernel, the strip
+    kernel with a nearest-upsampled residual (up ResBlocks at the top level) and the brick kernels all hand channel sums
+    to the GroupNorm that follows; only the stream-K layers still take the statistics pass."""
+    from oracle.weights import synth_state_dict
+    from ddpm3d_b200 import script_util as su
+    flags = cases.sr_flags(use_fp16=True)
+    sd = synth_state_dict(cases.cfg_from_flags(flags), seed=4)
+    shape = (1, 1, 8, 96, 96)
+    low, x, _ = synth_inputs(shape, 0)
+    t = torch.tensor([321], device=DEV)
+    outs, n_launch = {}, {}
+    for fuse in (1, 0):
+        model, _ = su.sr_create_model_and_diffusion(**flags)
+        model.load_state_dict(sd)
+        model.to(DEV)
+        model.set_half_dtype("fp16")
+        model.convert_to_fp16()
+        model.eval()
+        model.set_option("fuse_stats", fuse)
+        a = model(x.to(DEV), t, low_res=low.to(DEV)).cpu()
+        b = model(x.to(DEV), t, low_res=low.to(DEV)).cpu()
+        assert torch.equal(a, b)
+        outs[fuse] = a
+    err = max_rel(outs[1], outs[0])
+    print(f"C2 architecture, fused vs separate GroupNorm statistics: max-rel {err:.2e}")
+    assert err <= 3e-3
+
+
 @pytest.mark.parametrize("half", [True, "fp16", "bf16_strict"])
 @pytest.mark.parametrize("shape,learn_sigma,ch", [((1, 1, 7, 16, 32), True, 64), ((2, 1, 3, 48, 16), False, 64),
                                                   ((1, 1, 1, 16, 16), True, 64), ((1, 1, 5, 32, 32), True, 128)])
@@ -173,7 +209,8 @@ def test_fused_head_matches_the_unfused_head(half, shape, learn_sigma, ch):
     assert err <= 1e-3  # fp16 rounding of hn and of the head weights, fp32 accumulation
 
 
-@pytest.mark.parametrize("opts", [dict(strip=1, fold_identity=1), dict(fold_identity=1), dict(strip=1), dict(cluster=1), dict(stem_tc=0), dict(head_tc=0)])
+@pytest.mark.parametrize("opts", [dict(strip=2, fold_identity=1), dict(strip=1), dict(strip=0), dict(fold_identity=0), dict(cluster=1), dict(stem_tc=0),
+                                  dict(head_tc=0), dict(pdl=0), dict(pdl=1)])
 def test_c2_architecture_with_kernel_options(opts):
     """The optional kernel variants (strip staging with swapped MMA operands, identity skips folded into the
     accumulation as unit-weight 1x1x1 sources, weight multicast in 2-CTA clusters) on the shipped network:

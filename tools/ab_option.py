@@ -1,5 +1,5 @@
 """A/B a library option inside one process (alternating, to cancel box / clock drift):
-python tools/ab_option.py <option> [reps]   -> per-kind ms for option=1 and option=0."""
+python tools/ab_option.py <option>[:a:b] [reps] [fixed=value ...]  -> per-kind ms for option=a and option=b (default 1 and 0)."""
 import os, sys, collections
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -8,6 +8,10 @@ import bench
 from ddpm3d_b200 import script_util as su
 
 opt = sys.argv[1]
+VALS = (1, 0)
+if ":" in opt:
+    opt, va, vb = opt.split(":")
+    VALS = (int(va), int(vb))
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 fixed = [a.split("=") for a in sys.argv[3:]]
 dev = torch.device("cuda", 0)
@@ -21,10 +25,10 @@ for k_, v_ in fixed:
     model.set_option(k_, int(v_))
 for _ in range(3):
     model(x, t, low_res=low)
-res = {0: collections.defaultdict(float), 1: collections.defaultdict(float)}
-wall = {0: [], 1: []}
+res = {v: collections.defaultdict(float) for v in VALS}
+wall = {v: [] for v in VALS}
 for r in range(reps):
-    for v in (1, 0):
+    for v in VALS:
         model.set_option(opt, v)
         model.set_option("profile", 0)
         for _ in range(2):
@@ -41,6 +45,6 @@ for r in range(reps):
         model(x, t, low_res=low)
         for kind, ms, work in model.profile_read():
             res[v][kind] += ms / reps
-for v in (1, 0):
+for v in VALS:
     print(f"{opt}={v}: graph-replayed eval {sorted(wall[v])[len(wall[v]) // 2]:.3f} ms (median of {reps}); per kind:",
           {k: round(m, 3) for k, m in res[v].items()})
