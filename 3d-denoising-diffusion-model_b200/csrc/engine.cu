@@ -587,7 +587,7 @@ struct Run {
     a.cluster_allowed = ctx->cluster;
     a.strip_allowed = ctx->strip;
     a.strip_maxw = ctx->strip_w;
-    a.pdl = ctx->pdl >= 2;
+    a.pdl = ctx->pdl >= 2 && !ctx->profile;  // (an operator bracket between two kernels would time the overlap, not the operator)
     a.stem_tc_allowed = ctx->stem_tc;
     a.head_v2_allowed = ctx->head_v2;
     ++launches;
@@ -616,7 +616,7 @@ struct Run {
   int gn_stats(GnArgs& g) {
     g.B = B;
     g.Z = Z;
-    g.pdl = ctx->pdl;
+    g.pdl = (ctx->pdl >= 2 && ctx->profile) ? 1 : ctx->pdl;
     const int Ctot = g.C[0] + g.C[1];
     g.n_chunks = gn_chunks((int64_t)Z * g.H * g.W);
     g.partials = (double*)arena.alloc((size_t)B * g.n_chunks * 64 * sizeof(double));
@@ -632,7 +632,8 @@ struct Run {
   int gn(GnArgs& g) {
     g.B = B;
     g.Z = Z;
-    g.pdl = ctx->pdl;  // 1: finalize -> apply; 2: also conv -> finalize and apply -> conv (the whole conv / GroupNorm chain)
+    // 1: finalize -> apply; 2: also conv -> finalize and apply -> conv (the whole conv / GroupNorm chain; not under the profiler's brackets)
+    g.pdl = (ctx->pdl >= 2 && ctx->profile) ? 1 : ctx->pdl;
     g.stream_allowed = ctx->gn_stream;
     g.stream_min_mb = ctx->gn_stream_mb;
     const int Ctot = g.C[0] + g.C[1];
