@@ -1159,6 +1159,9 @@ int conv_tc_strip(ConvArgs& a, const StripPlan& plan, bool chsum, cudaStream_t s
   p.res = a.residual;
   p.res_mode = a.residual ? a.res_mode : RES_NONE;
   p.out = a.out;
+  // with a pooled residual the epilogue (four residual rows per voxel) already takes as long as the tile's MMAs: the second
+  // transpose the sums then need made that layer 29 % slower, more than the statistics pass it saves (r4h layer table)
+  if (a.residual && a.res_mode == RES_POOL) chsum = false;
   p.chsum = chsum ? a.chsum_out : nullptr;
   p.cs_slots = chsum_slots();
   p.cs_off = (uint32_t)((size_t)2 * plan.strip_stride + (size_t)plan.NW * 128 * BK * 2 + 1024);

@@ -360,13 +360,20 @@ __device__ __forceinline__ void chsum_group_sums(const float* __restrict__ cs0, 
       if (sl[u] == 0) { s += n_vox * bcd; q += n_vox * bcd * bcd; }
     }
   }
-  sh[0][tid] = s;
-  sh[1][tid] = q;
-  __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (tid < o) { sh[0][tid] += sh[0][tid + o]; sh[1][tid] += sh[1][tid + o]; }
-    __syncthreads();
+  // fixed-order reduction: butterfly inside each of the four warps, then the four partials in warp order (one barrier
+  // instead of a seven-level shared-memory tree)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
   }
+  if ((tid & 31) == 0) { sh[0][tid >> 5] = s; sh[1][tid >> 5] = q; }
+  __syncthreads();
+  if (tid == 0) {
+    sh[0][0] = ((sh[0][0] + sh[0][1]) + sh[0][2]) + sh[0][3];
+    sh[1][0] = ((sh[1][0] + sh[1][1]) + sh[1][2]) + sh[1][3];
+  }
+  __syncthreads();
 }
 
 // finalize from the conv epilogues' channel sums.  grid (32 groups, B), 128 threads.
@@ -381,6 +388,19 @@ __global__ void __launch_bounds__(128) gn_finalize_chsum_kernel(const float* __r
   const int Ctot = C0 + C1, gpc = Ctot / 32;
   pdl_wait();               // (pdl = 2) this grid was scheduled while the last epilogues of the producing convolution ran
   pdl_launch_dependents();  // the apply kernel may start its prologue now; it waits for this grid before reading `ab`
+  // this thread's channel (a group has at most 128 of them up to 4096 channels): fetch its affine parameters now, so
+  // that their latency overlaps the reduction instead of following it
+  const int c0 = g * gpc + tid;
+  const bool mine = tid < gpc;
+  float gam = 0.f, bet = 0.f, fsc = 1.f, fsh = 0.f;
+  if (mine) {
+    gam = gamma[c0];
+    bet = beta[c0];
+    if (film) {  // h = norm(h) * (1 + scale) + shift
+      fsc = 1.0f + film[(int64_t)b * film_stride + c0];
+      fsh = film[(int64_t)b * film_stride + Ctot + c0];
+    }
+  }
   chsum_group_sums(cs0, cs1, bias0, bias1, C0, C1, P0, P1, n_vox, g, b, sh);
   const double mean = sh[0][0] * inv_count;
   double var = sh[1][0] * inv_count - mean * mean;
@@ -388,7 +408,17 @@ __global__ void __launch_bounds__(128) gn_finalize_chsum_kernel(const float* __r
   const float fmean = (float)mean, rstd = (float)(1.0 / sqrt(var + 1e-5));
   float* A = ab + (int64_t)b * 2 * Ctot;
   float* Bv = A + Ctot;
-  for (int c = g * gpc + tid; c < (g + 1) * gpc; c += 128) {
+  if (mine) {
+    float a = rstd * gam;
+    float o = bet - fmean * a;
+    if (film) {
+      a *= fsc;
+      o = o * fsc + fsh;
+    }
+    A[c0] = a;
+    Bv[c0] = o;
+  }
+  for (int c = c0 + 128; c < (g + 1) * gpc; c += 128) {  // (more than 4096 channels)
     float a = rstd * gamma[c];
     float o = beta[c] - fmean * a;
     if (film) {

@@ -621,7 +621,7 @@ struct Run {
     g.n_chunks = gn_chunks((int64_t)Z * g.H * g.W);
     g.partials = (double*)arena.alloc((size_t)B * g.n_chunks * 64 * sizeof(double));
     g.ab = (float*)arena.alloc((size_t)B * 2 * Ctot * sizeof(float));
-    launches += 2;
+    launches += (!g.pre_add && g.chsum[0] && (g.C[1] == 0 || g.chsum[1])) ? 1 : 2;  // (statistics,) finalize
     if (arena.dry) return DDPM3D_OK;
     prof_begin(3, 0.0);
     const int r = gn_finalize_only(g, s);
@@ -648,13 +648,13 @@ struct Run {
       launches += 2;
       if (arena.dry && g.out_zpad && p2p()) launches += 2;  // (the live path counts them in halo_begin / halo_end)
     }
-    launches += 3;
+    const bool have_cs = !g.pre_add && g.chsum[0] && (g.C[1] == 0 || g.chsum[1]);
+    const bool fused = !zp && have_cs;
+    launches += fused ? 2 : 3;  // (statistics,) finalize, apply
     if (arena.dry) return DDPM3D_OK;
     const double n = (double)B * Z * g.H * g.W * Ctot;
     const double in_b = is_half_dt(g.dt) ? 2 : 4, out_b = (is_half_dt(g.dt) && !g.out_f32) ? 2 : 4;
     const double scale = g.resample == RS_POOL ? 0.25 : (g.resample == RS_UP ? 4.0 : 1.0);
-    const bool have_cs = !g.pre_add && g.chsum[0] && (g.C[1] == 0 || g.chsum[1]);
-    const bool fused = !zp && have_cs;
     prof_begin(4, n * ((have_cs ? 1 : 2) * in_b + out_b * scale));
     int r;
     if (fused) {
