@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libddpm3d.so")
+# DDPM3D_LIB: another build of the same library (same-box A/B of two kernel versions; tools only)
+LIB_PATH = os.environ.get("DDPM3D_LIB") or os.path.join(HERE, "libddpm3d.so")
 
 FP32, BF16, FP16, BF16_STRICT = 0, 1, 2, 3
 MEAN_PREVIOUS_X, MEAN_START_X, MEAN_EPSILON = 0, 1, 2

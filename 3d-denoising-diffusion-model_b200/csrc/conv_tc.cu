@@ -441,6 +441,8 @@ struct StripParams {
   int B, Z, H, W, Cout;
   int Wb, Wp, nbands, nh, tiles_per_band, nNt, num_tiles, zoff;
   int NV;            // voxels (padded-flattened positions) per tile = the MMA N: a multiple of 16, <= 256
+  int NP, nZt;       // z-planes per tile (1, or 2 on small planes: both planes share every weight tile) and ceil(Z / NP).
+                     // With NP = 2 the two plane accumulators fill the 512 TMEM columns: no double buffering
   int NW;            // stages of the weight ring (3 .. STRIP_MAXW): as many as fit beside the two strips.  A stage lasts
                      // 2 NV tensor cycles, so 4 stages of a 208-position tile cover ~1700 cycles -- less than a loaded L2 round trip
   int nsrc, chunks[3], n_macro_main, n_macro, Cin;
@@ -456,7 +458,7 @@ struct StripParams {
   uint32_t cs_off;
 };
 
-template <typename T, typename TS, int NB>
+template <typename T, typename TS, int NB, int NP>
 __global__ void __launch_bounds__(STRIP_THREADS, 1)
 conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW, const StripParams p) {
@@ -508,8 +510,8 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     int m = tile / p.nNt;
     const int tq = m % p.tiles_per_band; m /= p.tiles_per_band;
     const int band = m % p.nbands; m /= p.nbands;
-    z = m % p.Z;
-    b = m / p.Z;
+    z = (m % p.nZt) * NP;  // first plane of the tile
+    b = m / p.nZt;
     w0 = band * p.Wb;
     q0 = tq * p.NV;
     n0 = nt * BN;
@@ -578,6 +580,8 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
       const uint32_t idesc_extra = make_idesc(128, p.NV, !std::is_same<TS, f16>::value);
       int sb = 0, ws = 0, acc = 0;
       uint32_t sph = 0, wph = 0, aph = 0;
+      constexpr int nacc = NP == 2 ? 1 : 2;               // accumulator buffers (of NP * ACC_COLS columns)
+      const uint32_t plane_rows = (uint32_t)(p.nh * p.Wp);  // the planes of a strip follow each other (TMA box order)
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int b, z, w0, q0, n0;
         decode(tile, b, z, w0, q0, n0);
@@ -601,10 +605,14 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
             // 128 tensor cycles instead of 2 x (4 + 4) KB -- shared-memory read bandwidth (128 B/clk, shared with the
             // TMA fills) is what holds the M=128, N=128 form at ~65 % tensor-pipe utilisation.
             const uint64_t wdesc = make_sw128_desc(w_base + ws * W_BYTES);
-            const uint64_t sdesc = make_sw128_desc(strip + (uint32_t)(offbase + dh * p.Wp + dw) * 128u);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_bf16(d_tmem, wdesc + (uint64_t)(2 * k), sdesc + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+            for (int pl = 0; pl < NP; ++pl) {  // the planes of the tile share this weight tile
+              const uint64_t sdesc = make_sw128_desc(strip + ((uint32_t)pl * plane_rows + (uint32_t)(offbase + dh * p.Wp + dw)) * 128u);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_bf16(d_tmem + (uint32_t)(pl * ACC_COLS), wdesc + (uint64_t)(2 * k), sdesc + (uint64_t)(2 * k), idesc,
+                          (first && k == 0) ? 0u : 1u);
+            }
             first = false;
             umma_commit(wempty(ws));
             if (++ws == NW) { ws = 0; wph ^= 1; }
@@ -613,7 +621,7 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
           if (++sb == 2) { sb = 0; sph ^= 1; }
         }
         umma_commit(tfull(acc));
-        if (++acc == 2) { acc = 0; aph ^= 1; }
+        if (++acc == nacc) { acc = 0; aph ^= 1; }
       }
       pdl_launch_dependents();
     }
@@ -632,16 +640,21 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     }
     int acc = 0;
     uint32_t aph = 0;
+    constexpr int nacc = NP == 2 ? 1 : 2;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      int b, z, w0, q0, n0;
-      decode(tile, b, z, w0, q0, n0);
+      int b, z0, w0, q0, n0;
+      decode(tile, b, z0, w0, q0, n0);
       const int co = n0 + sub * 32 + lane;
       const float bias_co = __ldg(p.bias + co);
       const bool with_res = p.res_mode != RES_NONE;
       float ts = 0.f, tq = 0.f;
       mbar_wait(tfull(acc), aph);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+#pragma unroll 1
+      for (int pl = 0; pl < NP; ++pl) {
+      const int z = z0 + pl;
+      if (NP > 1 && z >= p.Z) break;  // odd Z: the second plane of the last pair does not exist (uniform over the CTA)
+      const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * ACC_COLS + pl * ACC_COLS);
 #pragma unroll 1
       for (int vc = 0; vc * 32 < p.NV; ++vc) {
         uint32_t r[32];
@@ -734,6 +747,7 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
           }
         }
       }
+      }  // planes of the tile
       if (p.chsum) {  // this thread is the only one of the CTA that owns channel `co`
         float* a2 = cs_acc + ((size_t)b * p.Cout + co) * 2;
         a2[0] += ts;
@@ -742,7 +756,7 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(acc));
-      if (++acc == 2) { acc = 0; aph ^= 1; }
+      if (++acc == nacc) { acc = 0; aph ^= 1; }
     }
     if (p.chsum) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -1038,16 +1052,19 @@ TcPlan make_plan(const ConvArgs& a, int nk) {
 namespace {
 
 struct StripPlan {
-  int Wb, Wp, nbands, nh, tiles_per_band, nNt, num_tiles, NW, NV;
+  int Wb, Wp, nbands, nh, tiles_per_band, nNt, num_tiles, NW, NV, NP, nZt;
   uint32_t strip_bytes, strip_stride;
   size_t smem;
 };
 
 // strip_allowed: 0 never; 1 the large layers only (planes >= 24 wide, tiles of 192..256 positions, >= 2 tiles per SM);
-// 2 also small planes (12..23 wide: one tile of 160..256 padded-flattened positions per plane).  For those the brick
-// kernel is bound by the bytes it pulls through L2 per MMA (one 16 KB A tile per tap, no reuse) and runs stream-K with an
-// fp32 fix-up pass; the strip form computes ~20 % pad positions but moves a third of the bytes and keeps the GroupNorm
-// channel sums in the epilogue.  DDPM3D_STRIP_EFF (percent) overrides the acceptance threshold of level 2 (tuning).
+// 2 also small planes (12..23 wide): one tile of 160..176 padded-flattened positions per plane and TWO z-planes per
+// tile (NP = 2), whose MMAs share every weight tile and whose accumulators fill the 512 TMEM columns.  For those planes
+// the brick kernel is bound by the bytes it pulls through L2 per MMA (one 16 KB A tile per tap, no reuse) and runs
+// stream-K with an fp32 fix-up pass.  With ONE plane per tile the strip form loses (a 16 KB weight tile per tap and
+// 2 x 176 tensor cycles is more than the L2 fabric delivers: 125 vs 110 us on 384 -> 384 at 12 x 12 x 96); with two it
+// wins 8-19 % on the 384-channel 12^2 layers (93 vs 110 us) and keeps the GroupNorm channel sums in the epilogue.
+// DDPM3D_STRIP_EFF (percent) overrides the acceptance threshold of level 2 (tuning).
 bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
   if (!a.strip_allowed || !is_half_dt(a.dt) || (a.taps != 27 && a.taps != 9) || a.stride_hw != 1 || a.out_planar_f32) return false;
   if (a.Cout % 128 != 0 || a.main.C % BK != 0) return false;
@@ -1083,22 +1100,30 @@ bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
   t.nh = 3 + (int)ceil_div(t.NV + 1, t.Wp);
   if (t.nh > 256) return false;
   t.nNt = a.Cout / 128;
-  const int64_t tiles = (int64_t)a.B * a.Z * t.nbands * t.tiles_per_band * t.nNt;
+  t.NP = 1;
+  t.nZt = a.Z;
+  int64_t tiles = (int64_t)a.B * a.Z * t.nbands * t.tiles_per_band * t.nNt;
   if (tiles >= ((int64_t)1 << 31)) return false;
   const int sms = sm_count();
   if (tiles < 2 * (int64_t)sms) classic = false;
   if (!classic) {
-    if (!small_ok || tiles < sms) return false;
+    if (!small_ok) return false;
+    // small planes: two z-planes per tile share every weight tile (with one plane of < 192 positions per tile the
+    // 16 KB weight tile per tap is more than the L2 fabric delivers); their accumulators fill the 512 TMEM columns
+    t.NP = 2;
+    t.nZt = (int)ceil_div(a.Z, 2);
+    tiles = (int64_t)a.B * t.nZt * t.nbands * t.tiles_per_band * t.nNt;
+    if (2 * tiles < sms) return false;
     // useful positions x how full the last wave is: accept from 0.60 (a 12 x 12 plane with 3 channel tiles: 0.78 x 0.97)
     static const double thr = [] {
       const char* e = getenv("DDPM3D_STRIP_EFF");
       return e ? atof(e) / 100.0 : 0.60;
     }();
-    const double wave = (double)tiles / ((double)ceil_div(tiles, sms) * sms);
+    const double wave = (double)tiles / ((double)ceil_div(tiles, sms) * sms) * ((double)a.Z / (2.0 * t.nZt));
     if (best_eff * wave < thr) return false;
   }
   t.num_tiles = (int)tiles;
-  t.strip_bytes = (uint32_t)(t.nh * t.Wp * 128);
+  t.strip_bytes = (uint32_t)(t.NP * t.nh * t.Wp * 128);
   t.strip_stride = (t.strip_bytes + 1023u) & ~1023u;
   const size_t cs = CS_TR_BYTES / 2 + (want_chsum ? (size_t)a.B * a.Cout * 2 * sizeof(float) : 0);  // the transpose scratch is always needed
   for (int nw = std::max(3, std::min(STRIP_MAXW, a.strip_maxw)); nw >= 3; --nw) {
@@ -1114,7 +1139,8 @@ int launch_strip(const CUtensorMap* maps, const CUtensorMap& mapW, const StripPa
                  bool pdl) {
   static uint64_t configured = 0;
   if (first_use_on_device(&configured)) {
-    DD_CUDA(cudaFuncSetAttribute(conv_tc_strip_kernel<T, TS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_strip_kernel<T, TS, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_strip_kernel<T, TS, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));
   }
   const int grid = std::min(p.num_tiles, sm_count());
   if (p.chsum && grid < p.cs_slots)
@@ -1129,7 +1155,8 @@ int launch_strip(const CUtensorMap* maps, const CUtensorMap& mapW, const StripPa
   attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_strip_kernel<T, TS, 2>, maps[0], maps[1], maps[2], mapW, p));
+  if (plan.NP == 2) DD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_strip_kernel<T, TS, 2, 2>, maps[0], maps[1], maps[2], mapW, p));
+  else DD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_strip_kernel<T, TS, 2, 1>, maps[0], maps[1], maps[2], mapW, p));
   return DDPM3D_OK;
 }
 
@@ -1139,6 +1166,8 @@ int conv_tc_strip(ConvArgs& a, const StripPlan& plan, bool chsum, cudaStream_t s
   p.Wb = plan.Wb; p.Wp = plan.Wp; p.nbands = plan.nbands; p.nh = plan.nh; p.tiles_per_band = plan.tiles_per_band;
   p.nNt = plan.nNt; p.num_tiles = plan.num_tiles; p.zoff = a.in_zpad;
   p.NV = plan.NV;
+  p.NP = plan.NP;
+  p.nZt = plan.nZt;
   p.NW = plan.NW;
   p.nsrc = 1 + a.n_extra;
   p.chunks[0] = a.main.C / BK;
@@ -1168,11 +1197,11 @@ int conv_tc_strip(ConvArgs& a, const StripPlan& plan, bool chsum, cudaStream_t s
   a.chsum_written = chsum ? 1 : 0;
   const CUtensorMapDataType tdt = tmap_dtype(a.dt), tdt_io = tmap_dtype(a.io_dt());
   CUtensorMap maps[3];
-  DD_TRY(make_act_map(&maps[0], tdt, a.main.ptr, a.B, a.Z + 2 * a.in_zpad, a.Ho, a.Wo, a.main.C, plan.Wp, plan.nh, 1));
+  DD_TRY(make_act_map(&maps[0], tdt, a.main.ptr, a.B, a.Z + 2 * a.in_zpad, a.Ho, a.Wo, a.main.C, plan.Wp, plan.nh, plan.NP));
   maps[1] = maps[0];
   maps[2] = maps[0];
   for (int e = 0; e < a.n_extra; ++e)
-    DD_TRY(make_act_map(&maps[1 + e], tdt_io, a.extra[e].ptr, a.B, a.Z, a.Ho, a.Wo, a.extra[e].C, plan.Wp, plan.nh, 1));
+    DD_TRY(make_act_map(&maps[1 + e], tdt_io, a.extra[e].ptr, a.B, a.Z, a.Ho, a.Wo, a.extra[e].C, plan.Wp, plan.nh, plan.NP));
   CUtensorMap mapW;
   DD_TRY(make_w_map(&mapW, tdt, a.w, a.Cout, a.w_ld ? a.w_ld : Ktot, 128));
   const bool pdl = a.pdl != 0;

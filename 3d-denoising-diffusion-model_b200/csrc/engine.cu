@@ -177,7 +177,7 @@ struct ddpm3d_ctx {
   float* d_img = nullptr;
   size_t img_cap = 0;
   // options
-  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 1, strip_w = 4, fold_identity = 1, stem_tc = 1, head_v2 = 1,
+  int use_graph = 1, conv_path = 0, profile = 0, fuse_stats = 1, split_k = 1, cluster = 0, strip = 2, strip_w = 4, fold_identity = 1, stem_tc = 1, head_v2 = 1,
       head_tc = 1, slab_p2p = 1, pdl = 2, gn_stream = 1, gn_stream_mb = 48;
   float* splitk_buf = nullptr;  // fp32 partial tiles of split-K convolutions (sized by the dry run)
   size_t splitk_cap = 0, splitk_need = 0;

@@ -50,8 +50,8 @@ struct ConvArgs {
   size_t splitk_bytes = 0;
   int splitk_allowed = 0;
   int strip_allowed = 2;    // (unit-test entry point default; the engine passes its `strip` option) strip variant: A staged once per (dz, chunk),
-                            // 9 in-plane taps by row-shifted descriptors.  1 = large layers only, 2 = also 12..23-wide planes
-  int strip_maxw = 8;       // strip variant: most stages of the weight ring (as many as fit beside the two strips are used)
+                            // 9 in-plane taps by row-shifted descriptors.  1 = large layers only, 2 = also 12..23-wide planes (two z-planes per tile)
+  int strip_maxw = 4;       // strip variant: most stages of the weight ring (as many as fit beside the two strips are used)
   int pdl = 0;              // tcgen05 kernels: launch with programmatic stream serialisation (the prologue overlaps the tail of the
                             // kernel before; every thread executes griddepcontrol.wait before it touches global memory)
   int cluster_allowed = 1;  // 2-CTA clusters sharing the weight tile by TMA multicast (big layers)

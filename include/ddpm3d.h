@@ -210,8 +210,8 @@ int ddpm3d_set_slab(ddpm3d_ctx* ctx, int z_begin, int z_total);
  * "strip" (0/1/2, default 2): 3x3x3 layers stage the A operand once per (dz, channel chunk) and address the 9
  * in-plane taps through row-shifted descriptors, with swapped MMA operands (M = channels, N = up to 256 voxels):
  * half the L2 traffic, -9 % on the network step.  1 = only planes >= 24 wide with >= 2 tiles per SM, 2 = also 12..23-wide
- * planes (one tile per plane) where that beats the stream-K brick kernel; "strip_w" (3..8, default 8): most stages of its
- * weight ring (as many as fit beside the two strips are used);
+ * planes, two z-planes per tile sharing every weight tile, where that beats the stream-K brick kernel (the 384-channel
+ * 12 x 12 layers of the shipped network); "strip_w" (3..8, default 4): most stages of its weight ring;
  * "cluster" (0/1, default 0): 2-CTA clusters multicast the weight tile (neutral);
  * "fold_identity" (0/1, default 1): identity skips enter the second conv of a ResBlock as a unit-weight 1x1x1 source;
  * "stem_tc" (0/1, default 1): the Cin == 2 stem runs as one tcgen05 tile per 128 voxels in the 16-bit modes;

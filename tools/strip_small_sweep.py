@@ -33,6 +33,13 @@ def run(path, Cin, Cout, Z, H, W, reps=30, res=False):
 
 
 print(f"DDPM3D_STRIP_EFF={os.environ.get('DDPM3D_STRIP_EFF', '(default 60)')}")
+SHAPES_CLASSIC = [(128, 128, 96, 96, 96), (128, 128, 96, 48, 48), (256, 256, 96, 24, 24)]
+if len(sys.argv) > 1 and sys.argv[1] == "classic":  # the large-layer shapes only, strip variant: `DDPM3D_LIB=... python ... classic`
+    for (Cin, Cout, Z, H, W) in SHAPES_CLASSIC * 2:
+        fl = 2.0 * Z * H * W * Cout * 27 * Cin
+        t2, _ = run(2, Cin, Cout, Z, H, W)
+        print(f"{os.environ.get('DDPM3D_LIB', 'libddpm3d.so')[-18:]:18s} Cin {Cin:4d} Cout {Cout:4d} {Z:4d}x{H}x{W}: {t2:7.1f} us ({fl / t2 / 1e6:6.0f} TF/s)", flush=True)
+    sys.exit(0)
 for (Cin, Cout, Z, H, W) in [(256, 256, 96, 12, 12), (256, 384, 96, 12, 12), (384, 384, 96, 12, 12), (768, 384, 96, 12, 12),
                              (640, 384, 96, 12, 12), (384, 512, 96, 12, 12), (512, 512, 96, 6, 6), (256, 256, 96, 24, 24),
                              (128, 128, 96, 48, 48), (256, 128, 96, 48, 48), (128, 128, 96, 96, 96), (384, 384, 160, 24, 24), (512, 512, 160, 12, 12)]:
