@@ -1113,7 +1113,10 @@ bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
     t.NP = 2;
     t.nZt = (int)ceil_div(a.Z, 2);
     tiles = (int64_t)a.B * t.nZt * t.nbands * t.tiles_per_band * t.nNt;
-    if (2 * tiles < sms) return false;
+    // one wave only: the single accumulator buffer cannot overlap a tile's epilogue with the next tile's MMAs, and over
+    // several waves the stream-K brick kernel is faster again (512 -> 512 on 12 x 12 x 160: 396 vs 286 us; the 640-plane
+    // volume of the c4 leg on one GPU: +2.7 % on the step)
+    if (2 * tiles < sms || tiles > sms) return false;
     // useful positions x how full the last wave is: accept from 0.60 (a 12 x 12 plane with 3 channel tiles: 0.78 x 0.97)
     static const double thr = [] {
       const char* e = getenv("DDPM3D_STRIP_EFF");

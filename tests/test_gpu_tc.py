@@ -41,8 +41,8 @@ from test_gpu_model import TOL, build  # noqa: E402
     (64, 128, (1, 12, 80, 80), 27, True),    # band width that is not a power of two
     # strip variant on small planes ("strip" level 2): tiles of 160 / 176 padded-flattened positions, two z-planes per
     # tile sharing every weight tile (their accumulators fill the 512 TMEM columns)
-    (128, 384, (1, 96, 16, 16), 27, False),  # 16-wide planes: two 160-position tiles per plane, the second one ragged
-    (128, 128, (1, 291, 20, 12), 27, True),  # 12-wide, 20 rows: N = 160, residual, odd Z (the last pair has one plane)
+    (128, 384, (1, 48, 16, 16), 27, False),  # 16-wide planes: two 160-position tiles per plane, the second one ragged
+    (128, 128, (1, 145, 20, 12), 27, True),  # 12-wide, 20 rows: N = 160, residual, odd Z (the last pair has one plane)
     (192, 384, (1, 95, 12, 12), 27, True),   # 12 x 12 planes, N = 176, three channel tiles (the shipped 12^2 level), odd Z
     (128, 384, (2, 48, 12, 12), 27, False),  # batch 2
 ])
