@@ -71,6 +71,7 @@ SIGNATURES = {
     "ddpm3d_launch_count": (C.c_int64, [_P]),
     "ddpm3d_profile_read": (_I, [_P, C.POINTER(ProfRecord), _I]),
     "ddpm3d_k_conv3d": (_I, [_I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "ddpm3d_k_conv_plan": (_I, [_I] * 12 + [C.POINTER(C.c_int32)]),
     "ddpm3d_k_probe_rowshift": (_I, [_P, _I, _P, _I, _I, _P, _P]),
     "ddpm3d_k_groupnorm": (_I, [_I, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
     "ddpm3d_k_conv3d_gn": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

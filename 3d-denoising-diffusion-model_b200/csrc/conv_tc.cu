@@ -988,6 +988,11 @@ int probe_rowshift(const void* a, int rows, const void* ident, int shift, int mo
 
 namespace {
 
+// SM count the planners assume: the device's, or the one a plan query names (host-side tests of the planning logic run
+// without a GPU)
+thread_local int g_plan_sms = 0;
+inline int plan_sms() { return g_plan_sms > 0 ? g_plan_sms : sm_count(); }
+
 struct TcPlan {
   int bw, bh, bz, pw = 0, ph = 0, pz = 0, nW, nH, nZ, MT = 1, BN = 128, S = 1 /* 2 = stream-K */, max_slots = 0;
 };
@@ -1001,7 +1006,7 @@ TcPlan make_plan(const ConvArgs& a, int nk) {
   choose_brick(a.Z, a.Ho, a.Wo, &best.bw, &best.bh, &best.bz);
   const int nW0 = (int)ceil_div(a.Wo, best.bw), nH0 = (int)ceil_div(a.Ho, best.bh), nZ0 = (int)ceil_div(a.Z, best.bz);
   best.nW = nW0; best.nH = nH0; best.nZ = nZ0;
-  const int sms = sm_count();
+  const int sms = plan_sms();
   const double rows = (double)a.B * a.Z * a.Ho * a.Wo;
   double best_cost = 1e30;
   struct Cfg { int MT, BN; double cyc_per_kstep; };
@@ -1104,7 +1109,7 @@ bool strip_plan(const ConvArgs& a, bool want_chsum, StripPlan* out) {
   t.nZt = a.Z;
   int64_t tiles = (int64_t)a.B * a.Z * t.nbands * t.tiles_per_band * t.nNt;
   if (tiles >= ((int64_t)1 << 31)) return false;
-  const int sms = sm_count();
+  const int sms = plan_sms();
   if (tiles < 2 * (int64_t)sms) classic = false;
   if (!classic) {
     if (!small_ok) return false;
@@ -1214,6 +1219,35 @@ int conv_tc_strip(ConvArgs& a, const StripPlan& plan, bool chsum, cudaStream_t s
 }
 
 }  // namespace
+
+// Which kernel and tiling conv_tc() would pick for this layer on a device with `sms` SMs (0 = the current device).
+// out[8] = {kind: 0 not eligible, 1 brick kernel, 2 brick kernel with stream-K, 3 strip kernel; MT | NP (z-planes per
+// strip tile); BN | NV (positions per strip tile = MMA N); tiles; grid; weight-ring stages | split-K slots; k-steps |
+// macro steps; strip box rows}.  Pure host arithmetic: nothing is launched and no device is needed when sms > 0.
+int conv_tc_plan_query(const ConvArgs& a0, int sms, int* out) {
+  ConvArgs a = a0;
+  for (int i = 0; i < 8; ++i) out[i] = 0;
+  if (!conv_tc_eligible(a)) return DDPM3D_OK;
+  g_plan_sms = sms;
+  StripPlan sp;
+  if (strip_plan(a, true, &sp) || strip_plan(a, false, &sp)) {  // (as conv_tc() does when the engine asks for channel sums)
+    const int n = plan_sms();
+    g_plan_sms = 0;
+    const int macro = (a.taps == 27 ? 3 : 1) * (a.main.C / BK) + (a.n_extra > 0 ? a.extra[0].C / BK : 0) + (a.n_extra > 1 ? a.extra[1].C / BK : 0);
+    const int v[8] = {3, sp.NP, sp.NV, sp.num_tiles, std::min(sp.num_tiles, n), sp.NW, macro, sp.nh};
+    for (int i = 0; i < 8; ++i) out[i] = v[i];
+    return DDPM3D_OK;
+  }
+  int nk = a.taps * (a.main.C / BK);
+  for (int e = 0; e < a.n_extra; ++e) nk += a.extra[e].C / BK;
+  const TcPlan plan = make_plan(a, nk);
+  const int n = plan_sms();
+  g_plan_sms = 0;
+  const int tiles = a.B * plan.nW * plan.nH * plan.nZ * (a.Cout / plan.BN);
+  const int v[8] = {plan.S > 1 ? 2 : 1, plan.MT, plan.BN, tiles, plan.S > 1 ? n : std::min(tiles, n), plan.max_slots, nk, 0};
+  for (int i = 0; i < 8; ++i) out[i] = v[i];
+  return DDPM3D_OK;
+}
 
 size_t conv_tc_scratch_bytes(const ConvArgs& a0) {
   ConvArgs a = a0;

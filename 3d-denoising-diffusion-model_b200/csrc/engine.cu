@@ -1696,6 +1696,20 @@ int ddpm3d_k_conv3d(int dtype, int path, const void* in, const void* w, const fl
   return conv_simt(a, (cudaStream_t)stream);
 }
 
+int ddpm3d_k_conv_plan(int dtype, int B, int Z, int H, int W, int Cin, int Cout, int taps, int extra_channels, int split_k,
+                       int strip, int sms, int32_t* out8) {
+  DD_CHECK(out8 != nullptr && B >= 1 && Z >= 1 && H >= 1 && W >= 1, DDPM3D_ERR_ARG, "k_conv_plan: bad argument");
+  ConvArgs a{};
+  a.dt = dtype; a.main = {nullptr, Cin}; a.taps = taps; a.B = B; a.Z = Z; a.Ho = H; a.Wo = W; a.Cout = Cout;
+  if (extra_channels > 0) { a.n_extra = 1; a.extra[0] = {nullptr, extra_channels}; }
+  a.splitk_allowed = split_k;
+  a.strip_allowed = strip;
+  int v[8];
+  DD_TRY(conv_tc_plan_query(a, sms, v));
+  for (int i = 0; i < 8; ++i) out8[i] = v[i];
+  return DDPM3D_OK;
+}
+
 int ddpm3d_k_probe_rowshift(const void* a, int rows, const void* ident, int shift, int mode, float* out, void* stream) {
   DD_CHECK(a && ident && out, DDPM3D_ERR_ARG, "k_probe_rowshift: null argument");
   return probe_rowshift(a, rows, ident, shift, mode, out, (cudaStream_t)stream);

@@ -71,6 +71,7 @@ int conv_head(const ConvArgs& a, cudaStream_t s);
 bool conv_tc_eligible(const ConvArgs& a);
 int conv_tc(ConvArgs& a, cudaStream_t s);
 size_t conv_tc_scratch_bytes(const ConvArgs& a);
+int conv_tc_plan_query(const ConvArgs& a, int sms, int* out8);  // kernel / tiling conv_tc() would pick (host arithmetic only)
 // test-only probe of row-shifted SWIZZLE_128B operand descriptors (see conv_tc.cu)
 int probe_rowshift(const void* a, int rows, const void* ident, int shift, int mode, float* out, cudaStream_t s);  // split-K scratch this launch wants (0 = no split)
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DDPM3D_ABI_VERSION 4
+#define DDPM3D_ABI_VERSION 5
 
 #define DDPM3D_OK 0
 #define DDPM3D_ERR_ARG (-1)     /* bad argument / unsupported configuration */
@@ -250,6 +250,16 @@ int ddpm3d_profile_read(ddpm3d_ctx* ctx, ddpm3d_prof_record* out, int cap);
  * to the large layers ("strip" option levels 0 / 1), 7 the strip variant with a 4-stage weight ring. */
 int ddpm3d_k_conv3d(int dtype, int path, const void* in, const void* w, const float* bias, const void* residual,
                     void* out, int B, int Z, int H, int W, int Cin, int Cout, int taps, int stride_hw, void* stream);
+
+/* Which tcgen05 kernel and tiling ddpm3d_k_conv3d (path 2) / the engine would pick for a 3x3x3 (taps 27), 3x3 (9) or
+ * 1x1x1 (1) layer on a device with `sms` SMs (0 = the current device): the planning logic of csrc/conv_tc.cu as plain host
+ * arithmetic -- nothing is launched and with sms > 0 no device is needed (the CPU test suite pins the plans of the
+ * shipped network).  extra_channels: channels of a folded 1x1x1 skip source (0 = none); split_k / strip: the options of
+ * the same names.  out8 = {kind: 0 not eligible, 1 brick, 2 brick + stream-K, 3 strip; MT | z-planes per strip tile;
+ * BN | positions per strip tile (MMA N); tiles; grid; split-K slots | weight-ring stages; k-steps | macro steps; strip
+ * box rows}. */
+int ddpm3d_k_conv_plan(int dtype, int B, int Z, int H, int W, int Cin, int Cout, int taps, int extra_channels, int split_k,
+                       int strip, int sms, int32_t* out8);
 
 /* Hardware probe used by the tests / design work: D = A[shift : shift+128, :] * I on tcgen05 with the A operand
  * descriptor starting `shift` rows into a [rows][64] bf16 SWIZZLE_128B tile (mode 0: base-offset field 0, mode 1:

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/ddpm3d.h but not exported"
     assert declared == set(N.SIGNATURES), "ctypes binding and header disagree"
-    assert N.lib().ddpm3d_abi_version() == 4
+    assert N.lib().ddpm3d_abi_version() == 5
 
 
 def test_struct_layouts_match_header():
@@ -242,3 +242,39 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["cores"] >= 1 and line["value"] > 0
     assert line["native_so_loaded"] is False  # the reference arm never maps the repo's library
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+def _conv_plan(B, Z, H, W, Cin, Cout, taps=27, extra=0, split_k=1, strip=2, sms=148, dt=None):
+    out = (C.c_int32 * 8)()
+    N.check(N.lib().ddpm3d_k_conv_plan(N.BF16 if dt is None else dt, B, Z, H, W, Cin, Cout, taps, extra, split_k, strip, sms, out))
+    return list(out)
+
+
+def test_conv_plans_of_the_shipped_network():
+    """The planning logic of csrc/conv_tc.cu (plain host arithmetic, no device) on the layer shapes of the shipped
+    network (one 96^3 patch, 148 SMs): which tcgen05 kernel runs each resolution class, with which tile.  kind 3 = strip
+    kernel {z-planes per tile, positions per tile = MMA N, tiles, grid, weight-ring stages, macro steps, strip rows};
+    kind 1 / 2 = brick kernel without / with stream-K {MT, BN, tiles, grid, split-K slots, k-steps}."""
+    # 96^2, 48^2 and the 256-channel 24^2 layers: one z-plane per tile, N chosen to tile the padded plane
+    assert _conv_plan(1, 96, 96, 96, 128, 128) == [3, 1, 256, 3552, 148, 4, 6, 6]       # 3552 tiles = 24 waves exactly
+    assert _conv_plan(1, 96, 96, 96, 128, 128, extra=128)[6] == 8                        # folded skip source: + 2 macro steps
+    assert _conv_plan(1, 96, 48, 48, 128, 128) == [3, 1, 240, 960, 148, 4, 6, 8]        # 2400 = 10 x 240 padded positions
+    assert _conv_plan(1, 96, 24, 24, 256, 256) == [3, 1, 208, 576, 148, 4, 12, 12]      # 624 = 3 x 208
+    # small planes that make one wave: two z-planes per tile share every weight tile
+    assert _conv_plan(1, 96, 12, 12, 384, 384) == [3, 2, 176, 144, 144, 4, 18, 16]
+    assert _conv_plan(1, 96, 12, 12, 768, 384)[:5] == [3, 2, 176, 144, 144]
+    assert _conv_plan(1, 96, 24, 24, 128, 128)[:5] == [3, 2, 208, 144, 144]
+    # ... but not when the layer needs several waves, has too few tiles, or the option is at level 1 / 0
+    assert _conv_plan(1, 640, 12, 12, 512, 512)[0] == 1
+    assert _conv_plan(1, 96, 12, 12, 256, 256)[:4] == [1, 2, 128, 108]
+    assert _conv_plan(1, 96, 12, 12, 384, 384, strip=1)[:4] == [2, 2, 128, 162]          # stream-K brick kernel
+    assert _conv_plan(1, 96, 12, 12, 384, 384, sms=132)[0] == 2                          # 144 tiles > 132 SMs
+    assert _conv_plan(1, 96, 96, 96, 128, 128, strip=0)[:4] == [1, 2, 128, 3456]
+    # the 6^2 level: 54 tiles of 128 x 256 for 148 SMs -> k-steps dealt evenly (stream-K), or whole tiles without it
+    assert _conv_plan(1, 96, 6, 6, 512, 512)[:5] == [2, 1, 256, 54, 148]
+    assert _conv_plan(1, 96, 6, 6, 512, 512, split_k=0)[0] == 1
+    # z-slab rank of the 640 x 192 x 192 volume on 8 GPUs: two 96-wide bands per plane
+    assert _conv_plan(1, 80, 192, 192, 128, 128)[:5] == [3, 1, 256, 11840, 148]
+    # not eligible: channel counts off the 64-element swizzle row, fp32
+    assert _conv_plan(1, 96, 12, 12, 100, 384)[0] == 0
+    assert _conv_plan(1, 96, 12, 12, 384, 384, dt=N.FP32)[0] == 0
