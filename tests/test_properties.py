@@ -99,3 +99,47 @@ def test_slab_bounds_partition(z, world):
     sizes = np.diff(b)
     assert b[0] == 0 and b[-1] == z and len(b) == world + 1 and sizes.min() >= 1 and sizes.max() - sizes.min() <= 1
     assert list(sizes) == sorted(sizes, reverse=True)   # the longer slabs come first
+
+
+@settings(max_examples=300, deadline=None)
+@given(B=st.integers(1, 2), Z=st.integers(1, 200), H=st.integers(2, 200), W=st.integers(2, 200),
+       cin=st.sampled_from([64, 128, 192, 256, 384, 512, 768]), cout=st.sampled_from([64, 128, 256, 384, 512]),
+       taps=st.sampled_from([27, 9, 1]), extra=st.sampled_from([0, 128, 640]), split_k=st.integers(0, 1),
+       strip=st.integers(0, 2), sms=st.sampled_from([148, 132, 80]))
+def test_conv_planner_invariants(B, Z, H, W, cin, cout, taps, extra, split_k, strip, sms):
+    """The conv planner (csrc/conv_tc.cu through ddpm3d_k_conv_plan; host arithmetic, no device) over arbitrary layer
+    shapes: every plan is launchable (tile counts, MMA N, TMA box and shared-memory limits) and the options gate what
+    they say they gate."""
+    import ctypes as C
+    from ddpm3d_b200 import _native as N
+    out = (C.c_int32 * 8)()
+    N.check(N.lib().ddpm3d_k_conv_plan(N.BF16, B, Z, H, W, cin, cout, taps, extra, split_k, strip, sms, out))
+    kind, a, b, tiles, grid, c, steps, rows = list(out)
+    assert kind in (1, 2, 3)                       # every channel count above is a multiple of 64: always eligible
+    assert tiles >= 1 and 1 <= grid <= sms
+    if kind == 3:                                  # strip kernel
+        NP, NV, NW = a, b, c
+        assert strip >= 1 and taps in (27, 9) and cout % 128 == 0
+        assert NP in (1, 2) and NV % 16 == 0 and 160 <= NV <= 256      # tcgen05 N for M = 128; N = 256 fills the accumulator
+        assert 3 <= NW <= 8 and rows <= 256                            # weight ring, TMA box extent
+        assert grid == min(tiles, sms)
+        if NP == 2:                                # plane pairs: level 2 only, one wave (no double-buffered accumulator)
+            assert strip == 2 and tiles <= sms
+        else:
+            assert tiles >= 2 * sms
+        # a tile covers NV consecutive positions of a padded band: the tiles of one (batch, plane group) cover it
+        per_plane_group = tiles // (B * -(-Z // NP) * (cout // 128))
+        assert per_plane_group * B * -(-Z // NP) * (cout // 128) == tiles
+        assert per_plane_group * NV >= H * W       # (bands x tiles per band) x NV >= the plane, pad columns aside
+        macro_main = (3 if taps == 27 else 1) * (cin // 64)
+        assert steps == macro_main + extra // 64
+    else:                                          # brick kernel
+        MT, BN = a, b
+        assert MT in (1, 2) and BN in (64, 128, 256) and cout % BN == 0 and MT * BN <= 256
+        assert steps == taps * (cin // 64) + extra // 64
+        if kind == 2:
+            assert split_k == 1 and grid == sms and c >= 2      # stream-K: every SM gets an equal share of the k-steps
+        else:
+            assert grid == min(tiles, sms)
+    if strip == 0:
+        assert kind != 3
