@@ -443,8 +443,8 @@ struct StripParams {
   int NV;            // voxels (padded-flattened positions) per tile = the MMA N: a multiple of 16, <= 256
   int NP, nZt;       // z-planes per tile (1, or 2 on small planes: both planes share every weight tile) and ceil(Z / NP).
                      // With NP = 2 the two plane accumulators fill the 512 TMEM columns: no double buffering
-  int NW;            // stages of the weight ring (3 .. STRIP_MAXW): as many as fit beside the two strips.  A stage lasts
-                     // 2 NV tensor cycles, so 4 stages of a 208-position tile cover ~1700 cycles -- less than a loaded L2 round trip
+  int NW;            // stages of the weight ring (3 .. min(STRIP_MAXW, ConvArgs::strip_maxw)) that fit beside the two strips.
+                     // Measured: 8 stages instead of 4 on the 48^2 / 24^2 layers change nothing (profiles/r4_ab_options.txt)
   int nsrc, chunks[3], n_macro_main, n_macro, Cin;
   int dz0;           // z offset of the first tap plane: -1 for 3x3x3, 0 for the 3x3 kernels of a dims = 2 network
   int taps;          // 27 or 9
