@@ -44,8 +44,8 @@ PATCHES_PER_VOLUME = 18    # scripts/test.py:205-230 tiling of a (110,200,200) v
 C2_CONFIG = {"workload": "C2: paper-default 3D UNet (128ch, 2 res blocks, mult 1-1-2-3-4), one 96x96x96 low-dose-conditioned "
                          "patch per GPU, one DDPM reverse step (UNet eval + posterior update) per bench step"}
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch, from the committed ncu capture
-DOMINANT_LAUNCH_DRAM_BYTES = 454000640 + 200749568
-DOMINANT_LAUNCH_PROFILE = "profiles/r2_conv_strip_ncu_full.txt"
+DOMINANT_LAUNCH_DRAM_BYTES = 453965824 + 198740480
+DOMINANT_LAUNCH_PROFILE = "profiles/r4h_ncu_full_table.txt (launch 6; the same layer in r2_conv_strip_ncu_full.txt: 454.0 + 200.7 MB)"
 C2_FLAGS = dict(
     large_size=96, small_size=96, class_cond=False, learn_sigma=True, num_channels=128, num_res_blocks=2,
     num_heads=4, num_head_channels=64, num_heads_upsample=-1, attention_resolutions="1000", dropout=0.0,
